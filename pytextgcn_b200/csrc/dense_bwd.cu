@@ -1,0 +1,351 @@
+// Dense part of the backward pass between the two SpMMs, one pass over the node rows:
+//   dW2       = H1d^T G2                 (H x C)   -- weight gradient of layer 2
+//   db_out    = colsum(dZ2)              (C)       -- bias gradient of layer 2
+//   dZ1       = (G2 W2^T) .* keep/(1-p) .* act'    -- gradient entering layer 1's propagation
+//   db_hidden = colsum(dZ1)              (H)       -- bias gradient of layer 1
+// Replaces the autograd of torch.matmul(x, weight), `out += bias` and F.dropout
+// (flat_amazon.py:105 through [PyG-1.6.3] GCNConv.forward and models.py:23).
+// Deterministic: per-CTA partial sums in a workspace, reduced in CTA order by a second kernel.
+//
+// The contraction is H x C <= 256 x 219 per row: far too thin for tensor cores, so it is
+// register-tiled FMA over shared-memory tiles of 32 rows.
+#include "common.cuh"
+
+namespace tgcn {
+
+constexpr int DB_ROWS = 32;       // rows per tile
+constexpr int DB_THREADS = 256;
+constexpr int DB_MAXNB = 4;       // 4x4 dW2 blocks per thread
+
+struct DenseBwdParams {
+  const float* __restrict__ G2; int64_t ldg2;
+  const void* __restrict__ H1d; int64_t ldh; int32_t h_dtype;
+  const float* __restrict__ W2;
+  const float* __restrict__ dZ2; int64_t lddz2;
+  int64_t n_rows; int64_t row_offset;
+  int32_t H, C;
+  int32_t act, drop_mode; float drop_p, drop_scale; const uint8_t* __restrict__ keep_mask; int64_t ldmask;
+  uint64_t philox_seed, philox_offset;
+  void* dZ1; int64_t lddz1; int32_t dz1_dtype;
+  // workspace partials
+  float* part_dW2;   // [n_cta_x][H*C]
+  float* part_dbh;   // [n_cta_x][H]
+  float* part_dbo;   // [n_cta_x][C]
+  int32_t cb_per_y;  // c-blocks (of 4 classes) handled per blockIdx.y
+  int32_t n_tiles;
+};
+
+__device__ __forceinline__ float load_h(const void* H1d, int h_dtype, int64_t idx) {
+  return h_dtype == TGCN_F32 ? reinterpret_cast<const float*>(H1d)[idx]
+                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(H1d)[idx]);
+}
+
+template <int KMAX>   // KMAX = ceil(H/32) upper bound
+__global__ void __launch_bounds__(DB_THREADS) k_dense_bwd(const DenseBwdParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, C = p.C;
+  const int Hp = (H + 3) & ~3, Cp = (C + 3) & ~3;
+  const int ldw = C | 1;                         // odd stride: conflict-free W2s[h][c] across lanes h
+  float* W2s = smem;                             // [H][ldw]
+  float* Hs = W2s + ((H * ldw + 3) & ~3);        // [DB_ROWS][Hp]
+  float* G2s = Hs + DB_ROWS * Hp;                // [DB_ROWS][Cp]   (row-major, for the dW2 outer products)
+  float* G2t = G2s + DB_ROWS * Cp;               // [Cp][DB_ROWS]   (transposed, for the dZ1 contraction)
+  float* red = G2t + Cp * DB_ROWS;               // [8][max(Hp, Cp)] cross-warp reduction scratch
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool do_rows = (blockIdx.y == 0);        // dZ1 / db are produced once, by the y == 0 slice
+
+  for (int i = tid; i < H * C; i += DB_THREADS) W2s[(i / C) * ldw + (i % C)] = p.W2[i];
+
+  // dW2 register tile: block id -> (hb, cb) with cb restricted to this y-slice
+  const int HB = Hp >> 2;
+  const int cb0 = blockIdx.y * p.cb_per_y;
+  const int CBl = min(p.cb_per_y, (Cp >> 2) - cb0);
+  const int n_blocks = HB * CBl;
+  float dw[DB_MAXNB][16];
+#pragma unroll
+  for (int b = 0; b < DB_MAXNB; ++b)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dw[b][i] = 0.0f;
+  float dbh[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) dbh[k] = 0.0f;
+  float dbo = 0.0f;   // thread c < C accumulates db_out[c]
+  __syncthreads();
+
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int64_t r0 = (int64_t)tile * DB_ROWS;
+    // ---- stage the tile ----
+    for (int i = tid; i < DB_ROWS * Hp; i += DB_THREADS) {
+      const int r = i / Hp, h = i - r * Hp;
+      const int64_t row = r0 + r;
+      Hs[i] = (row < p.n_rows && h < H) ? load_h(p.H1d, p.h_dtype, row * p.ldh + h) : 0.0f;
+    }
+    for (int i = tid; i < DB_ROWS * Cp; i += DB_THREADS) {
+      const int r = i / Cp, c = i - r * Cp;
+      const int64_t row = r0 + r;
+      const float g = (row < p.n_rows && c < C) ? p.G2[row * p.ldg2 + c] : 0.0f;
+      G2s[i] = g;
+      G2t[c * DB_ROWS + r] = g;
+    }
+    if (do_rows && p.dZ2 && tid < C) {
+      for (int r = 0; r < DB_ROWS; ++r) {
+        const int64_t row = r0 + r;
+        if (row < p.n_rows) dbo += p.dZ2[row * p.lddz2 + tid];
+      }
+    }
+    __syncthreads();
+
+    // ---- dW2 += Hs^T G2s  (4x4 register blocks) ----
+#pragma unroll
+    for (int b = 0; b < DB_MAXNB; ++b) {
+      const int blk = tid + b * DB_THREADS;
+      if (blk < n_blocks) {
+        const int hb = blk / CBl, cb = blk - hb * CBl + cb0;
+#pragma unroll 4
+        for (int r = 0; r < DB_ROWS; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(Hs + r * Hp + hb * 4);
+          const float4 g = *reinterpret_cast<const float4*>(G2s + r * Cp + cb * 4);
+          dw[b][0] = fmaf(a.x, g.x, dw[b][0]);  dw[b][1] = fmaf(a.x, g.y, dw[b][1]);
+          dw[b][2] = fmaf(a.x, g.z, dw[b][2]);  dw[b][3] = fmaf(a.x, g.w, dw[b][3]);
+          dw[b][4] = fmaf(a.y, g.x, dw[b][4]);  dw[b][5] = fmaf(a.y, g.y, dw[b][5]);
+          dw[b][6] = fmaf(a.y, g.z, dw[b][6]);  dw[b][7] = fmaf(a.y, g.w, dw[b][7]);
+          dw[b][8] = fmaf(a.z, g.x, dw[b][8]);  dw[b][9] = fmaf(a.z, g.y, dw[b][9]);
+          dw[b][10] = fmaf(a.z, g.z, dw[b][10]); dw[b][11] = fmaf(a.z, g.w, dw[b][11]);
+          dw[b][12] = fmaf(a.w, g.x, dw[b][12]); dw[b][13] = fmaf(a.w, g.y, dw[b][13]);
+          dw[b][14] = fmaf(a.w, g.z, dw[b][14]); dw[b][15] = fmaf(a.w, g.w, dw[b][15]);
+        }
+      }
+    }
+
+    // ---- dZ1 rows: warp `wid` owns rows 4*wid .. 4*wid+3, lane owns h = lane + 32k ----
+    if (do_rows && p.dZ1) {
+      float dz[4][KMAX];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) dz[q][k] = 0.0f;
+      const int rb = wid * 4;
+      for (int c = 0; c < C; ++c) {
+        const float4 g = *reinterpret_cast<const float4*>(G2t + c * DB_ROWS + rb);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int h = lane + 32 * k;
+          const float w = (h < H) ? W2s[h * ldw + c] : 0.0f;
+          dz[0][k] = fmaf(g.x, w, dz[0][k]); dz[1][k] = fmaf(g.y, w, dz[1][k]);
+          dz[2][k] = fmaf(g.z, w, dz[2][k]); dz[3][k] = fmaf(g.w, w, dz[3][k]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = rb + q;
+        const int64_t row = r0 + r;
+        if (row >= p.n_rows) continue;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int h = lane + 32 * k;
+          if (h >= H) continue;
+          float v = dz[q][k];
+          if (p.act == TGCN_ACT_RELU) {
+            // forward was dropout(relu(z)): the output is > 0 iff kept and z > 0
+            v = (Hs[r * Hp + h] > 0.0f) ? v * p.drop_scale : 0.0f;
+          } else if (p.drop_mode == TGCN_DROP_MASK) {
+            v = p.keep_mask[row * p.ldmask + h] ? v * p.drop_scale : 0.0f;
+          } else if (p.drop_mode == TGCN_DROP_PHILOX) {
+            const uint64_t e = (uint64_t)(row + p.row_offset) * (uint64_t)H + (uint64_t)h;
+            const uint4 rr = philox_quad(e >> 2, p.philox_seed, p.philox_offset);
+            const uint32_t bits = (e & 3) == 0 ? rr.x : (e & 3) == 1 ? rr.y : (e & 3) == 2 ? rr.z : rr.w;
+            v = (u01(bits) >= p.drop_p) ? v * p.drop_scale : 0.0f;
+          }
+          dbh[k] += v;
+          if (p.dz1_dtype == TGCN_F32) reinterpret_cast<float*>(p.dZ1)[row * p.lddz1 + h] = v;
+          else reinterpret_cast<__nv_bfloat16*>(p.dZ1)[row * p.lddz1 + h] = __float2bfloat16_rn(v);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- per-CTA partials ----
+  float* my_dw = p.part_dW2 + (int64_t)blockIdx.x * H * C;
+#pragma unroll
+  for (int b = 0; b < DB_MAXNB; ++b) {
+    const int blk = tid + b * DB_THREADS;
+    if (blk < n_blocks) {
+      const int hb = blk / CBl, cb = blk - hb * CBl + cb0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int h = hb * 4 + i, c = cb * 4 + j;
+          if (h < H && c < C) my_dw[h * C + c] = dw[b][i * 4 + j];
+        }
+    }
+  }
+  if (do_rows) {
+    // db_hidden: fixed-order sum over the 8 warps
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int h = lane + 32 * k;
+      if (h < H) red[wid * Hp + h] = dbh[k];
+    }
+    __syncthreads();
+    for (int h = tid; h < H; h += DB_THREADS) {
+      float s = 0.0f;
+      for (int w = 0; w < DB_THREADS / 32; ++w) s += red[w * Hp + h];
+      p.part_dbh[(int64_t)blockIdx.x * H + h] = s;
+    }
+    if (tid < C) p.part_dbo[(int64_t)blockIdx.x * C + tid] = dbo;
+  }
+}
+
+// out[i] = sum over CTAs (in CTA order) of part[cta][i]
+__global__ void k_reduce_partials(const float* __restrict__ part, int n_parts, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int c = 0; c < n_parts; ++c) s += part[(int64_t)c * n + i];
+  out[i] = s;
+}
+
+// thin projection P = X W, one warp per row, W staged in shared memory when it fits
+__global__ void __launch_bounds__(256) k_project(const void* __restrict__ X, int64_t ldx, int x_dtype, int64_t n_rows, int K,
+                                                 const float* __restrict__ W, int M, float* __restrict__ P, int64_t ldp,
+                                                 int w_in_smem) {
+  extern __shared__ __align__(16) float smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Kp = (K + 3) & ~3;
+  float* Ws = smem;
+  float* rowbuf = smem + (w_in_smem ? ((K * M + 3) & ~3) : 0) + wid * Kp;
+  if (w_in_smem) {
+    for (int i = threadIdx.x; i < K * M; i += blockDim.x) Ws[i] = W[i];
+  }
+  __syncthreads();
+  const float* Wp = w_in_smem ? Ws : W;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid; row < n_rows; row += warps) {
+    for (int k = lane; k < K; k += 32) rowbuf[k] = load_h(X, x_dtype, row * ldx + k);
+    __syncwarp();
+    for (int m = lane; m < M; m += 32) {
+      float s0 = 0.f, s1 = 0.f;
+      int k = 0;
+      for (; k + 1 < K; k += 2) {
+        s0 = fmaf(rowbuf[k], Wp[(int64_t)k * M + m], s0);
+        s1 = fmaf(rowbuf[k + 1], Wp[(int64_t)(k + 1) * M + m], s1);
+      }
+      if (k < K) s0 = fmaf(rowbuf[k], Wp[(int64_t)k * M + m], s0);
+      P[row * ldp + m] = s0 + s1;
+    }
+    __syncwarp();
+  }
+}
+
+struct DbLayout { size_t off_dw, off_dbh, off_dbo, total; int n_cta; };
+static DbLayout db_layout(int H, int C, int n_cta) {
+  DbLayout L; size_t off = 0;
+  L.n_cta = n_cta;
+  L.off_dw = off; off += align_up((size_t)n_cta * H * C * 4, 256);
+  L.off_dbh = off; off += align_up((size_t)n_cta * H * 4, 256);
+  L.off_dbo = off; off += align_up((size_t)n_cta * C * 4, 256);
+  L.total = off;
+  return L;
+}
+static int db_grid_x() { return sm_count(); }
+
+}  // namespace tgcn
+
+using namespace tgcn;
+
+extern "C" int tgcn_dense_bwd_workspace_bytes(int32_t H, int32_t C, size_t* bytes_out) {
+  TGCN_CHECK_ARG(bytes_out && H > 0 && C > 0, "dense_bwd_workspace_bytes: bad arguments");
+  *bytes_out = db_layout(H, C, db_grid_x()).total;
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TGCN_CHECK_ARG(a != nullptr, "dense_bwd: args null");
+  TGCN_CHECK_ARG(a->G2 && a->H1d && a->W2, "dense_bwd: input pointer null");
+  TGCN_CHECK_ARG(a->dW2 != nullptr, "dense_bwd: dW2 null");
+  TGCN_CHECK_ARG(a->n_rows > 0 && a->H > 0 && a->C > 0, "dense_bwd: bad shape");
+  TGCN_CHECK_ARG(a->H <= 512, "dense_bwd: hidden width %d > 512 not supported", a->H);
+  TGCN_CHECK_ARG(a->ldg2 >= a->C && a->ldh >= a->H, "dense_bwd: leading dimension too small");
+  TGCN_CHECK_ARG(a->dZ1 == nullptr || a->lddz1 >= a->H, "dense_bwd: lddz1 < H");
+  TGCN_CHECK_ARG(a->drop_mode != TGCN_DROP_MASK || a->act == TGCN_ACT_RELU || a->keep_mask || a->drop_p == 0.0f,
+                 "dense_bwd: TGCN_DROP_MASK needs keep_mask");
+  const int H = a->H, C = a->C;
+  const int n_tiles = (int)cdiv(a->n_rows, DB_ROWS);
+  const int gx = (int)std::min<int64_t>(db_grid_x(), n_tiles);
+  DbLayout L = db_layout(H, C, db_grid_x());
+  if (!workspace || workspace_bytes < L.total) {
+    set_error("dense_bwd workspace too small: need %zu bytes, got %zu", L.total, workspace_bytes);
+    return TGCN_EWORKSPACE;
+  }
+  DenseBwdParams p;
+  p.G2 = a->G2; p.ldg2 = a->ldg2; p.H1d = a->H1d; p.ldh = a->ldh; p.h_dtype = a->h_dtype;
+  p.W2 = a->W2; p.dZ2 = a->dZ2; p.lddz2 = a->lddz2;
+  p.n_rows = a->n_rows; p.row_offset = a->row_offset; p.H = H; p.C = C;
+  p.act = a->act;
+  p.drop_mode = (a->drop_mode != TGCN_DROP_NONE && a->drop_p > 0.0f) ? a->drop_mode : TGCN_DROP_NONE;
+  p.drop_p = a->drop_p; p.drop_scale = p.drop_mode == TGCN_DROP_NONE ? 1.0f : 1.0f / (1.0f - a->drop_p);
+  p.keep_mask = a->keep_mask; p.ldmask = a->ldmask;
+  p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset;
+  p.dZ1 = a->dZ1; p.lddz1 = a->lddz1; p.dz1_dtype = a->dz1_dtype;
+  p.part_dW2 = (float*)((char*)workspace + L.off_dw);
+  p.part_dbh = (float*)((char*)workspace + L.off_dbh);
+  p.part_dbo = (float*)((char*)workspace + L.off_dbo);
+  p.n_tiles = n_tiles;
+  const int Hp = (H + 3) & ~3, Cp = (C + 3) & ~3;
+  const int HB = Hp / 4, CB = Cp / 4;
+  int cb_per_y = std::max(1, (DB_THREADS * DB_MAXNB) / HB);
+  cb_per_y = std::min(cb_per_y, CB);
+  p.cb_per_y = cb_per_y;
+  const int gy = (CB + cb_per_y - 1) / cb_per_y;
+  const int ldw = C | 1;
+  size_t smem = ((size_t)((H * ldw + 3) & ~3) + (size_t)DB_ROWS * Hp + 2 * (size_t)DB_ROWS * Cp +
+                 (size_t)(DB_THREADS / 32) * std::max(Hp, Cp)) * sizeof(float);
+  TGCN_CHECK_ARG(smem <= 227 * 1024, "dense_bwd: H=%d C=%d needs %zu bytes of shared memory (> 227 KB)", H, C, smem);
+  const int kmax = (H + 31) / 32;
+  dim3 grid(gx, gy);
+#define TGCN_DB_LAUNCH(K)                                                                                       \
+  do {                                                                                                          \
+    if (smem > 48 * 1024)                                                                                       \
+      TGCN_CUDA(cudaFuncSetAttribute(k_dense_bwd<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    k_dense_bwd<K><<<grid, DB_THREADS, smem, stream>>>(p);                                                      \
+  } while (0)
+  if (kmax <= 1) TGCN_DB_LAUNCH(1);
+  else if (kmax <= 2) TGCN_DB_LAUNCH(2);
+  else if (kmax <= 4) TGCN_DB_LAUNCH(4);
+  else if (kmax <= 8) TGCN_DB_LAUNCH(8);
+  else TGCN_DB_LAUNCH(16);
+#undef TGCN_DB_LAUNCH
+  TGCN_LAUNCH_CHECK();
+  const int T = 256;
+  k_reduce_partials<<<(unsigned)cdiv((int64_t)H * C, T), T, 0, stream>>>(p.part_dW2, gx, (int64_t)H * C, a->dW2);
+  TGCN_LAUNCH_CHECK();
+  if (a->db_hidden) {
+    k_reduce_partials<<<(unsigned)cdiv(H, T), T, 0, stream>>>(p.part_dbh, gx, H, a->db_hidden);
+    TGCN_LAUNCH_CHECK();
+  }
+  if (a->db_out) {
+    TGCN_CHECK_ARG(a->dZ2 != nullptr, "dense_bwd: db_out needs dZ2");
+    k_reduce_partials<<<(unsigned)cdiv(C, T), T, 0, stream>>>(p.part_dbo, gx, C, a->db_out);
+    TGCN_LAUNCH_CHECK();
+  }
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_project(const void* X, int64_t ldx, int32_t x_dtype, int64_t n_rows, int32_t K,
+                            const float* W, int32_t M, float* P, int64_t ldp, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TGCN_CHECK_ARG(X && W && P, "project: null pointer");
+  TGCN_CHECK_ARG(n_rows > 0 && K > 0 && M > 0 && ldx >= K && ldp >= M, "project: bad shape");
+  const int threads = 256, wpb = threads / 32;
+  const int Kp = (K + 3) & ~3;
+  const int w_in_smem = ((size_t)K * M * 4 <= 96 * 1024) ? 1 : 0;
+  size_t smem = ((w_in_smem ? ((K * M + 3) & ~3) : 0) + (size_t)wpb * Kp) * sizeof(float);
+  if (smem > 48 * 1024) TGCN_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(cdiv(n_rows, wpb), (int64_t)sm_count() * 8);
+  k_project<<<grid, threads, smem, stream>>>(X, ldx, x_dtype, n_rows, K, W, M, P, ldp, w_in_smem);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}

@@ -1,0 +1,150 @@
+// Masked log-softmax / NLL (+ gradient, argmax, #correct) in one pass over the logits.
+// Replaces `criterion(gcn(g)[g.train_mask], g.y[g.train_mask])` with
+// CrossEntropyLoss(reduction='mean') and its backward (flat_amazon.py:82,101-102,105), and the
+// host-side argmax/accuracy of the eval half of the epoch (flat_amazon.py:111-114).
+// y is never read where mask == 0 (labels may be -1 there, perlabel_amazon.py:108-109).
+#include "common.cuh"
+
+namespace tgcn {
+
+// one warp per row
+__global__ void __launch_bounds__(256) k_masked_nll(const float* __restrict__ Z, int64_t ldz, int64_t n_rows, int C,
+                                                    const int64_t* __restrict__ y, const uint8_t* __restrict__ mask,
+                                                    float inv_n, float* __restrict__ dZ, int64_t lddz,
+                                                    int32_t* __restrict__ pred, float* __restrict__ row_nll,
+                                                    int32_t* __restrict__ row_hit) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const bool m = mask ? (mask[row] != 0) : true;
+  const bool need_fwd = m || pred;
+  const float* z = Z + row * ldz;
+  if (!need_fwd) {
+    if (dZ) for (int c = lane; c < C; c += 32) dZ[row * lddz + c] = 0.0f;
+    if (lane == 0) { row_nll[row] = 0.0f; if (row_hit) row_hit[row] = 0; }
+    return;
+  }
+  float mx = -INFINITY; int arg = 0;
+  for (int c = lane; c < C; c += 32) {
+    float v = z[c];
+    if (v > mx) { mx = v; arg = c; }
+  }
+  // warp argmax, lowest index wins ties (numpy argmax, flat_amazon.py:111)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+    int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
+  }
+  if (pred && lane == 0) pred[row] = arg;
+  if (!m) {
+    if (dZ) for (int c = lane; c < C; c += 32) dZ[row * lddz + c] = 0.0f;
+    if (lane == 0) { row_nll[row] = 0.0f; if (row_hit) row_hit[row] = 0; }
+    return;
+  }
+  float se = 0.0f;
+  for (int c = lane; c < C; c += 32) se += expf(z[c] - mx);
+  se = warp_sum(se);
+  const float lse = mx + logf(se);
+  const int64_t yi = y[row];
+  if (lane == 0) {
+    row_nll[row] = (yi >= 0 && yi < C) ? (lse - z[yi]) : 0.0f;
+    if (row_hit) row_hit[row] = (arg == (int)yi) ? 1 : 0;
+  }
+  if (dZ) {
+    for (int c = lane; c < C; c += 32) {
+      float pr = expf(z[c] - lse);
+      dZ[row * lddz + c] = (pr - (c == (int)yi ? 1.0f : 0.0f)) * inv_n;
+    }
+  }
+}
+
+// fixed-order reduction of the per-row terms (deterministic): one CTA, fp64 accumulators
+__global__ void __launch_bounds__(1024) k_nll_reduce(const float* __restrict__ row_nll, const int32_t* __restrict__ row_hit,
+                                                     const uint8_t* __restrict__ mask, int64_t n_rows, int64_t n_mask_total,
+                                                     float* __restrict__ loss_out, double* __restrict__ partial_out,
+                                                     int32_t* __restrict__ correct_out) {
+  __shared__ double s_sum[1024];
+  __shared__ int s_cnt[1024];
+  __shared__ int s_hit[1024];
+  double s = 0.0; int cnt = 0, hit = 0;
+  for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    s += (double)row_nll[r];
+    cnt += mask ? (mask[r] != 0) : 1;
+    if (row_hit) hit += row_hit[r];
+  }
+  s_sum[threadIdx.x] = s; s_cnt[threadIdx.x] = cnt; s_hit[threadIdx.x] = hit;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
+      s_hit[threadIdx.x] += s_hit[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = n_mask_total > 0 ? (double)n_mask_total : (double)s_cnt[0];
+    if (loss_out) { loss_out[0] = (float)(s_sum[0] / n); loss_out[1] = (float)s_cnt[0]; }
+    if (partial_out) { partial_out[0] = s_sum[0]; partial_out[1] = (double)s_cnt[0]; }
+    if (correct_out) correct_out[0] = s_hit[0];
+  }
+}
+
+__global__ void k_count_mask(const uint8_t* __restrict__ mask, int64_t n, int32_t* __restrict__ out) {
+  __shared__ int s[1024];
+  int c = 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) c += mask[i] != 0;
+  s[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = s[0];
+}
+
+}  // namespace tgcn
+
+using namespace tgcn;
+
+extern "C" int tgcn_masked_nll_workspace_bytes(int64_t n_rows, size_t* bytes_out) {
+  TGCN_CHECK_ARG(bytes_out != nullptr && n_rows >= 0, "masked_nll_workspace_bytes: bad arguments");
+  *bytes_out = align_up((size_t)n_rows * 4, 256) * 2;
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_masked_nll(const float* Z, int64_t ldz, int64_t n_rows, int32_t C,
+                               const int64_t* y, const uint8_t* mask, int64_t n_mask_total,
+                               float* loss_out, double* partial_out, float* dZ, int64_t lddz,
+                               int32_t* pred_out, int32_t* correct_out,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TGCN_CHECK_ARG(Z && y, "masked_nll: Z / y null");
+  TGCN_CHECK_ARG(n_rows > 0 && C > 0 && ldz >= C, "masked_nll: bad shape");
+  TGCN_CHECK_ARG(dZ == nullptr || lddz >= C, "masked_nll: lddz < C");
+  TGCN_CHECK_ARG(dZ == nullptr || n_mask_total > 0, "masked_nll: the gradient needs the global mask count (n_mask_total > 0)");
+  size_t need = align_up((size_t)n_rows * 4, 256) * 2;
+  if (!workspace || workspace_bytes < need) {
+    set_error("masked_nll workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    return TGCN_EWORKSPACE;
+  }
+  float* row_nll = (float*)workspace;
+  int32_t* row_hit = (int32_t*)((char*)workspace + align_up((size_t)n_rows * 4, 256));
+  const float inv_n = n_mask_total > 0 ? 1.0f / (float)n_mask_total : 0.0f;
+  const int T = 256;
+  k_masked_nll<<<(unsigned)cdiv(n_rows * 32, T), T, 0, stream>>>(Z, ldz, n_rows, C, y, mask, inv_n, dZ, lddz, pred_out, row_nll,
+                                                                  correct_out ? row_hit : nullptr);
+  TGCN_LAUNCH_CHECK();
+  k_nll_reduce<<<1, 1024, 0, stream>>>(row_nll, correct_out ? row_hit : nullptr, mask, n_rows, n_mask_total, loss_out,
+                                       partial_out, correct_out);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_count_mask(const uint8_t* mask, int64_t n, int32_t* count_out, void* stream_) {
+  TGCN_CHECK_ARG(mask && count_out && n >= 0, "count_mask: bad arguments");
+  k_count_mask<<<1, 1024, 0, (cudaStream_t)stream_>>>(mask, n, count_out);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}

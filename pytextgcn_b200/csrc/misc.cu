@@ -1,0 +1,254 @@
+// Error plumbing, device info, fused Adam/AMSGrad, the [I | F] hierarchy-feature kernels and
+// small utility kernels of the textgcn_b200 C ABI.
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+
+namespace tgcn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ---- Adam / AMSGrad (torch.optim.Adam semantics; flat_amazon.py:89,106) ----
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, float* __restrict__ vmax, int64_t n, float lr,
+                                              float b1, float b2, float eps, int amsgrad, int64_t step_host,
+                                              const int64_t* __restrict__ step_dev) {
+  __shared__ float s_hyp[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)(step_dev ? *step_dev : step_host);
+    const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
+    s_hyp[0] = (float)((double)lr / bc1);
+    s_hyp[1] = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_hyp[0], bc2s = s_hyp[1];
+  const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)(vmax ? vmax : p)) & 15) == 0);
+  int64_t start_tail = 0;
+  if (vec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 P = reinterpret_cast<float4*>(p)[i];
+      const float4 G = reinterpret_cast<const float4*>(g)[i];
+      float4 M = reinterpret_cast<float4*>(m)[i];
+      float4 V = reinterpret_cast<float4*>(v)[i];
+      float4 X = amsgrad ? reinterpret_cast<float4*>(vmax)[i] : make_float4(0, 0, 0, 0);
+      float* pp = &P.x; const float* gg = &G.x; float* mm = &M.x; float* vv = &V.x; float* xx = &X.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        mm[k] = mm[k] * b1 + omb1 * gg[k];
+        vv[k] = vv[k] * b2 + omb2 * (gg[k] * gg[k]);
+        float vh = vv[k];
+        if (amsgrad) { xx[k] = fmaxf(xx[k], vv[k]); vh = xx[k]; }
+        const float denom = sqrtf(vh) / bc2s + eps;
+        pp[k] = pp[k] - step_size * (mm[k] / denom);
+      }
+      reinterpret_cast<float4*>(p)[i] = P;
+      reinterpret_cast<float4*>(m)[i] = M;
+      reinterpret_cast<float4*>(v)[i] = V;
+      if (amsgrad) reinterpret_cast<float4*>(vmax)[i] = X;
+    }
+    start_tail = n4 << 2;
+  }
+  for (int64_t i = start_tail + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i];
+    const float mi = m[i] * b1 + omb1 * gi;
+    const float vi = v[i] * b2 + omb2 * (gi * gi);
+    float vh = vi;
+    if (amsgrad) { vh = fmaxf(vmax[i], vi); vmax[i] = vh; }
+    m[i] = mi; v[i] = vi;
+    p[i] = p[i] - step_size * (mi / (sqrtf(vh) / bc2s + eps));
+  }
+}
+
+__global__ void k_increment(int64_t* c) { *c += 1; }
+
+__global__ void k_cast_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// ---- X = [I | F]: XW = W1[:N] (+ F @ W1[N:] on document rows) ----  text2graph.py:237-241
+__global__ void __launch_bounds__(256) k_hier_forward(const float* __restrict__ W1, int64_t ldw, int64_t N, int64_t n_vocab,
+                                                      const float* __restrict__ Fd, int64_t ldf, int c_prev, int H,
+                                                      float* __restrict__ XW, int64_t ldxw) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* tail = W1 + N * ldw;
+  for (int h0 = 0; h0 < H; h0 += 32) {
+    const int h = h0 + lane;
+    float s = (h < H) ? W1[row * ldw + h] : 0.0f;
+    if (row >= n_vocab) {
+      const float* f = Fd + (row - n_vocab) * ldf;
+      for (int c = 0; c < c_prev; ++c) {
+        const float fc = f[c];                       // warp-uniform
+        if (fc != 0.0f && h < H) s = fmaf(fc, tail[(int64_t)c * ldw + h], s);
+      }
+    }
+    if (h < H) XW[row * ldxw + h] = s;
+  }
+}
+
+// dW1[N:, :] = F^T G1[docs]: each CTA owns a contiguous block of documents and keeps a private
+// (c_prev x H) accumulator in shared memory; partials are summed in CTA order afterwards.
+__global__ void __launch_bounds__(256) k_hier_backward(const float* __restrict__ G1, int64_t ldg, int64_t n_vocab, int64_t n_docs,
+                                                       const float* __restrict__ Fd, int64_t ldf, int c_prev, int H,
+                                                       float* __restrict__ part) {
+  extern __shared__ __align__(16) float smem[];
+  float* acc = smem;                         // [c_prev * H]
+  float* fval = acc + c_prev * H;            // [c_prev] compacted non-zero values of the current F row
+  int* fidx = reinterpret_cast<int*>(fval + c_prev);
+  __shared__ int s_nnz;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < c_prev * H; i += blockDim.x) acc[i] = 0.0f;
+  const int64_t per = (n_docs + gridDim.x - 1) / gridDim.x;
+  const int64_t d0 = (int64_t)blockIdx.x * per, d1 = min(n_docs, d0 + per);
+  __syncthreads();
+  for (int64_t d = d0; d < d1; ++d) {
+    if (tid < 32) {   // warp 0 compacts the non-zeros of F[d, :] in column order
+      int cnt = 0;
+      for (int c0 = 0; c0 < c_prev; c0 += 32) {
+        const int c = c0 + tid;
+        const float f = (c < c_prev) ? Fd[d * ldf + c] : 0.0f;
+        const unsigned b = __ballot_sync(0xffffffffu, f != 0.0f);
+        if (f != 0.0f) { const int pos = cnt + __popc(b & ((1u << tid) - 1)); fval[pos] = f; fidx[pos] = c; }
+        cnt += __popc(b);
+      }
+      if (tid == 0) s_nnz = cnt;
+    }
+    __syncthreads();
+    const int work = s_nnz * H;
+    const float* g = G1 + (n_vocab + d) * ldg;
+    for (int i = tid; i < work; i += blockDim.x) {
+      const int k = i / H, h = i - k * H;
+      acc[fidx[k] * H + h] = fmaf(fval[k], g[h], acc[fidx[k] * H + h]);
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < c_prev * H; i += blockDim.x) part[(int64_t)blockIdx.x * c_prev * H + i] = acc[i];
+}
+
+__global__ void k_reduce_parts(const float* __restrict__ part, int n_parts, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int c = 0; c < n_parts; ++c) s += part[(int64_t)c * n + i];
+  out[i] = s;
+}
+
+}  // namespace tgcn
+
+using namespace tgcn;
+
+extern "C" const char* tgcn_last_error(void) { return g_err; }
+extern "C" int tgcn_version(void) { return 100; }
+
+extern "C" int tgcn_device_info(int* sm, int* major, int* minor) {
+  int dev = 0;
+  TGCN_CUDA(cudaGetDevice(&dev));
+  int a = 0, b = 0, c = 0;
+  TGCN_CUDA(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev));
+  TGCN_CUDA(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev));
+  TGCN_CUDA(cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm) *sm = a;
+  if (major) *major = b;
+  if (minor) *minor = c;
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
+                              int64_t n, float lr, float beta1, float beta2, float eps, int32_t amsgrad,
+                              int64_t step, const int64_t* step_dev, void* stream_) {
+  TGCN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
+  TGCN_CHECK_ARG(!amsgrad || max_exp_avg_sq, "adam_step: amsgrad needs max_exp_avg_sq");
+  TGCN_CHECK_ARG(n >= 0, "adam_step: n < 0");
+  TGCN_CHECK_ARG(step_dev != nullptr || step >= 1, "adam_step: step must be >= 1");
+  if (n == 0) return TGCN_OK;
+  const int T = 256;
+  const int64_t blocks = std::min<int64_t>(cdiv(cdiv(n, 4), T), (int64_t)sm_count() * 8);
+  k_adam<<<(unsigned)std::max<int64_t>(blocks, 1), T, 0, (cudaStream_t)stream_>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr,
+                                                                                 beta1, beta2, eps, amsgrad, step, step_dev);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_increment_step(int64_t* step_dev, void* stream_) {
+  TGCN_CHECK_ARG(step_dev != nullptr, "increment_step: null pointer");
+  k_increment<<<1, 1, 0, (cudaStream_t)stream_>>>(step_dev);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream_) {
+  TGCN_CHECK_ARG(src && dst && n >= 0, "cast: bad arguments");
+  if (n == 0) return TGCN_OK;
+  const int T = 256;
+  const int64_t blocks = std::min<int64_t>(cdiv(n, T), (int64_t)sm_count() * 16);
+  k_cast_bf16<<<(unsigned)blocks, T, 0, (cudaStream_t)stream_>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_hier_forward(const float* W1, int64_t ldw, int64_t N, int64_t n_vocab, const float* Fdoc, int64_t ldf,
+                                 int32_t c_prev, int32_t H, float* XW, int64_t ldxw, void* stream_) {
+  TGCN_CHECK_ARG(W1 && XW && (c_prev == 0 || Fdoc), "hier_forward: null pointer");
+  TGCN_CHECK_ARG(N > 0 && n_vocab >= 0 && n_vocab <= N && H > 0 && c_prev >= 0, "hier_forward: bad shape");
+  TGCN_CHECK_ARG(ldw >= H && ldxw >= H && (c_prev == 0 || ldf >= c_prev), "hier_forward: leading dimension too small");
+  const int T = 256;
+  k_hier_forward<<<(unsigned)cdiv(N * 32, T), T, 0, (cudaStream_t)stream_>>>(W1, ldw, N, n_vocab, Fdoc, ldf, c_prev, H, XW, ldxw);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
+static int hier_grid(int64_t n_docs) { return (int)std::min<int64_t>(std::max<int64_t>(n_docs / 64, 1), (int64_t)sm_count() * 2); }
+
+extern "C" int tgcn_hier_backward_workspace_bytes(int32_t c_prev, int32_t H, size_t* bytes_out) {
+  TGCN_CHECK_ARG(bytes_out && c_prev > 0 && H > 0, "hier_backward_workspace_bytes: bad arguments");
+  *bytes_out = (size_t)sm_count() * 2 * c_prev * H * sizeof(float);
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_hier_backward(const float* G1, int64_t ldg, int64_t N, int64_t n_vocab, const float* Fdoc, int64_t ldf,
+                                  int32_t c_prev, int32_t H, float* dW_tail, void* workspace, size_t workspace_bytes,
+                                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TGCN_CHECK_ARG(G1 && Fdoc && dW_tail, "hier_backward: null pointer");
+  TGCN_CHECK_ARG(N > 0 && n_vocab >= 0 && n_vocab < N && H > 0 && c_prev > 0, "hier_backward: bad shape");
+  const int64_t n_docs = N - n_vocab;
+  const int grid = hier_grid(n_docs);
+  const size_t need = (size_t)grid * c_prev * H * sizeof(float);
+  if (!workspace || workspace_bytes < need) {
+    set_error("hier_backward workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    return TGCN_EWORKSPACE;
+  }
+  size_t smem = ((size_t)c_prev * H + 2 * (size_t)c_prev) * sizeof(float);
+  TGCN_CHECK_ARG(smem <= 227 * 1024, "hier_backward: c_prev*H too large for shared memory");
+  if (smem > 48 * 1024) TGCN_CUDA(cudaFuncSetAttribute(k_hier_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_hier_backward<<<grid, 256, smem, stream>>>(G1, ldg, n_vocab, n_docs, Fdoc, ldf, c_prev, H, (float*)workspace);
+  TGCN_LAUNCH_CHECK();
+  const int T = 256;
+  k_reduce_parts<<<(unsigned)cdiv((int64_t)c_prev * H, T), T, 0, stream>>>((const float*)workspace, grid, (int64_t)c_prev * H, dW_tail);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}

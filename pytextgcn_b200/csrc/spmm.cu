@@ -1,0 +1,453 @@
+// CSR SpMM with fused epilogue for the symmetric-normalised adjacency A_hat.
+//   C[r,:] = dropout(act( sum_k val[k] * B[colidx[k],:] + bias ))      (+ optional P = C @ W_proj)
+// Replaces GCNConv.propagate (index_select + mul + scatter_add with atomics) + bias add
+// (textgcn/lib/models.py:20, [PyG-1.6.3] message_passing.py) and F.dropout (models.py:23).
+// Also used for the backward pass (A_hat is symmetric for TextGCN graphs; in general the
+// caller passes the CSR of the transpose).
+//
+// Work decomposition: one warp per row CHUNK (tgcn_spmm_plan splits rows longer than
+// chunk_nnz, so hub word rows with 10^4+ neighbours do not serialise a warp).  Inside a warp
+// LPR lanes cover one gathered B row with 16-byte vector loads (VPL vectors per lane) and
+// 32/LPR non-zeros are processed side by side; the (col,val) stream is loaded coalesced, 32
+// entries per warp load, and broadcast by shuffle.  Split rows write fp32 partial rows to a
+// scratch buffer and a fix-up kernel adds them in slot order: deterministic, no atomics.
+#include "common.cuh"
+
+namespace tgcn {
+
+struct SpmmParams {
+  const int32_t* __restrict__ rowptr; const int32_t* __restrict__ colidx; const float* __restrict__ val;
+  const int4* __restrict__ chunks; int32_t n_chunks;
+  const int32_t* __restrict__ split_rows; int32_t n_split_rows;
+  float* scratch;
+  const void* __restrict__ B; int64_t ldb;
+  void* C; int64_t ldc; int32_t c_dtype;
+  int32_t F;
+  int64_t c_row_offset;
+  const float* __restrict__ bias; int32_t bias_len;
+  int32_t act;
+  int32_t drop_mode; float drop_p; float drop_scale; const uint8_t* __restrict__ keep_mask; int64_t ldmask;
+  uint64_t philox_seed; uint64_t philox_offset;
+  const float* __restrict__ W_proj; int32_t n_proj; float* P; int64_t ldp;
+  int32_t wproj_in_smem;
+};
+
+// ---- loads of 16 bytes of the dense operand -> 4 (fp32) or 8 (bf16) floats ----
+template <typename TB> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int E = 4;
+  __device__ __forceinline__ static void load(const float* p, float (&x)[4]) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+  }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int E = 8;
+  __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&x)[8]) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x[2 * i] = __uint_as_float(w[i] << 16);
+      x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+// Epilogue on one finished row held as: lane l (< LPR) owns elements
+// [ (l + v*LPR)*E , +E ) for v < VPL.  All 32 lanes call this (lanes >= LPR idle in the
+// element part but take part in the projection).
+template <int LPR, int VPL, int E>
+__device__ __forceinline__ void row_epilogue(const SpmmParams& p, int64_t row, int lane, float (&acc)[VPL][E],
+                                             float* smem_row, const float* smem_w) {
+  const int F = p.F;
+  const int64_t lrow = row - p.c_row_offset;
+  const bool need_proj = (p.P != nullptr);
+  if (lane < LPR) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c0 = (lane + v * LPR) * E;
+      if (c0 < F) {
+        float z[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) z[i] = acc[v][i];
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < E; ++i) if (c0 + i < p.bias_len) z[i] += __ldg(p.bias + c0 + i);
+        }
+        if (p.act == TGCN_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < E; ++i) z[i] = fmaxf(z[i], 0.0f);
+        }
+        if (p.drop_mode == TGCN_DROP_MASK) {
+          const uint8_t* m = p.keep_mask + lrow * p.ldmask + c0;
+#pragma unroll
+          for (int i = 0; i < E; ++i) z[i] = m[i] ? z[i] * p.drop_scale : 0.0f;
+        } else if (p.drop_mode == TGCN_DROP_PHILOX) {
+#pragma unroll
+          for (int q = 0; q < E / 4; ++q) {
+            uint64_t e4 = ((uint64_t)row * (uint64_t)F + (uint64_t)(c0 + 4 * q)) >> 2;
+            uint4 r = philox_quad(e4, p.philox_seed, p.philox_offset);
+            z[4 * q + 0] = (u01(r.x) >= p.drop_p) ? z[4 * q + 0] * p.drop_scale : 0.0f;
+            z[4 * q + 1] = (u01(r.y) >= p.drop_p) ? z[4 * q + 1] * p.drop_scale : 0.0f;
+            z[4 * q + 2] = (u01(r.z) >= p.drop_p) ? z[4 * q + 2] * p.drop_scale : 0.0f;
+            z[4 * q + 3] = (u01(r.w) >= p.drop_p) ? z[4 * q + 3] * p.drop_scale : 0.0f;
+          }
+        }
+        if (p.C) {
+          if (p.c_dtype == TGCN_F32) {
+            float* c = reinterpret_cast<float*>(p.C) + lrow * p.ldc + c0;
+#pragma unroll
+            for (int q = 0; q < E / 4; ++q)
+              *reinterpret_cast<float4*>(c + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+          } else {
+            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + lrow * p.ldc + c0;
+#pragma unroll
+            for (int q = 0; q < E / 2; ++q)
+              *reinterpret_cast<__nv_bfloat162*>(c + 2 * q) = __floats2bfloat162_rn(z[2 * q], z[2 * q + 1]);
+          }
+        }
+        if (need_proj) {
+#pragma unroll
+          for (int i = 0; i < E; ++i) {
+            float zi = z[i];
+            // the projection consumes exactly what the next layer would read back
+            if (p.C && p.c_dtype == TGCN_BF16) zi = __bfloat162float(__float2bfloat16_rn(zi));
+            smem_row[c0 + i] = zi;
+          }
+        }
+      }
+    }
+  }
+  if (need_proj) {
+    __syncwarp();
+    const float* W = p.wproj_in_smem ? smem_w : p.W_proj;
+    const int M = p.n_proj;
+    for (int m = lane; m < M; m += 32) {
+      float s0 = 0.f, s1 = 0.f;
+      int c = 0;
+      for (; c + 1 < F; c += 2) {
+        s0 = fmaf(smem_row[c], W[(int64_t)c * M + m], s0);
+        s1 = fmaf(smem_row[c + 1], W[(int64_t)(c + 1) * M + m], s1);
+      }
+      if (c < F) s0 = fmaf(smem_row[c], W[(int64_t)c * M + m], s0);
+      p.P[lrow * p.ldp + m] = s0 + s1;
+    }
+    __syncwarp();
+  }
+}
+
+template <typename TB, int LPR, int VPL>
+__global__ void __launch_bounds__(256) k_spmm(const SpmmParams p) {
+  constexpr int E = Vec<TB>::E;
+  constexpr int NZP = 32 / LPR;          // non-zeros processed side by side in a warp
+  constexpr int U = 4;                   // gathers kept in flight per lane group
+  extern __shared__ __align__(16) float smem[];
+  const int warps_per_block = blockDim.x >> 5;
+  const int wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float* smem_w = smem;                                   // [F * n_proj] when staged
+  float* smem_row = nullptr;
+  if (p.P) {
+    const int wfloats = p.wproj_in_smem ? ((p.F * p.n_proj + 3) & ~3) : 0;
+    smem_row = smem + wfloats + wib * ((p.F + 3) & ~3);
+    if (p.wproj_in_smem) {
+      for (int i = threadIdx.x; i < p.F * p.n_proj; i += blockDim.x) smem_w[i] = p.W_proj[i];
+    }
+    __syncthreads();
+  }
+  const int chunk_id = blockIdx.x * warps_per_block + wib;
+  if (chunk_id >= p.n_chunks) return;
+  const int4 ch = __ldg(p.chunks + chunk_id);   // {row, begin, end, slot}
+  const int sub = lane / LPR;                   // which of the NZP side-by-side non-zeros
+  const int l = lane % LPR;
+  const TB* __restrict__ B = reinterpret_cast<const TB*>(p.B);
+  const int F = p.F;
+
+  float acc[VPL][E];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int i = 0; i < E; ++i) acc[v][i] = 0.0f;
+
+  bool active[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) active[v] = ((l + v * LPR) * E) < F;
+
+  for (int base = ch.y; base < ch.z; base += 32) {
+    const int k = base + lane;
+    int mc = 0; float mv = 0.0f;
+    if (k < ch.z) { mc = __ldg(p.colidx + k); mv = __ldg(p.val + k); }
+    const int cnt = min(32, ch.z - base);
+    // NZP non-zeros per step, U steps in flight
+    for (int j = 0; j < cnt; j += NZP * U) {
+      int cc[U]; float vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int srcl = j + u * NZP + sub;         // may run past cnt: then mv == 0 and mc == 0 (row 0 is valid memory)
+        cc[u] = __shfl_sync(0xffffffffu, mc, srcl & 31);
+        vv[u] = __shfl_sync(0xffffffffu, mv, srcl & 31);
+        if (srcl >= cnt) vv[u] = 0.0f;
+      }
+      float x[U][VPL][E];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const TB* brow = B + (int64_t)cc[u] * p.ldb;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          if (active[v] && vv[u] != 0.0f) Vec<TB>::load(brow + (l + v * LPR) * E, x[u][v]);
+          else {
+#pragma unroll
+            for (int i = 0; i < E; ++i) x[u][v][i] = 0.0f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int i = 0; i < E; ++i) acc[v][i] = fmaf(vv[u], x[u][v][i], acc[v][i]);
+    }
+  }
+  // fold the NZP side-by-side partial rows into lanes [0, LPR)
+#pragma unroll
+  for (int o = 16; o >= LPR; o >>= 1)
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+      for (int i = 0; i < E; ++i) acc[v][i] += __shfl_down_sync(0xffffffffu, acc[v][i], o);
+
+  if (ch.w >= 0) {
+    // split row: raw fp32 partial, reduced by k_spmm_fixup
+    if (lane < LPR) {
+      float* s = p.scratch + (int64_t)ch.w * F;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int c0 = (l + v * LPR) * E;
+        if (c0 < F) {
+#pragma unroll
+          for (int q = 0; q < E / 4; ++q)
+            *reinterpret_cast<float4*>(s + c0 + 4 * q) = make_float4(acc[v][4 * q], acc[v][4 * q + 1], acc[v][4 * q + 2], acc[v][4 * q + 3]);
+        }
+      }
+    }
+    return;
+  }
+  row_epilogue<LPR, VPL, E>(p, ch.x, lane, acc, smem_row, smem_w);
+}
+
+// one warp per split row: add its partial rows in slot order, then the same epilogue
+template <int LPR, int VPL, int E>
+__global__ void __launch_bounds__(256) k_spmm_fixup(const SpmmParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int warps_per_block = blockDim.x >> 5;
+  const int wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float* smem_w = smem;
+  float* smem_row = nullptr;
+  if (p.P) {
+    const int wfloats = p.wproj_in_smem ? ((p.F * p.n_proj + 3) & ~3) : 0;
+    smem_row = smem + wfloats + wib * ((p.F + 3) & ~3);
+    if (p.wproj_in_smem) {
+      for (int i = threadIdx.x; i < p.F * p.n_proj; i += blockDim.x) smem_w[i] = p.W_proj[i];
+    }
+    __syncthreads();
+  }
+  const int sr = blockIdx.x * warps_per_block + wib;
+  if (sr >= p.n_split_rows) return;
+  const int row = p.split_rows[3 * sr], first = p.split_rows[3 * sr + 1], n = p.split_rows[3 * sr + 2];
+  const int F = p.F;
+  float acc[VPL][E];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int i = 0; i < E; ++i) acc[v][i] = 0.0f;
+  if (lane < LPR) {
+    for (int s = 0; s < n; ++s) {
+      const float* src = p.scratch + (int64_t)(first + s) * F;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int c0 = (lane + v * LPR) * E;
+        if (c0 < F) {
+#pragma unroll
+          for (int q = 0; q < E / 4; ++q) {
+            float4 t = *reinterpret_cast<const float4*>(src + c0 + 4 * q);
+            acc[v][4 * q] += t.x; acc[v][4 * q + 1] += t.y; acc[v][4 * q + 2] += t.z; acc[v][4 * q + 3] += t.w;
+          }
+        }
+      }
+    }
+  }
+  row_epilogue<LPR, VPL, E>(p, row, lane, acc, smem_row, smem_w);
+}
+
+// ---- spmm plan: chunk list ------------------------------------------------------------
+// Single CTA, three running prefix sums (chunks, partial slots, split rows) over the rows.
+__global__ void __launch_bounds__(1024) k_plan(const int32_t* __restrict__ rowptr, int64_t row_begin, int64_t row_end,
+                                               int32_t chunk_nnz, int4* __restrict__ chunks, int64_t cap,
+                                               int32_t* __restrict__ split_rows, int32_t* __restrict__ counts) {
+  __shared__ int s_warp[3][32];
+  __shared__ int s_base[3];
+  __shared__ int s_maxlen;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) { s_base[0] = s_base[1] = s_base[2] = 0; s_maxlen = 0; }
+  __syncthreads();
+  int my_max = 0;
+  for (int64_t r0 = row_begin; r0 < row_end; r0 += blockDim.x) {
+    const int64_t r = r0 + tid;
+    int len = 0, nch = 0, b = 0;
+    if (r < row_end) { b = rowptr[r]; len = rowptr[r + 1] - b; nch = max(1, (len + chunk_nnz - 1) / chunk_nnz); }
+    my_max = max(my_max, len);
+    int v[3] = {nch, nch > 1 ? nch : 0, nch > 1 ? 1 : 0};
+    int inc[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      int x = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      inc[q] = x;
+      if (lane == 31) s_warp[q][wid] = x;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        int x = (lane < (blockDim.x >> 5)) ? s_warp[q][lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        s_warp[q][lane] = x;   // inclusive over warps
+      }
+    }
+    __syncthreads();
+    int excl[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) excl[q] = s_base[q] + (wid ? s_warp[q][wid - 1] : 0) + inc[q] - v[q];
+    if (r < row_end) {
+      if (nch == 1) {
+        if (excl[0] < cap) chunks[excl[0]] = make_int4((int)r, b, b + len, -1);
+      } else {
+        // even split keeps the chunks of a hub row the same size
+        const int per = (len + nch - 1) / nch;
+        for (int c = 0; c < nch; ++c) {
+          const int cb = b + c * per, ce = min(b + len, cb + per);
+          if (excl[0] + c < cap) chunks[excl[0] + c] = make_int4((int)r, cb, ce, excl[1] + c);
+        }
+        split_rows[3 * excl[2]] = (int)r; split_rows[3 * excl[2] + 1] = excl[1]; split_rows[3 * excl[2] + 2] = nch;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int nw = blockDim.x >> 5;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) s_base[q] += s_warp[q][nw - 1];
+    }
+    __syncthreads();
+  }
+  atomicMax(&s_maxlen, my_max);
+  __syncthreads();
+  if (tid == 0) { counts[0] = s_base[0]; counts[1] = s_base[1]; counts[2] = s_base[2]; counts[3] = s_maxlen; }
+}
+
+template <typename TB, int LPR, int VPL>
+static int launch_spmm(const SpmmParams& p, cudaStream_t stream) {
+  constexpr int E = Vec<TB>::E;
+  const int threads = 256, wpb = threads / 32;
+  size_t smem = 0;
+  if (p.P) smem = ((p.wproj_in_smem ? ((p.F * p.n_proj + 3) & ~3) : 0) + wpb * ((p.F + 3) & ~3)) * sizeof(float);
+  if (smem > 48 * 1024) {
+    TGCN_CUDA(cudaFuncSetAttribute(k_spmm<TB, LPR, VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TGCN_CUDA(cudaFuncSetAttribute(k_spmm_fixup<LPR, VPL, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (p.n_chunks > 0) {
+    k_spmm<TB, LPR, VPL><<<(unsigned)cdiv(p.n_chunks, wpb), threads, smem, stream>>>(p);
+    TGCN_LAUNCH_CHECK();
+  }
+  if (p.n_split_rows > 0) {
+    k_spmm_fixup<LPR, VPL, E><<<(unsigned)cdiv(p.n_split_rows, wpb), threads, smem, stream>>>(p);
+    TGCN_LAUNCH_CHECK();
+  }
+  return TGCN_OK;
+}
+
+template <typename TB>
+static int dispatch_spmm(const SpmmParams& p, cudaStream_t stream) {
+  constexpr int E = Vec<TB>::E;
+  const int nvec = (p.F + E - 1) / E;   // 16-byte vectors per dense row
+  if (nvec <= 4) return launch_spmm<TB, 4, 1>(p, stream);
+  if (nvec <= 8) return launch_spmm<TB, 8, 1>(p, stream);
+  if (nvec <= 16) return launch_spmm<TB, 16, 1>(p, stream);
+  if (nvec <= 32) return launch_spmm<TB, 32, 1>(p, stream);
+  if (nvec <= 64) return launch_spmm<TB, 32, 2>(p, stream);
+  if (nvec <= 128) return launch_spmm<TB, 32, 4>(p, stream);
+  set_error("spmm: feature width %d too large (max %d)", p.F, 128 * E);
+  return TGCN_EINVAL;
+}
+
+}  // namespace tgcn
+
+using namespace tgcn;
+
+extern "C" int tgcn_spmm_plan_workspace_bytes(int64_t n_rows, size_t* bytes_out) {
+  TGCN_CHECK_ARG(bytes_out != nullptr, "bytes_out is null");
+  (void)n_rows;
+  *bytes_out = 0;   // the plan kernel keeps its running sums in shared memory
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_spmm_plan(const int32_t* rowptr, int64_t row_begin, int64_t row_end, int32_t chunk_nnz,
+                              int32_t* chunks, int64_t chunk_capacity, int32_t* split_rows, int32_t* counts_out,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+  (void)workspace; (void)workspace_bytes;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TGCN_CHECK_ARG(rowptr && chunks && split_rows && counts_out, "spmm_plan: null pointer");
+  TGCN_CHECK_ARG(row_begin >= 0 && row_end >= row_begin, "spmm_plan: bad row range");
+  TGCN_CHECK_ARG(chunk_nnz >= 32, "spmm_plan: chunk_nnz must be >= 32");
+  k_plan<<<1, 1024, 0, stream>>>(rowptr, row_begin, row_end, chunk_nnz, reinterpret_cast<int4*>(chunks), chunk_capacity,
+                                 split_rows, counts_out);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_spmm(const tgcn_spmm_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TGCN_CHECK_ARG(a != nullptr, "spmm: args null");
+  TGCN_CHECK_ARG(a->rowptr && a->colidx && a->val && a->chunks, "spmm: CSR/plan pointer null");
+  TGCN_CHECK_ARG(a->B != nullptr, "spmm: B null");
+  TGCN_CHECK_ARG(a->C != nullptr || a->P != nullptr, "spmm: no output requested");
+  TGCN_CHECK_ARG(a->F > 0, "spmm: F must be > 0");
+  TGCN_CHECK_ARG(a->b_dtype == TGCN_F32 || a->b_dtype == TGCN_BF16, "spmm: bad b_dtype");
+  TGCN_CHECK_ARG(a->c_dtype == TGCN_F32 || a->c_dtype == TGCN_BF16, "spmm: bad c_dtype");
+  const int eb = a->b_dtype == TGCN_F32 ? 4 : 8;
+  TGCN_CHECK_ARG(a->F % eb == 0, "spmm: F (%d) must be a multiple of %d for this dtype (pad the operand)", a->F, eb);
+  TGCN_CHECK_ARG(a->ldb % eb == 0 && ((uintptr_t)a->B % 16) == 0, "spmm: B must be 16-byte aligned with ldb %% %d == 0", eb);
+  if (a->C) {
+    const int ec = a->c_dtype == TGCN_F32 ? 4 : 2;
+    TGCN_CHECK_ARG(a->ldc % ec == 0 && ((uintptr_t)a->C % 16) == 0, "spmm: C must be 16-byte aligned with ldc %% %d == 0", ec);
+    TGCN_CHECK_ARG(a->ldc >= a->F, "spmm: ldc < F");
+  }
+  TGCN_CHECK_ARG(a->n_split_rows == 0 || (a->split_rows && a->scratch), "spmm: split rows need split_rows and scratch");
+  TGCN_CHECK_ARG(a->drop_mode >= TGCN_DROP_NONE && a->drop_mode <= TGCN_DROP_PHILOX, "spmm: bad drop_mode");
+  TGCN_CHECK_ARG(a->drop_mode == TGCN_DROP_NONE || (a->drop_p >= 0.0f && a->drop_p < 1.0f), "spmm: dropout p must be in [0,1)");
+  TGCN_CHECK_ARG(a->drop_mode != TGCN_DROP_MASK || a->keep_mask, "spmm: TGCN_DROP_MASK needs keep_mask");
+  TGCN_CHECK_ARG(a->act == TGCN_ACT_NONE || a->act == TGCN_ACT_RELU, "spmm: bad act");
+  TGCN_CHECK_ARG(a->P == nullptr || (a->W_proj && a->n_proj > 0 && a->ldp >= a->n_proj), "spmm: bad projection arguments");
+
+  SpmmParams p;
+  p.rowptr = a->rowptr; p.colidx = a->colidx; p.val = a->val;
+  p.chunks = reinterpret_cast<const int4*>(a->chunks); p.n_chunks = a->n_chunks;
+  p.split_rows = a->split_rows; p.n_split_rows = a->n_split_rows;
+  p.scratch = a->scratch;
+  p.B = a->B; p.ldb = a->ldb;
+  p.C = a->C; p.ldc = a->ldc; p.c_dtype = a->c_dtype;
+  p.F = a->F; p.c_row_offset = a->c_row_offset;
+  p.bias = a->bias; p.bias_len = (a->bias_len > 0 && a->bias_len <= a->F) ? a->bias_len : a->F; p.act = a->act;
+  p.drop_mode = (a->drop_mode != TGCN_DROP_NONE && a->drop_p > 0.0f) ? a->drop_mode : TGCN_DROP_NONE;
+  p.drop_p = a->drop_p; p.drop_scale = 1.0f / (1.0f - a->drop_p);
+  p.keep_mask = a->keep_mask; p.ldmask = a->ldmask;
+  p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset;
+  p.W_proj = a->W_proj; p.n_proj = a->n_proj; p.P = a->P; p.ldp = a->ldp;
+  p.wproj_in_smem = (p.P && (size_t)p.F * p.n_proj * sizeof(float) <= 96 * 1024) ? 1 : 0;
+  if (a->b_dtype == TGCN_F32) return dispatch_spmm<float>(p, stream);
+  return dispatch_spmm<__nv_bfloat16>(p, stream);
+}

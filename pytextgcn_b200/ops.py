@@ -1,0 +1,276 @@
+"""Thin Python wrappers over the C ABI (one function per entry point of
+include/textgcn_b200.h).  All tensors must be CUDA tensors; nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native
+from .graph import GraphCSR, SpmmPlan
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU = 0, 1
+DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"unsupported dtype {t.dtype} (fp32 or bf16 only)")
+
+
+def _need_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pytextgcn_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def pad4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+def pad8(n: int) -> int:
+    return (n + 7) & ~7
+
+
+def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Optional[torch.Tensor] = None,
+         out_dtype: Optional[torch.dtype] = None, plan: Optional[SpmmPlan] = None,
+         bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         drop_mode: int = DROP_NONE, drop_p: float = 0.0, keep_mask: Optional[torch.Tensor] = None,
+         philox_seed: int = 0, philox_offset: int = 0,
+         W_proj: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
+         want_out: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """C = epi(A_hat[rows of plan] @ B[:, :F]) (+ P = C @ W_proj).  See tgcn_spmm.
+
+    B: [>= n_nodes, >= F] fp32/bf16, row stride a multiple of 4 (fp32) / 8 (bf16) elements.
+    Returns (C or None, P or None).  C has plan.row_end - plan.row_begin rows.
+    """
+    _need_cuda(B, out, bias, keep_mask, W_proj, P)
+    lib = _native.load()
+    plan = plan or graph.plan()
+    F = int(B.shape[1]) if F is None else int(F)
+    n_out = plan.row_end - plan.row_begin
+    if B.dim() != 2 or B.stride(1) != 1:
+        raise RuntimeError("spmm: B must be a 2-D row-major tensor")
+    if B.shape[0] < graph.n_nodes:
+        raise RuntimeError(f"spmm: B has {B.shape[0]} rows, the graph has {graph.n_nodes} nodes")
+    a = _native.SpmmArgs()
+    a.rowptr, a.colidx, a.val = graph.rowptr.data_ptr(), graph.colidx.data_ptr(), graph.val.data_ptr()
+    a.chunks, a.n_chunks = plan.chunks.data_ptr(), plan.n_chunks
+    a.split_rows, a.n_split_rows = (plan.split_rows.data_ptr() if plan.n_split_rows else None), plan.n_split_rows
+    scratch = plan.scratch(F)
+    a.scratch = _native.ptr(scratch)
+    a.B, a.ldb, a.b_dtype = B.data_ptr(), B.stride(0), _dt(B)
+    if want_out:
+        if out is None:
+            out = torch.empty((n_out, F), dtype=out_dtype or torch.float32, device=B.device)
+        if out.stride(1) != 1 or out.shape[0] < n_out or out.shape[1] < F:
+            raise RuntimeError("spmm: bad `out` tensor")
+        a.C, a.ldc, a.c_dtype = out.data_ptr(), out.stride(0), _dt(out)
+    else:
+        out = None
+        a.C, a.ldc, a.c_dtype = None, 0, F32
+    a.F = F
+    a.c_row_offset = plan.row_begin
+    a.bias = _native.ptr(bias)
+    a.bias_len = int(bias.numel()) if bias is not None else 0
+    a.act = act
+    a.drop_mode, a.drop_p = drop_mode, float(drop_p)
+    if keep_mask is not None:
+        if keep_mask.dtype not in (torch.uint8, torch.bool) or keep_mask.stride(1) != 1:
+            raise RuntimeError("spmm: keep_mask must be a row-major uint8/bool tensor")
+        a.keep_mask, a.ldmask = keep_mask.data_ptr(), keep_mask.stride(0)
+    a.philox_seed, a.philox_offset = philox_seed & (2**64 - 1), philox_offset & (2**64 - 1)
+    if W_proj is not None:
+        if W_proj.dtype != torch.float32 or not W_proj.is_contiguous() or W_proj.shape[0] != F:
+            raise RuntimeError("spmm: W_proj must be a contiguous fp32 [F, n_proj] tensor")
+        n_proj = int(W_proj.shape[1])
+        if P is None:
+            P = torch.zeros((n_out, pad4(n_proj)), dtype=torch.float32, device=B.device)
+        a.W_proj, a.n_proj, a.P, a.ldp = W_proj.data_ptr(), n_proj, P.data_ptr(), P.stride(0)
+    with torch.cuda.device(B.device):
+        _native.check(lib.tgcn_spmm(C.byref(a), _stream()))
+    return out, P
+
+
+def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[torch.Tensor], n_mask_total: int,
+               *, want_grad: bool = True, dZ: Optional[torch.Tensor] = None, want_pred: bool = False,
+               want_correct: bool = False, loss_out: Optional[torch.Tensor] = None,
+               workspace: Optional[torch.Tensor] = None):
+    """Masked mean cross-entropy over rows of Z (+ gradient / argmax / #correct).  See tgcn_masked_nll.
+    Returns dict(loss=[2] fp32 (mean nll, count), dZ, pred, correct, partial)."""
+    _need_cuda(Z, y, mask, dZ)
+    lib = _native.load()
+    n = int(Z.shape[0])
+    if Z.dtype != torch.float32 or Z.stride(1) != 1:
+        raise RuntimeError("masked_nll: Z must be a row-major fp32 tensor")
+    if y.dtype != torch.int64 or not y.is_contiguous():
+        raise RuntimeError("masked_nll: y must be a contiguous int64 tensor")
+    if mask is not None and (mask.dtype not in (torch.bool, torch.uint8) or not mask.is_contiguous()):
+        raise RuntimeError("masked_nll: mask must be a contiguous bool/uint8 tensor")
+    dev = Z.device
+    if loss_out is None:
+        loss_out = torch.empty(2, dtype=torch.float32, device=dev)
+    partial = torch.empty(2, dtype=torch.float64, device=dev)
+    if want_grad and dZ is None:
+        dZ = torch.zeros((n, pad4(n_classes)), dtype=torch.float32, device=dev)
+    pred = torch.empty(n, dtype=torch.int32, device=dev) if want_pred else None
+    correct = torch.zeros(1, dtype=torch.int32, device=dev) if want_correct else None
+    need = C.c_size_t(0)
+    _native.check(lib.tgcn_masked_nll_workspace_bytes(n, C.byref(need)))
+    if workspace is None or workspace.numel() < need.value:
+        workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(lib.tgcn_masked_nll(Z.data_ptr(), Z.stride(0), n, n_classes, y.data_ptr(), _native.ptr(mask),
+                                          int(n_mask_total), loss_out.data_ptr(), partial.data_ptr(),
+                                          _native.ptr(dZ) if want_grad else None, dZ.stride(0) if want_grad else 0,
+                                          _native.ptr(pred), _native.ptr(correct),
+                                          workspace.data_ptr(), workspace.numel(), _stream()))
+    return dict(loss=loss_out, dZ=dZ if want_grad else None, pred=pred, correct=correct, partial=partial)
+
+
+def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Optional[torch.Tensor], *,
+              H: int, n_classes: int, act: int = ACT_NONE, drop_mode: int = DROP_NONE, drop_p: float = 0.0,
+              keep_mask: Optional[torch.Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,
+              row_offset: int = 0, dZ1: Optional[torch.Tensor] = None, dz1_dtype: torch.dtype = torch.float32,
+              want_dz1: bool = True, workspace: Optional[torch.Tensor] = None,
+              dW2: Optional[torch.Tensor] = None, db_hidden: Optional[torch.Tensor] = None,
+              db_out: Optional[torch.Tensor] = None):
+    """dW2 = H1d^T G2, db_out = colsum(dZ2), dZ1 = (G2 W2^T) * dropout' * act', db_hidden = colsum(dZ1)."""
+    _need_cuda(G2, H1d, W2, dZ2, keep_mask, dZ1)
+    lib = _native.load()
+    dev = G2.device
+    n = int(G2.shape[0])
+    if W2.dtype != torch.float32 or not W2.is_contiguous() or tuple(W2.shape) != (H, n_classes):
+        raise RuntimeError("dense_bwd: W2 must be a contiguous fp32 [H, C] tensor")
+    a = _native.DenseBwdArgs()
+    a.G2, a.ldg2 = G2.data_ptr(), G2.stride(0)
+    a.H1d, a.ldh, a.h_dtype = H1d.data_ptr(), H1d.stride(0), _dt(H1d)
+    a.W2 = W2.data_ptr()
+    a.dZ2, a.lddz2 = (_native.ptr(dZ2), dZ2.stride(0)) if dZ2 is not None else (None, 0)
+    a.n_rows, a.row_offset = n, row_offset
+    a.H, a.C = H, n_classes
+    a.act, a.drop_mode, a.drop_p = act, drop_mode, float(drop_p)
+    if keep_mask is not None:
+        a.keep_mask, a.ldmask = keep_mask.data_ptr(), keep_mask.stride(0)
+    a.philox_seed, a.philox_offset = philox_seed & (2**64 - 1), philox_offset & (2**64 - 1)
+    if want_dz1:
+        if dZ1 is None:
+            width = pad4(H) if dz1_dtype == torch.float32 else pad8(H)
+            dZ1 = torch.zeros((n, width), dtype=dz1_dtype, device=dev)
+        a.dZ1, a.lddz1, a.dz1_dtype = dZ1.data_ptr(), dZ1.stride(0), _dt(dZ1)
+    if dW2 is None:
+        dW2 = torch.empty((H, n_classes), dtype=torch.float32, device=dev)
+    if db_hidden is None and want_dz1:
+        db_hidden = torch.empty(H, dtype=torch.float32, device=dev)
+    if db_out is None and dZ2 is not None:
+        db_out = torch.empty(n_classes, dtype=torch.float32, device=dev)
+    a.dW2, a.db_hidden, a.db_out = dW2.data_ptr(), _native.ptr(db_hidden), _native.ptr(db_out)
+    need = C.c_size_t(0)
+    with torch.cuda.device(dev):
+        _native.check(lib.tgcn_dense_bwd_workspace_bytes(H, n_classes, C.byref(need)))
+        if workspace is None or workspace.numel() < need.value:
+            workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        _native.check(lib.tgcn_dense_bwd(C.byref(a), workspace.data_ptr(), workspace.numel(), _stream()))
+    return dict(dW2=dW2, db_hidden=db_hidden, db_out=db_out, dZ1=dZ1 if want_dz1 else None, workspace=workspace)
+
+
+def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """P = X[:, :K] @ W (thin hidden->classes projection), P padded to a multiple of 4 columns."""
+    _need_cuda(X, W, out)
+    lib = _native.load()
+    K = int(W.shape[0]) if K is None else K
+    M = int(W.shape[1])
+    n = int(X.shape[0])
+    if W.dtype != torch.float32 or not W.is_contiguous():
+        raise RuntimeError("project: W must be contiguous fp32")
+    if out is None:
+        out = torch.zeros((n, pad4(M)), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        _native.check(lib.tgcn_project(X.data_ptr(), X.stride(0), _dt(X), n, K, W.data_ptr(), M,
+                                       out.data_ptr(), out.stride(0), _stream()))
+    return out
+
+
+def hier_forward(W1: torch.Tensor, n_nodes: int, n_vocab: int, Fdoc: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """XW = [I | F] @ W1 for X with hierarchy features on the document rows (text2graph.py:237-241)."""
+    _need_cuda(W1, Fdoc, out)
+    lib = _native.load()
+    H = int(W1.shape[1])
+    c_prev = int(Fdoc.shape[1])
+    if W1.shape[0] != n_nodes + c_prev:
+        raise RuntimeError(f"hier_forward: W1 has {W1.shape[0]} rows, expected n_nodes + c_prev = {n_nodes + c_prev}")
+    if out is None:
+        out = torch.zeros((n_nodes, pad4(H)), dtype=torch.float32, device=W1.device)
+    with torch.cuda.device(W1.device):
+        _native.check(lib.tgcn_hier_forward(W1.data_ptr(), W1.stride(0), n_nodes, n_vocab, Fdoc.data_ptr(), Fdoc.stride(0),
+                                            c_prev, H, out.data_ptr(), out.stride(0), _stream()))
+    return out
+
+
+def hier_backward(G1: torch.Tensor, n_nodes: int, n_vocab: int, Fdoc: torch.Tensor, H: int, dW_tail: torch.Tensor):
+    """dW1[N:, :] = F^T G1[doc rows]."""
+    _need_cuda(G1, Fdoc, dW_tail)
+    lib = _native.load()
+    c_prev = int(Fdoc.shape[1])
+    need = C.c_size_t(0)
+    with torch.cuda.device(G1.device):
+        _native.check(lib.tgcn_hier_backward_workspace_bytes(c_prev, H, C.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=G1.device)
+        if not dW_tail.is_contiguous():
+            raise RuntimeError("hier_backward: dW_tail must be contiguous")
+        _native.check(lib.tgcn_hier_backward(G1.data_ptr(), G1.stride(0), n_nodes, n_vocab, Fdoc.data_ptr(), Fdoc.stride(0),
+                                             c_prev, H, dW_tail.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return dW_tail
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+              max_exp_avg_sq: Optional[torch.Tensor], *, lr: float, beta1: float = 0.9, beta2: float = 0.999,
+              eps: float = 1e-8, amsgrad: bool = False, step: int = 0, step_dev: Optional[torch.Tensor] = None) -> None:
+    """In-place fused Adam/AMSGrad update (torch.optim.Adam semantics, flat_amazon.py:89,106)."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, step_dev)
+    lib = _native.load()
+    for t in (param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise RuntimeError("adam_step: tensors must be contiguous fp32")
+    with torch.cuda.device(param.device):
+        _native.check(lib.tgcn_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                         _native.ptr(max_exp_avg_sq), param.numel(), lr, beta1, beta2, eps,
+                                         1 if amsgrad else 0, int(step), _native.ptr(step_dev), _stream()))
+
+
+def increment_step(step_dev: torch.Tensor) -> None:
+    lib = _native.load()
+    with torch.cuda.device(step_dev.device):
+        _native.check(lib.tgcn_increment_step(step_dev.data_ptr(), _stream()))
+
+
+def count_mask(mask: torch.Tensor) -> torch.Tensor:
+    _need_cuda(mask)
+    lib = _native.load()
+    out = torch.empty(1, dtype=torch.int32, device=mask.device)
+    with torch.cuda.device(mask.device):
+        _native.check(lib.tgcn_count_mask(mask.data_ptr(), mask.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(src, out)
+    lib = _native.load()
+    if not src.is_contiguous() or src.dtype != torch.float32:
+        raise RuntimeError("cast_bf16: src must be contiguous fp32")
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        _native.check(lib.tgcn_cast_f32_to_bf16(src.data_ptr(), out.data_ptr(), src.numel(), _stream()))
+    return out
