@@ -99,7 +99,8 @@ class GraphCSR:
     def is_symmetric(self) -> bool:
         """A_hat == A_hat^T (true for Text2GraphTransformer graphs: PMI and TF-IDF edges are
         emitted in both directions with equal weights, text2graph.py:148-170).  Checked once, on
-        the device, by comparing the sorted (row, col, value-bits) triples of A_hat and A_hat^T."""
+        the device, by comparing the sorted (row, col, value) triples of A_hat and A_hat^T (values to
+        within 1e-6 relative: the two multiplication orders may round differently in the last bit)."""
         if self._symmetric is None:
             rows = self.row_ids()
             cols = self.colidx.to(torch.int64)
@@ -109,7 +110,11 @@ class GraphCSR:
             o1 = torch.argsort(k1)
             o2 = torch.argsort(k2)
             same_pattern = bool(torch.equal(k1[o1], k2[o2]))
-            same_vals = same_pattern and bool(torch.equal(self.val[o1].view(torch.int32), self.val[o2].view(torch.int32)))
+            same_vals = False
+            if same_pattern:
+                # (dis[j]*w)*dis[i] and (dis[i]*w)*dis[j] may differ in the last bit: compare to a few ulp
+                a, b = self.val[o1], self.val[o2]
+                same_vals = bool(((a - b).abs() <= 1e-6 * torch.maximum(a.abs(), b.abs())).all())
             self._symmetric = same_vals
         return self._symmetric
 
