@@ -50,6 +50,8 @@ extern "C" {
 
 const char* tgcn_last_error(void);
 int tgcn_version(void);
+/* number of kernels this library has launched (or captured into a CUDA graph) so far in this process */
+uint64_t tgcn_launch_count(void);
 /* number of SMs / compute capability of the current device (host sync; used by the host to size grids) */
 int tgcn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -117,6 +119,7 @@ typedef struct {
   int32_t act;
   int32_t drop_mode; float drop_p; const uint8_t* keep_mask; int64_t ldmask;
   uint64_t philox_seed; uint64_t philox_offset;
+  const int64_t* philox_offset_dev;   /* optional device counter added to philox_offset (CUDA-graph replays) */
   const float* W_proj; int32_t n_proj; float* P; int64_t ldp;       /* optional projection */
 } tgcn_spmm_args;
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
@@ -153,7 +156,7 @@ typedef struct {
   int64_t n_rows; int64_t row_offset;   /* global row id of local row 0 (Philox index) */
   int32_t H; int32_t C;
   int32_t act; int32_t drop_mode; float drop_p; const uint8_t* keep_mask; int64_t ldmask;
-  uint64_t philox_seed; uint64_t philox_offset;
+  uint64_t philox_seed; uint64_t philox_offset; const int64_t* philox_offset_dev;
   void* dZ1; int64_t lddz1; int32_t dz1_dtype;      /* out [n_rows, H] */
   float* dW2; float* db_hidden; float* db_out;      /* out [H*C], [H], [C] */
 } tgcn_dense_bwd_args;

@@ -31,7 +31,7 @@ class SpmmArgs(C.Structure):
         ("bias", c_void), ("bias_len", C.c_int32),
         ("act", C.c_int32),
         ("drop_mode", C.c_int32), ("drop_p", C.c_float), ("keep_mask", c_void), ("ldmask", C.c_int64),
-        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_offset_dev", c_void),
         ("W_proj", c_void), ("n_proj", C.c_int32), ("P", c_void), ("ldp", C.c_int64),
     ]
 
@@ -47,7 +47,7 @@ class DenseBwdArgs(C.Structure):
         ("H", C.c_int32), ("C", C.c_int32),
         ("act", C.c_int32), ("drop_mode", C.c_int32), ("drop_p", C.c_float),
         ("keep_mask", c_void), ("ldmask", C.c_int64),
-        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_offset_dev", c_void),
         ("dZ1", c_void), ("lddz1", C.c_int64), ("dz1_dtype", C.c_int32),
         ("dW2", c_void), ("db_hidden", c_void), ("db_out", c_void),
     ]
@@ -57,6 +57,7 @@ class DenseBwdArgs(C.Structure):
 SIGNATURES = {
     "tgcn_last_error": (C.c_char_p, []),
     "tgcn_version": (C.c_int, []),
+    "tgcn_launch_count": (C.c_uint64, []),
     "tgcn_device_info": (C.c_int, [c_i32p, c_i32p, c_i32p]),
     "tgcn_csr_workspace_bytes": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]),
     "tgcn_csr_from_coo_gcn_norm": (C.c_int, [c_void, c_void, C.c_int64, c_void, C.c_int64, C.c_int64,

@@ -10,6 +10,7 @@
 namespace tgcn {
 
 void set_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of this library bumps tgcn_launch_count()
 
 #define TGCN_CHECK_ARG(cond, ...)                         \
   do {                                                    \
@@ -31,6 +32,7 @@ void set_error(const char* fmt, ...);
 
 #define TGCN_LAUNCH_CHECK()                                                               \
   do {                                                                                    \
+    ::tgcn::count_launch();                                                               \
     cudaError_t _e = cudaPeekAtLastError();                                               \
     if (_e != cudaSuccess) {                                                              \
       ::tgcn::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,          \

@@ -25,7 +25,7 @@ struct DenseBwdParams {
   int64_t n_rows; int64_t row_offset;
   int32_t H, C;
   int32_t act, drop_mode; float drop_p, drop_scale; const uint8_t* __restrict__ keep_mask; int64_t ldmask;
-  uint64_t philox_seed, philox_offset;
+  uint64_t philox_seed, philox_offset; const int64_t* __restrict__ philox_offset_dev;
   void* dZ1; int64_t lddz1; int32_t dz1_dtype;
   // workspace partials
   float* part_dW2;   // [n_cta_x][H*C]
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(DB_THREADS) k_dense_bwd(const DenseBwdParams p
             v = p.keep_mask[row * p.ldmask + h] ? v * p.drop_scale : 0.0f;
           } else if (p.drop_mode == TGCN_DROP_PHILOX) {
             const uint64_t e = (uint64_t)(row + p.row_offset) * (uint64_t)H + (uint64_t)h;
-            const uint4 rr = philox_quad(e >> 2, p.philox_seed, p.philox_offset);
+            const uint4 rr = philox_quad(e >> 2, p.philox_seed, p.philox_offset + (p.philox_offset_dev ? (uint64_t)__ldg(p.philox_offset_dev) : 0ull));
             const uint32_t bits = (e & 3) == 0 ? rr.x : (e & 3) == 1 ? rr.y : (e & 3) == 2 ? rr.z : rr.w;
             v = (u01(bits) >= p.drop_p) ? v * p.drop_scale : 0.0f;
           }
@@ -288,7 +288,7 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
   p.drop_mode = (a->drop_mode != TGCN_DROP_NONE && a->drop_p > 0.0f) ? a->drop_mode : TGCN_DROP_NONE;
   p.drop_p = a->drop_p; p.drop_scale = p.drop_mode == TGCN_DROP_NONE ? 1.0f : 1.0f / (1.0f - a->drop_p);
   p.keep_mask = a->keep_mask; p.ldmask = a->ldmask;
-  p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset;
+  p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset; p.philox_offset_dev = a->philox_offset_dev;
   p.dZ1 = a->dZ1; p.lddz1 = a->lddz1; p.dz1_dtype = a->dz1_dtype;
   p.part_dW2 = (float*)((char*)workspace + L.off_dw);
   p.part_dbh = (float*)((char*)workspace + L.off_dbh);

@@ -7,6 +7,8 @@
 namespace tgcn {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -163,6 +165,7 @@ using namespace tgcn;
 
 extern "C" const char* tgcn_last_error(void) { return g_err; }
 extern "C" int tgcn_version(void) { return 100; }
+extern "C" uint64_t tgcn_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int tgcn_device_info(int* sm, int* major, int* minor) {
   int dev = 0;

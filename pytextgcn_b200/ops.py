@@ -47,7 +47,7 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
          out_dtype: Optional[torch.dtype] = None, plan: Optional[SpmmPlan] = None,
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          drop_mode: int = DROP_NONE, drop_p: float = 0.0, keep_mask: Optional[torch.Tensor] = None,
-         philox_seed: int = 0, philox_offset: int = 0,
+         philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[torch.Tensor] = None,
          W_proj: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
          want_out: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """C = epi(A_hat[rows of plan] @ B[:, :F]) (+ P = C @ W_proj).  See tgcn_spmm.
@@ -91,6 +91,7 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
             raise RuntimeError("spmm: keep_mask must be a row-major uint8/bool tensor")
         a.keep_mask, a.ldmask = keep_mask.data_ptr(), keep_mask.stride(0)
     a.philox_seed, a.philox_offset = philox_seed & (2**64 - 1), philox_offset & (2**64 - 1)
+    a.philox_offset_dev = _native.ptr(philox_offset_dev)
     if W_proj is not None:
         if W_proj.dtype != torch.float32 or not W_proj.is_contiguous() or W_proj.shape[0] != F:
             raise RuntimeError("spmm: W_proj must be a contiguous fp32 [F, n_proj] tensor")
@@ -106,7 +107,8 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
 def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[torch.Tensor], n_mask_total: int,
                *, want_grad: bool = True, dZ: Optional[torch.Tensor] = None, want_pred: bool = False,
                want_correct: bool = False, loss_out: Optional[torch.Tensor] = None,
-               workspace: Optional[torch.Tensor] = None):
+               workspace: Optional[torch.Tensor] = None, pred: Optional[torch.Tensor] = None,
+               correct: Optional[torch.Tensor] = None, want_partial: bool = False):
     """Masked mean cross-entropy over rows of Z (+ gradient / argmax / #correct).  See tgcn_masked_nll.
     Returns dict(loss=[2] fp32 (mean nll, count), dZ, pred, correct, partial)."""
     _need_cuda(Z, y, mask, dZ)
@@ -121,18 +123,19 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
     dev = Z.device
     if loss_out is None:
         loss_out = torch.empty(2, dtype=torch.float32, device=dev)
-    partial = torch.empty(2, dtype=torch.float64, device=dev)
+    partial = torch.empty(2, dtype=torch.float64, device=dev) if want_partial else None
     if want_grad and dZ is None:
         dZ = torch.zeros((n, pad4(n_classes)), dtype=torch.float32, device=dev)
-    pred = torch.empty(n, dtype=torch.int32, device=dev) if want_pred else None
-    correct = torch.zeros(1, dtype=torch.int32, device=dev) if want_correct else None
-    need = C.c_size_t(0)
-    _native.check(lib.tgcn_masked_nll_workspace_bytes(n, C.byref(need)))
-    if workspace is None or workspace.numel() < need.value:
-        workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    if pred is None and want_pred:
+        pred = torch.empty(n, dtype=torch.int32, device=dev)
+    if correct is None and want_correct:
+        correct = torch.zeros(1, dtype=torch.int32, device=dev)
+    need = 2 * ((n * 4 + 255) // 256 * 256)        # == tgcn_masked_nll_workspace_bytes(n)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _native.check(lib.tgcn_masked_nll(Z.data_ptr(), Z.stride(0), n, n_classes, y.data_ptr(), _native.ptr(mask),
-                                          int(n_mask_total), loss_out.data_ptr(), partial.data_ptr(),
+                                          int(n_mask_total), loss_out.data_ptr(), _native.ptr(partial),
                                           _native.ptr(dZ) if want_grad else None, dZ.stride(0) if want_grad else 0,
                                           _native.ptr(pred), _native.ptr(correct),
                                           workspace.data_ptr(), workspace.numel(), _stream()))
@@ -142,7 +145,7 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
 def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Optional[torch.Tensor], *,
               H: int, n_classes: int, act: int = ACT_NONE, drop_mode: int = DROP_NONE, drop_p: float = 0.0,
               keep_mask: Optional[torch.Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,
-              row_offset: int = 0, dZ1: Optional[torch.Tensor] = None, dz1_dtype: torch.dtype = torch.float32,
+              philox_offset_dev: Optional[torch.Tensor] = None, row_offset: int = 0, dZ1: Optional[torch.Tensor] = None, dz1_dtype: torch.dtype = torch.float32,
               want_dz1: bool = True, workspace: Optional[torch.Tensor] = None,
               dW2: Optional[torch.Tensor] = None, db_hidden: Optional[torch.Tensor] = None,
               db_out: Optional[torch.Tensor] = None):
@@ -164,6 +167,7 @@ def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Option
     if keep_mask is not None:
         a.keep_mask, a.ldmask = keep_mask.data_ptr(), keep_mask.stride(0)
     a.philox_seed, a.philox_offset = philox_seed & (2**64 - 1), philox_offset & (2**64 - 1)
+    a.philox_offset_dev = _native.ptr(philox_offset_dev)
     if want_dz1:
         if dZ1 is None:
             width = pad4(H) if dz1_dtype == torch.float32 else pad8(H)

@@ -1,0 +1,233 @@
+"""Fused full-batch trainer: the reference's epoch loop (flat_amazon.py:99-117) with every
+device-side step routed through the C ABI and captured in CUDA graphs.
+
+One reference epoch =
+    train step : gcn(g)[train_mask] -> CrossEntropyLoss(mean) -> backward -> Adam/AMSGrad step
+                 (flat_amazon.py:100-106)
+    eval       : gcn.eval() forward, val loss, argmax / accuracy  (flat_amazon.py:107-116)
+Here the train step is 8 kernels families (2 forward SpMMs with fused bias/dropout/projection,
+masked NLL + gradient, 2 backward SpMMs, the dense dW/db/dZ1 pass, Adam) on static buffers;
+parameters are updated in place, so the wrapped `GCN` stays an ordinary nn.Module
+(state_dict / th.save keep working, flat_amazon.py:126-128).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .graph import GraphCSR, get_graph
+from .models import GCN, decode_features
+
+
+class TextGCNTrainer:
+    def __init__(self, gcn: GCN, g, lr: float = 0.05, amsgrad: bool = True, betas=(0.9, 0.999), eps: float = 1e-8,
+                 use_cuda_graph: bool = True, seed: int = 0, chunk_nnz: Optional[int] = None,
+                 graph: Optional[GraphCSR] = None, assume_symmetric: bool = False):
+        if len(gcn.layers) != 2:
+            raise NotImplementedError("TextGCNTrainer fuses the 2-layer TextGCN (the configuration of every reference script)")
+        l0, l1 = gcn.layers
+        if not l0.weight.is_cuda:
+            raise RuntimeError("TextGCNTrainer needs the module and the graph on a CUDA device (no CPU path)")
+        self.gcn, self.g = gcn, g
+        self.dev = l0.weight.device
+        self.n = int(g.x.shape[0])
+        self.feat = decode_features(g.x, getattr(g, "n_vocab", None))
+        if self.feat is None:
+            raise RuntimeError("TextGCNTrainer expects featureless input x = I or [I | F] (text2graph.py:226-246)")
+        self.graph = graph if graph is not None else get_graph(g.edge_index, g.edge_attr, self.n, holder=g)
+        if assume_symmetric:
+            self.graph._symmetric = True
+        self.graph_t = self.graph.transpose()
+        kw = {} if chunk_nnz is None else dict(chunk_nnz=chunk_nnz)
+        self.plan = self.graph.plan(**kw)
+        self.plan_t = self.plan if self.graph_t is self.graph else self.graph_t.plan(**kw)
+        self.lr, self.amsgrad, self.betas, self.eps = float(lr), bool(amsgrad), betas, float(eps)
+        self.act = ops.ACT_RELU if gcn.apply_activation else ops.ACT_NONE
+        self.p = float(gcn.dropout)
+        self.seed = int(seed)
+        self.use_cuda_graph = use_cuda_graph
+        self.H, self.C = int(l0.weight.shape[1]), int(l1.weight.shape[1])
+        self.in_ch = int(l0.weight.shape[0])
+        if self.H % 4 != 0:
+            raise NotImplementedError("TextGCNTrainer needs a hidden width that is a multiple of 4 "
+                                      "(reference widths: 32, 64, 100, 200, 256)")
+        self.Cp = ops.pad4(self.C)
+        n, H, Cp, dev = self.n, self.H, self.Cp, self.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.params = [l0.weight, l0.bias, l1.weight, l1.bias]
+        for p_ in self.params:
+            if not p_.is_contiguous():
+                raise RuntimeError("parameters must be contiguous")
+        self.grads = [torch.zeros_like(p_.data) for p_ in self.params]
+        self.exp_avg = [torch.zeros_like(p_.data) for p_ in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p_.data) for p_ in self.params]
+        self.max_exp_avg_sq = [torch.zeros_like(p_.data) for p_ in self.params] if amsgrad else [None] * 4
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.XW = torch.zeros((n, H), **f32) if self.feat.Fdoc is not None else None
+        self.H1d = torch.empty((n, H), **f32)
+        self.P = torch.zeros((n, Cp), **f32)
+        self.Z2 = torch.zeros((n, Cp), **f32)
+        self.dZ2 = torch.zeros((n, Cp), **f32)
+        self.G2 = torch.zeros((n, Cp), **f32)
+        self.dZ1 = torch.zeros((n, H), **f32)
+        self.loss_train = torch.zeros(2, **f32)
+        self.loss_val = torch.zeros(2, **f32)
+        self.loss_tr_eval = torch.zeros(2, **f32)
+        self.pred = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.correct_val = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.correct_train = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.hier_tail = torch.empty((self.in_ch - n, H), **f32) if self.feat.Fdoc is not None else None
+        self._nll_ws = torch.empty(2 * ((n * 4 + 255) // 256 * 256), dtype=torch.uint8, device=dev)
+        self._db_ws = None
+        self.logits = self.Z2[:, :self.C]
+        self.set_masks(g.y, g.train_mask, getattr(g, "val_mask", None))
+        self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        self._warm: Dict[str, int] = {}
+        self.launches_per_train_step = 0
+        self.launches_per_eval = 0
+
+    # ---- labels / masks (per-call inputs of the loss, flat_amazon.py:101-102,110) ----
+    def set_masks(self, y: torch.Tensor, train_mask: torch.Tensor, val_mask: Optional[torch.Tensor]) -> None:
+        """Copies into static device buffers (so captured graphs stay valid) and recounts."""
+        dev = self.dev
+        if not hasattr(self, "y"):
+            self.y = torch.empty(self.n, dtype=torch.int64, device=dev)
+            self.train_mask = torch.empty(self.n, dtype=torch.bool, device=dev)
+            self.val_mask = torch.zeros(self.n, dtype=torch.bool, device=dev)
+        self.y.copy_(y, non_blocking=True)
+        self.train_mask.copy_(train_mask, non_blocking=True)
+        if val_mask is not None:
+            self.val_mask.copy_(val_mask, non_blocking=True)
+        n_train = int(train_mask.sum().item())
+        n_val = int(val_mask.sum().item()) if val_mask is not None else 0
+        if getattr(self, "n_train", n_train) != n_train or getattr(self, "n_val", n_val) != n_val:
+            self._graphs = {}      # the divisor is baked into the captured launches
+            self._warm = {}
+        self.n_train, self.n_val = n_train, n_val
+        if n_train == 0:
+            raise RuntimeError("train_mask selects no rows")
+
+    # ---- the step bodies (eager; captured once warmed up) ----
+    def _forward(self, training: bool) -> int:
+        l0, l1 = self.gcn.layers
+        W1, b1, W2, b2 = l0.weight.data, l0.bias.data, l1.weight.data, l1.bias.data
+        k = 0
+        if self.feat.Fdoc is not None:
+            ops.hier_forward(W1, self.n, self.feat.n_vocab, self.feat.Fdoc, out=self.XW)
+            B1 = self.XW
+            k += 1
+        else:
+            B1 = W1[:self.n]
+        drop = training and self.p > 0.0
+        ops.spmm(self.graph, B1, F=self.H, plan=self.plan, out=self.H1d, bias=b1, act=self.act,
+                 drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p,
+                 philox_seed=self.seed, philox_offset=0, philox_offset_dev=self.step_dev if drop else None,
+                 W_proj=W2, P=self.P)
+        ops.spmm(self.graph, self.P, F=self.Cp, plan=self.plan, out=self.Z2, bias=b2)
+        return k + 2 + 2 * (1 if self.plan.n_split_rows else 0)
+
+    def _train_body(self) -> int:
+        l0, l1 = self.gcn.layers
+        W2 = l1.weight.data
+        k = self._forward(True)
+        ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2,
+                       loss_out=self.loss_train, workspace=self._nll_ws)
+        k += 2
+        ops.spmm(self.graph_t, self.dZ2, F=self.Cp, plan=self.plan_t, out=self.G2)
+        drop = self.p > 0.0
+        r = ops.dense_bwd(self.G2, self.H1d, W2, self.dZ2, H=self.H, n_classes=self.C, act=self.act,
+                          drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p,
+                          philox_seed=self.seed, philox_offset=0, philox_offset_dev=self.step_dev if drop else None,
+                          dZ1=self.dZ1, workspace=self._db_ws, dW2=self.grads[2], db_hidden=self.grads[1],
+                          db_out=self.grads[3])
+        self._db_ws = r["workspace"]
+        k += 1 + 4
+        ops.spmm(self.graph_t, self.dZ1, F=self.H, plan=self.plan_t, out=self.grads[0])
+        k += 2 + 2 * (1 if self.plan_t.n_split_rows else 0)
+        if self.feat.Fdoc is not None:
+            ops.hier_backward(self.grads[0], self.n, self.feat.n_vocab, self.feat.Fdoc, self.H, self.hier_tail)
+            self.grads[0][self.n:].copy_(self.hier_tail)
+            k += 3
+        ops.increment_step(self.step_dev)
+        k += 1
+        for i, p_ in enumerate(self.params):
+            ops.adam_step(p_.data, self.grads[i], self.exp_avg[i], self.exp_avg_sq[i], self.max_exp_avg_sq[i],
+                          lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad,
+                          step_dev=self.step_dev)
+            k += 1
+        return k
+
+    def _eval_body(self) -> int:
+        """eval forward, val loss, argmax of every row, #correct on the val and train rows
+        (flat_amazon.py:107-114 without the D2H copies)."""
+        k = self._forward(False)
+        if self.n_val > 0:
+            ops.masked_nll(self.Z2, self.C, self.y, self.val_mask, self.n_val, want_grad=False,
+                           loss_out=self.loss_val, workspace=self._nll_ws, pred=self.pred, correct=self.correct_val)
+            k += 2
+        ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=False,
+                       loss_out=self.loss_tr_eval, workspace=self._nll_ws, pred=self.pred, correct=self.correct_train)
+        return k + 2
+
+    # ---- graph capture plumbing ----
+    def _run(self, name: str, body) -> None:
+        from . import _native
+        lib = _native.load()
+        if not self.use_cuda_graph:
+            c0 = lib.tgcn_launch_count()
+            body()
+            self._set_launches(name, int(lib.tgcn_launch_count() - c0))
+            return
+        gph = self._graphs.get(name)
+        if gph is not None:
+            gph.replay()
+            return
+        warm = self._warm.get(name, 0)
+        if warm < 2:                      # eager warm-up (sets func attributes, sizes workspaces)
+            c0 = lib.tgcn_launch_count()
+            body()
+            self._set_launches(name, int(lib.tgcn_launch_count() - c0))   # exact kernel count of this step
+            self._warm[name] = warm + 1
+            return
+        torch.cuda.synchronize(self.dev)
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            body()
+        self._graphs[name] = gph
+        gph.replay()
+
+    def _set_launches(self, name: str, k: int) -> None:
+        if name == "train":
+            self.launches_per_train_step = k
+        else:
+            self.launches_per_eval = k
+
+    # ---- public API ----
+    def train_step(self) -> torch.Tensor:
+        """One full-batch training step.  Returns the device tensor [mean train loss, #rows]."""
+        self.gcn.train()
+        self._run("train", self._train_body)
+        return self.loss_train
+
+    def eval_step(self) -> Dict[str, torch.Tensor]:
+        """Eval forward + val loss + on-device argmax/accuracy counts (device tensors, no sync)."""
+        self.gcn.eval()
+        self._run("eval", self._eval_body)
+        return dict(logits=self.logits, val_loss=self.loss_val, pred=self.pred, correct_val=self.correct_val,
+                    correct_train=self.correct_train)
+
+    def epoch(self) -> Dict[str, float]:
+        """One reference epoch; the only host sync is the final read-back (like loss.item(),
+        flat_amazon.py:115)."""
+        self.train_step()
+        self.eval_step()
+        vals = torch.cat([self.loss_train[:1], self.loss_val[:1],
+                          self.correct_train.float() / max(self.n_train, 1),
+                          self.correct_val.float() / max(self.n_val, 1)]).cpu().tolist()
+        return dict(loss=vals[0], val_loss=vals[1], acc_train=vals[2], acc_val=vals[3])
+
+    @property
+    def step(self) -> int:
+        return int(self.step_dev.item())

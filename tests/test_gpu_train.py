@@ -1,0 +1,161 @@
+"""GPU parity of the training-side kernels: masked NLL, fused Adam/AMSGrad, the dense backward
+pass, and the fused TextGCNTrainer (CUDA-graph epochs) against the oracle's reference epoch."""
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import gcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.mark.parametrize("C", [3, 20, 64, 219])
+def test_masked_nll_and_gradient(cuda, C):
+    from pytextgcn_b200 import ops
+    torch.manual_seed(C)
+    n = 3000
+    z = (torch.randn(n, C) * 3).requires_grad_()
+    y = torch.randint(0, C, (n,))
+    mask = torch.rand(n) > 0.6
+    y_masked = y.clone()
+    y_masked[~mask] = -1                               # never read where mask == 0
+    loss_ref = O.masked_cross_entropy(z, y, mask)
+    loss_ref.backward()
+    Cp = ops.pad4(C)
+    zd = torch.zeros(n, Cp, device=cuda)
+    zd[:, :C] = z.detach().to(cuda)
+    r = ops.masked_nll(zd, C, y_masked.to(cuda), mask.to(cuda), int(mask.sum()), want_grad=True, want_pred=True,
+                       want_correct=True)
+    assert abs(r["loss"][0].item() - loss_ref.item()) < TOL * abs(loss_ref.item())
+    assert int(r["loss"][1].item()) == int(mask.sum())
+    assert rel_err(r["dZ"][:, :C], z.grad) < TOL
+    assert torch.all(r["dZ"][:, C:] == 0)
+    pred_ref = z.detach().numpy().argmax(axis=1)
+    assert (r["pred"].cpu().numpy()[mask.numpy()] == pred_ref[mask.numpy()]).all()
+    assert int(r["correct"].item()) == int((torch.from_numpy(pred_ref)[mask] == y[mask]).sum())
+
+
+@pytest.mark.parametrize("amsgrad", [False, True])
+def test_adam_matches_torch(cuda, amsgrad):
+    from pytextgcn_b200 import ops
+    torch.manual_seed(0)
+    n = 10007                                           # odd length: vector body + scalar tail
+    p_ref = torch.randn(n).requires_grad_()
+    opt = torch.optim.Adam([p_ref], lr=0.05, amsgrad=amsgrad)
+    p = p_ref.detach().clone().to(cuda)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    vmax = torch.zeros_like(p) if amsgrad else None
+    step_dev = torch.zeros(1, dtype=torch.int64, device=cuda)
+    for step in range(1, 6):
+        grad = torch.randn(n) * (0.1 if step % 2 else 2.0)
+        p_ref.grad = grad.clone()
+        opt.step()
+        ops.increment_step(step_dev)
+        ops.adam_step(p, grad.to(cuda), m, v, vmax, lr=0.05, amsgrad=amsgrad, step_dev=step_dev)
+        assert rel_err(p, p_ref) < 2e-6
+    assert int(step_dev.item()) == 5
+
+
+@pytest.mark.parametrize("H,C,act", [(200, 20, 0), (100, 64, 0), (32, 219, 0), (256, 20, 1), (64, 6, 0), (256, 220, 0)])
+def test_dense_backward(cuda, H, C, act):
+    from pytextgcn_b200 import ops
+    torch.manual_seed(H + C)
+    n, p = 777, 0.5
+    G2 = torch.randn(n, C)
+    keep = torch.rand(n, H) > p
+    z1 = torch.randn(n, H)
+    h_pre = torch.relu(z1) if act else z1
+    H1d = h_pre * keep * (1 / (1 - p))
+    W2 = torch.randn(H, C) * 0.1
+    dZ2 = torch.randn(n, C)
+    # oracle: autograd through hd = dropout(act(z1)); out = hd @ W2, with upstream grad G2
+    z1r = z1.clone().requires_grad_()
+    W2r = W2.clone().requires_grad_()
+    hd = (torch.relu(z1r) if act else z1r) * keep * (1 / (1 - p))
+    (hd @ W2r).backward(G2)
+    Cp = ops.pad4(C)
+    G2d = torch.zeros(n, Cp, device=cuda); G2d[:, :C] = G2.to(cuda)
+    dZ2d = torch.zeros(n, Cp, device=cuda); dZ2d[:, :C] = dZ2.to(cuda)
+    r = ops.dense_bwd(G2d, H1d.to(cuda), W2.to(cuda), dZ2d, H=H, n_classes=C, act=act, drop_mode=ops.DROP_MASK,
+                      drop_p=p, keep_mask=keep.to(torch.uint8).to(cuda))
+    assert rel_err(r["dW2"], W2r.grad) < TOL
+    assert rel_err(r["dZ1"][:, :H], z1r.grad) < TOL
+    assert rel_err(r["db_hidden"], z1r.grad.sum(0)) < 5e-5
+    assert rel_err(r["db_out"], dZ2.sum(0)) < 5e-5
+
+
+def _make_pair(cuda, shape_name="small", p=0.0, amsgrad=True, hier=None, relu=False):
+    from pytextgcn_b200 import GCN
+    from pytextgcn_b200.synthetic import make_graph, SHAPES
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    shape = SHAPES[shape_name]
+    g = make_graph(shape, seed=1, hierarchy_classes=hier)
+    n, in_ch = int(g.x.shape[0]), int(g.x.shape[1])
+    torch.manual_seed(0)
+    ref = O.OracleGCN(in_ch, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=p, relu=relu)
+    mod = GCN(in_ch, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=p, apply_activation=relu)
+    with torch.no_grad():
+        for pd, ps in zip(mod.parameters(), ref.parameters()):
+            pd.copy_(ps)
+    mod = mod.to(cuda)
+    gd = g.clone().to(cuda)
+    return g, gd, ref, mod, shape
+
+
+@pytest.mark.parametrize("graph_mode", [False, True])
+@pytest.mark.parametrize("hier", [None, 5])
+def test_trainer_gradients_and_first_steps_match_reference_epoch(cuda, graph_mode, hier):
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    g, gd, ref, mod, shape = _make_pair(cuda, p=0.0, hier=hier)
+    tr = TextGCNTrainer(mod, gd, lr=0.01, amsgrad=True, use_cuda_graph=graph_mode)
+    opt = torch.optim.Adam(ref.parameters(), lr=0.01, amsgrad=True)
+    for step in range(5):                                 # crosses the eager warm-up -> graph replay boundary
+        out_ref = O.reference_epoch(ref, g, opt)
+        out = tr.epoch()
+        # gradients of this step (trainer keeps them in static buffers)
+        for gbuf, pr in zip(tr.grads, ref.parameters()):
+            assert rel_err(gbuf, pr.grad) < 2e-5 * (step + 1), f"step {step}"
+        assert abs(out["loss"] - out_ref[0]) < 1e-5 * max(1, abs(out_ref[0])) * (step + 1)
+        assert abs(out["val_loss"] - out_ref[1]) < 1e-4 * max(1, abs(out_ref[1])) * (step + 1)
+        assert abs(out["acc_train"] - out_ref[2]) < 0.01 and abs(out["acc_val"] - out_ref[3]) < 0.02
+    assert tr.step == 5
+    # parameters were updated IN PLACE: the wrapped module is the trained model (state_dict/th.save keep working)
+    for pm, pr in zip(mod.parameters(), ref.parameters()):
+        assert rel_err(pm, pr) < 1e-3
+
+
+def test_trainer_with_dropout_learns_and_is_reproducible(cuda):
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    runs = []
+    for _ in range(2):
+        g, gd, ref, mod, shape = _make_pair(cuda, p=0.5)
+        tr = TextGCNTrainer(mod, gd, lr=0.05, amsgrad=True, seed=7)
+        runs.append([tr.epoch()["loss"] for _ in range(12)])
+    assert runs[0] == runs[1]                              # deterministic kernels + counter-based Philox
+    assert runs[0][-1] < runs[0][0]
+
+
+def test_trainer_dropout_mask_differs_per_step_and_matches_backward(cuda):
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    g, gd, ref, mod, shape = _make_pair(cuda, p=0.5)
+    tr = TextGCNTrainer(mod, gd, lr=0.0, amsgrad=False, seed=3)   # lr 0: weights frozen, only the mask moves
+    masks = []
+    for _ in range(4):
+        tr.train_step()
+        masks.append((tr.H1d != 0).clone())
+        # backward used the same mask: dZ1 is zero exactly where the forward dropped
+        assert torch.all(tr.dZ1[~masks[-1]] == 0)
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[2], masks[3])
+    assert abs(masks[0].float().mean().item() - 0.5) < 0.01
+
+
+def test_trainer_relu_variant(cuda):
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    g, gd, ref, mod, shape = _make_pair(cuda, p=0.0, relu=True)
+    tr = TextGCNTrainer(mod, gd, lr=0.01, amsgrad=False)
+    opt = torch.optim.Adam(ref.parameters(), lr=0.01)
+    for _ in range(3):
+        out_ref = O.reference_epoch(ref, g, opt)
+        out = tr.epoch()
+        assert abs(out["loss"] - out_ref[0]) < 5e-5 * max(1, abs(out_ref[0]))
