@@ -33,6 +33,7 @@ struct DenseBwdParams {
   float* part_dbo;   // [n_cta_x][C]
   int32_t cb_per_y;  // c-blocks (of 4 classes) handled per blockIdx.y
   int32_t n_tiles;
+  int32_t w2_in_smem;  // 0: W2 too large for shared memory, read it through L1/L2 instead
 };
 
 __device__ __forceinline__ float load_h(const void* H1d, int h_dtype, int64_t idx) {
@@ -40,60 +41,77 @@ __device__ __forceinline__ float load_h(const void* H1d, int h_dtype, int64_t id
                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(H1d)[idx]);
 }
 
-template <int KMAX>   // KMAX = ceil(H/32) upper bound
-__global__ void __launch_bounds__(DB_THREADS) k_dense_bwd(const DenseBwdParams p) {
+// Lane l of a warp owns the hidden quads q = l + 32*k (h = 4q .. 4q+3), k < KQ.
+template <int KQ>   // KQ = ceil(H/128) upper bound
+__global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParams p) {
   extern __shared__ __align__(16) float smem[];
-  const int H = p.H, C = p.C;
-  const int Hp = (H + 3) & ~3, Cp = (C + 3) & ~3;
-  const int ldw = C | 1;                         // odd stride: conflict-free W2s[h][c] across lanes h
-  float* W2s = smem;                             // [H][ldw]
-  float* Hs = W2s + ((H * ldw + 3) & ~3);        // [DB_ROWS][Hp]
-  float* G2s = Hs + DB_ROWS * Hp;                // [DB_ROWS][Cp]   (row-major, for the dW2 outer products)
-  float* G2t = G2s + DB_ROWS * Cp;               // [Cp][DB_ROWS]   (transposed, for the dZ1 contraction)
-  float* red = G2t + Cp * DB_ROWS;               // [8][max(Hp, Cp)] cross-warp reduction scratch
+  const int H = p.H, C = p.C;                    // H % 4 == 0 (host pads)
+  const int Cp = (C + 3) & ~3;
+  float* W2t = smem;                             // [C][H]   transposed weights (h contiguous) when staged
+  float* Hs = W2t + (p.w2_in_smem ? C * H : 0);  // [DB_ROWS][H]
+  float* G2s = Hs + DB_ROWS * H;                 // [DB_ROWS][Cp]   row-major, for the dW2 outer products
+  float* G2t = G2s + DB_ROWS * Cp;               // [Cp][DB_ROWS]   transposed, for the dZ1 contraction
+  float* dZs = G2t + Cp * DB_ROWS;               // [DB_ROWS][Cp]   dZ2 tile for db_out
+  float* red = dZs + DB_ROWS * Cp;               // [8][H] cross-warp reduction scratch
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool do_rows = (blockIdx.y == 0);        // dZ1 / db are produced once, by the y == 0 slice
+  const int HQ = H >> 2;
 
-  for (int i = tid; i < H * C; i += DB_THREADS) W2s[(i / C) * ldw + (i % C)] = p.W2[i];
+  if (p.w2_in_smem)
+    for (int i = tid; i < H * C; i += DB_THREADS) { const int h = i / C, c = i - h * C; W2t[c * H + h] = p.W2[i]; }
 
   // dW2 register tile: block id -> (hb, cb) with cb restricted to this y-slice
-  const int HB = Hp >> 2;
   const int cb0 = blockIdx.y * p.cb_per_y;
   const int CBl = min(p.cb_per_y, (Cp >> 2) - cb0);
-  const int n_blocks = HB * CBl;
+  const int n_blocks = HQ * CBl;
   float dw[DB_MAXNB][16];
 #pragma unroll
   for (int b = 0; b < DB_MAXNB; ++b)
 #pragma unroll
     for (int i = 0; i < 16; ++i) dw[b][i] = 0.0f;
-  float dbh[KMAX];
+  float dbh[KQ][4];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) dbh[k] = 0.0f;
+  for (int k = 0; k < KQ; ++k) dbh[k][0] = dbh[k][1] = dbh[k][2] = dbh[k][3] = 0.0f;
   float dbo = 0.0f;   // thread c < C accumulates db_out[c]
+  const uint64_t ph_off = p.philox_offset + (p.philox_offset_dev ? (uint64_t)__ldg(p.philox_offset_dev) : 0ull);
   __syncthreads();
 
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int64_t r0 = (int64_t)tile * DB_ROWS;
-    // ---- stage the tile ----
-    for (int i = tid; i < DB_ROWS * Hp; i += DB_THREADS) {
-      const int r = i / Hp, h = i - r * Hp;
+    // ---- stage the tile: warp w loads rows 4w .. 4w+3 with 16-byte loads ----
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = wid * 4 + q;
       const int64_t row = r0 + r;
-      Hs[i] = (row < p.n_rows && h < H) ? load_h(p.H1d, p.h_dtype, row * p.ldh + h) : 0.0f;
+      for (int hq = lane; hq < HQ; hq += 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < p.n_rows) {
+          if (p.h_dtype == TGCN_F32) {
+            v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.H1d) + row * p.ldh) + hq);
+          } else {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.H1d) + row * p.ldh) + hq);
+            v = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                            __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+          }
+        }
+        *reinterpret_cast<float4*>(Hs + r * H + 4 * hq) = v;
+      }
     }
     for (int i = tid; i < DB_ROWS * Cp; i += DB_THREADS) {
       const int r = i / Cp, c = i - r * Cp;
       const int64_t row = r0 + r;
-      const float g = (row < p.n_rows && c < C) ? p.G2[row * p.ldg2 + c] : 0.0f;
+      const bool ok = (row < p.n_rows && c < C);
+      const float g = ok ? p.G2[row * p.ldg2 + c] : 0.0f;
       G2s[i] = g;
       G2t[c * DB_ROWS + r] = g;
-    }
-    if (do_rows && p.dZ2 && tid < C) {
-      for (int r = 0; r < DB_ROWS; ++r) {
-        const int64_t row = r0 + r;
-        if (row < p.n_rows) dbo += p.dZ2[row * p.lddz2 + tid];
-      }
+      if (p.dZ2) dZs[i] = ok ? p.dZ2[row * p.lddz2 + c] : 0.0f;
     }
     __syncthreads();
+
+    if (do_rows && p.dZ2 && tid < C) {
+#pragma unroll 8
+      for (int r = 0; r < DB_ROWS; ++r) dbo += dZs[r * Cp + tid];
+    }
 
     // ---- dW2 += Hs^T G2s  (4x4 register blocks) ----
 #pragma unroll
@@ -101,9 +119,9 @@ __global__ void __launch_bounds__(DB_THREADS) k_dense_bwd(const DenseBwdParams p
       const int blk = tid + b * DB_THREADS;
       if (blk < n_blocks) {
         const int hb = blk / CBl, cb = blk - hb * CBl + cb0;
-#pragma unroll 4
+#pragma unroll 8
         for (int r = 0; r < DB_ROWS; ++r) {
-          const float4 a = *reinterpret_cast<const float4*>(Hs + r * Hp + hb * 4);
+          const float4 a = *reinterpret_cast<const float4*>(Hs + r * H + hb * 4);
           const float4 g = *reinterpret_cast<const float4*>(G2s + r * Cp + cb * 4);
           dw[b][0] = fmaf(a.x, g.x, dw[b][0]);  dw[b][1] = fmaf(a.x, g.y, dw[b][1]);
           dw[b][2] = fmaf(a.x, g.z, dw[b][2]);  dw[b][3] = fmaf(a.x, g.w, dw[b][3]);
@@ -117,22 +135,34 @@ __global__ void __launch_bounds__(DB_THREADS) k_dense_bwd(const DenseBwdParams p
       }
     }
 
-    // ---- dZ1 rows: warp `wid` owns rows 4*wid .. 4*wid+3, lane owns h = lane + 32k ----
+    // ---- dZ1 rows: warp `wid` owns rows 4*wid .. 4*wid+3; lane owns hidden quads lane + 32k ----
     if (do_rows && p.dZ1) {
-      float dz[4][KMAX];
+      float dz[4][KQ][4];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) dz[q][k] = 0.0f;
+        for (int k = 0; k < KQ; ++k) dz[q][k][0] = dz[q][k][1] = dz[q][k][2] = dz[q][k][3] = 0.0f;
       const int rb = wid * 4;
       for (int c = 0; c < C; ++c) {
-        const float4 g = *reinterpret_cast<const float4*>(G2t + c * DB_ROWS + rb);
+        const float4 g = *reinterpret_cast<const float4*>(G2t + c * DB_ROWS + rb);   // 4 rows, broadcast
+        const float gq[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          const int h = lane + 32 * k;
-          const float w = (h < H) ? W2s[h * ldw + c] : 0.0f;
-          dz[0][k] = fmaf(g.x, w, dz[0][k]); dz[1][k] = fmaf(g.y, w, dz[1][k]);
-          dz[2][k] = fmaf(g.z, w, dz[2][k]); dz[3][k] = fmaf(g.w, w, dz[3][k]);
+        for (int k = 0; k < KQ; ++k) {
+          const int hq = lane + 32 * k;
+          if (hq < HQ) {
+            float4 w;
+            if (p.w2_in_smem) {
+              w = *reinterpret_cast<const float4*>(W2t + c * H + 4 * hq);
+            } else {
+              const float* wp = p.W2 + (int64_t)(4 * hq) * C + c;
+              w = make_float4(__ldg(wp), __ldg(wp + C), __ldg(wp + 2 * C), __ldg(wp + 3 * C));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              dz[q][k][0] = fmaf(gq[q], w.x, dz[q][k][0]); dz[q][k][1] = fmaf(gq[q], w.y, dz[q][k][1]);
+              dz[q][k][2] = fmaf(gq[q], w.z, dz[q][k][2]); dz[q][k][3] = fmaf(gq[q], w.w, dz[q][k][3]);
+            }
+          }
         }
       }
 #pragma unroll
@@ -141,24 +171,36 @@ __global__ void __launch_bounds__(DB_THREADS) k_dense_bwd(const DenseBwdParams p
         const int64_t row = r0 + r;
         if (row >= p.n_rows) continue;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          const int h = lane + 32 * k;
-          if (h >= H) continue;
-          float v = dz[q][k];
+        for (int k = 0; k < KQ; ++k) {
+          const int hq = lane + 32 * k;
+          if (hq >= HQ) continue;
+          float v[4] = {dz[q][k][0], dz[q][k][1], dz[q][k][2], dz[q][k][3]};
           if (p.act == TGCN_ACT_RELU) {
             // forward was dropout(relu(z)): the output is > 0 iff kept and z > 0
-            v = (Hs[r * Hp + h] > 0.0f) ? v * p.drop_scale : 0.0f;
+            const float4 hv = *reinterpret_cast<const float4*>(Hs + r * H + 4 * hq);
+            v[0] = hv.x > 0.0f ? v[0] * p.drop_scale : 0.0f; v[1] = hv.y > 0.0f ? v[1] * p.drop_scale : 0.0f;
+            v[2] = hv.z > 0.0f ? v[2] * p.drop_scale : 0.0f; v[3] = hv.w > 0.0f ? v[3] * p.drop_scale : 0.0f;
           } else if (p.drop_mode == TGCN_DROP_MASK) {
-            v = p.keep_mask[row * p.ldmask + h] ? v * p.drop_scale : 0.0f;
+            const uint8_t* m = p.keep_mask + row * p.ldmask + 4 * hq;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = m[i] ? v[i] * p.drop_scale : 0.0f;
           } else if (p.drop_mode == TGCN_DROP_PHILOX) {
-            const uint64_t e = (uint64_t)(row + p.row_offset) * (uint64_t)H + (uint64_t)h;
-            const uint4 rr = philox_quad(e >> 2, p.philox_seed, p.philox_offset + (p.philox_offset_dev ? (uint64_t)__ldg(p.philox_offset_dev) : 0ull));
-            const uint32_t bits = (e & 3) == 0 ? rr.x : (e & 3) == 1 ? rr.y : (e & 3) == 2 ? rr.z : rr.w;
-            v = (u01(bits) >= p.drop_p) ? v * p.drop_scale : 0.0f;
+            const uint64_t e4 = ((uint64_t)(row + p.row_offset) * (uint64_t)H + (uint64_t)(4 * hq)) >> 2;
+            const uint4 rr = philox_quad(e4, p.philox_seed, ph_off);
+            v[0] = (u01(rr.x) >= p.drop_p) ? v[0] * p.drop_scale : 0.0f;
+            v[1] = (u01(rr.y) >= p.drop_p) ? v[1] * p.drop_scale : 0.0f;
+            v[2] = (u01(rr.z) >= p.drop_p) ? v[2] * p.drop_scale : 0.0f;
+            v[3] = (u01(rr.w) >= p.drop_p) ? v[3] * p.drop_scale : 0.0f;
           }
-          dbh[k] += v;
-          if (p.dz1_dtype == TGCN_F32) reinterpret_cast<float*>(p.dZ1)[row * p.lddz1 + h] = v;
-          else reinterpret_cast<__nv_bfloat16*>(p.dZ1)[row * p.lddz1 + h] = __float2bfloat16_rn(v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dbh[k][i] += v[i];
+          if (p.dz1_dtype == TGCN_F32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dZ1) + row * p.lddz1 + 4 * hq) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+            __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dZ1) + row * p.lddz1 + 4 * hq);
+            o[0] = __floats2bfloat162_rn(v[0], v[1]);
+            o[1] = __floats2bfloat162_rn(v[2], v[3]);
+          }
         }
       }
     }
@@ -184,14 +226,14 @@ __global__ void __launch_bounds__(DB_THREADS) k_dense_bwd(const DenseBwdParams p
   if (do_rows) {
     // db_hidden: fixed-order sum over the 8 warps
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int h = lane + 32 * k;
-      if (h < H) red[wid * Hp + h] = dbh[k];
+    for (int k = 0; k < KQ; ++k) {
+      const int hq = lane + 32 * k;
+      if (hq < HQ) *reinterpret_cast<float4*>(red + wid * H + 4 * hq) = make_float4(dbh[k][0], dbh[k][1], dbh[k][2], dbh[k][3]);
     }
     __syncthreads();
     for (int h = tid; h < H; h += DB_THREADS) {
       float s = 0.0f;
-      for (int w = 0; w < DB_THREADS / 32; ++w) s += red[w * Hp + h];
+      for (int w = 0; w < DB_THREADS / 32; ++w) s += red[w * H + h];
       p.part_dbh[(int64_t)blockIdx.x * H + h] = s;
     }
     if (tid < C) p.part_dbo[(int64_t)blockIdx.x * C + tid] = dbo;
@@ -249,7 +291,7 @@ static DbLayout db_layout(int H, int C, int n_cta) {
   L.total = off;
   return L;
 }
-static int db_grid_x() { return sm_count(); }
+static int db_grid_x() { return 2 * sm_count(); }
 
 }  // namespace tgcn
 
@@ -294,17 +336,22 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
   p.part_dbh = (float*)((char*)workspace + L.off_dbh);
   p.part_dbo = (float*)((char*)workspace + L.off_dbo);
   p.n_tiles = n_tiles;
-  const int Hp = (H + 3) & ~3, Cp = (C + 3) & ~3;
-  const int HB = Hp / 4, CB = Cp / 4;
+  TGCN_CHECK_ARG(H % 4 == 0, "dense_bwd: H (%d) must be a multiple of 4 (pad the hidden width)", H);
+  TGCN_CHECK_ARG(a->ldh % 4 == 0 && ((uintptr_t)a->H1d % 16) == 0, "dense_bwd: H1d must be 16-byte aligned with ldh %% 4 == 0");
+  TGCN_CHECK_ARG(a->dZ1 == nullptr || (a->lddz1 % 4 == 0 && ((uintptr_t)a->dZ1 % 16) == 0),
+                 "dense_bwd: dZ1 must be 16-byte aligned with lddz1 %% 4 == 0");
+  const int Cp = (C + 3) & ~3;
+  const int HB = H / 4, CB = Cp / 4;
   int cb_per_y = std::max(1, (DB_THREADS * DB_MAXNB) / HB);
   cb_per_y = std::min(cb_per_y, CB);
   p.cb_per_y = cb_per_y;
   const int gy = (CB + cb_per_y - 1) / cb_per_y;
-  const int ldw = C | 1;
-  size_t smem = ((size_t)((H * ldw + 3) & ~3) + (size_t)DB_ROWS * Hp + 2 * (size_t)DB_ROWS * Cp +
-                 (size_t)(DB_THREADS / 32) * std::max(Hp, Cp)) * sizeof(float);
+  const size_t smem_rest = ((size_t)DB_ROWS * H + 3 * (size_t)DB_ROWS * Cp + (size_t)(DB_THREADS / 32) * H) * sizeof(float);
+  const size_t smem_w2 = (size_t)H * C * sizeof(float);
+  p.w2_in_smem = (smem_rest + smem_w2 <= 110 * 1024) ? 1 : 0;     // keep 2 CTAs per SM
+  size_t smem = smem_rest + (p.w2_in_smem ? smem_w2 : 0);
   TGCN_CHECK_ARG(smem <= 227 * 1024, "dense_bwd: H=%d C=%d needs %zu bytes of shared memory (> 227 KB)", H, C, smem);
-  const int kmax = (H + 31) / 32;
+  const int kq = (H / 4 + 31) / 32;
   dim3 grid(gx, gy);
 #define TGCN_DB_LAUNCH(K)                                                                                       \
   do {                                                                                                          \
@@ -312,11 +359,9 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
       TGCN_CUDA(cudaFuncSetAttribute(k_dense_bwd<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
     k_dense_bwd<K><<<grid, DB_THREADS, smem, stream>>>(p);                                                      \
   } while (0)
-  if (kmax <= 1) TGCN_DB_LAUNCH(1);
-  else if (kmax <= 2) TGCN_DB_LAUNCH(2);
-  else if (kmax <= 4) TGCN_DB_LAUNCH(4);
-  else if (kmax <= 8) TGCN_DB_LAUNCH(8);
-  else TGCN_DB_LAUNCH(16);
+  if (kq <= 1) TGCN_DB_LAUNCH(1);
+  else if (kq <= 2) TGCN_DB_LAUNCH(2);
+  else TGCN_DB_LAUNCH(4);
 #undef TGCN_DB_LAUNCH
   TGCN_LAUNCH_CHECK();
   const int T = 256;

@@ -57,87 +57,116 @@ template <> struct Vec<__nv_bfloat16> {
 // Epilogue on one finished row held as: lane l (< LPR) owns elements
 // [ (l + v*LPR)*E , +E ) for v < VPL.  All 32 lanes call this (lanes >= LPR idle in the
 // element part but take part in the projection).
-template <int LPR, int VPL, int E>
+template <int LPR, int VPL, int E, bool PROJ>
 __device__ __forceinline__ void row_epilogue(const SpmmParams& p, int64_t row, int lane, float (&acc)[VPL][E],
-                                             float* smem_row, const float* smem_w) {
+                                             const float* smem_w) {
   const int F = p.F;
   const int64_t lrow = row - p.c_row_offset;
-  const bool need_proj = (p.P != nullptr);
-  if (lane < LPR) {
+  const uint64_t ph_off = p.philox_offset + (p.philox_offset_dev ? (uint64_t)__ldg(p.philox_offset_dev) : 0ull);
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int c0 = (lane + v * LPR) * E;
-      if (c0 < F) {
-        float z[E];
+  for (int v = 0; v < VPL; ++v) {
+    const int c0 = (lane + v * LPR) * E;
+    float (&z)[E] = acc[v];
+    if (lane < LPR && c0 < F) {
+      if (p.bias) {
 #pragma unroll
-        for (int i = 0; i < E; ++i) z[i] = acc[v][i];
-        if (p.bias) {
+        for (int i = 0; i < E; ++i) if (c0 + i < p.bias_len) z[i] += __ldg(p.bias + c0 + i);
+      }
+      if (p.act == TGCN_ACT_RELU) {
 #pragma unroll
-          for (int i = 0; i < E; ++i) if (c0 + i < p.bias_len) z[i] += __ldg(p.bias + c0 + i);
-        }
-        if (p.act == TGCN_ACT_RELU) {
+        for (int i = 0; i < E; ++i) z[i] = fmaxf(z[i], 0.0f);
+      }
+      if (p.drop_mode == TGCN_DROP_MASK) {
+        const uint8_t* m = p.keep_mask + lrow * p.ldmask + c0;
 #pragma unroll
-          for (int i = 0; i < E; ++i) z[i] = fmaxf(z[i], 0.0f);
-        }
-        if (p.drop_mode == TGCN_DROP_MASK) {
-          const uint8_t* m = p.keep_mask + lrow * p.ldmask + c0;
+        for (int i = 0; i < E; ++i) z[i] = m[i] ? z[i] * p.drop_scale : 0.0f;
+      } else if (p.drop_mode == TGCN_DROP_PHILOX) {
 #pragma unroll
-          for (int i = 0; i < E; ++i) z[i] = m[i] ? z[i] * p.drop_scale : 0.0f;
-        } else if (p.drop_mode == TGCN_DROP_PHILOX) {
-#pragma unroll
-          for (int q = 0; q < E / 4; ++q) {
-            uint64_t e4 = ((uint64_t)row * (uint64_t)F + (uint64_t)(c0 + 4 * q)) >> 2;
-            uint4 r = philox_quad(e4, p.philox_seed, p.philox_offset + (p.philox_offset_dev ? (uint64_t)__ldg(p.philox_offset_dev) : 0ull));
-            z[4 * q + 0] = (u01(r.x) >= p.drop_p) ? z[4 * q + 0] * p.drop_scale : 0.0f;
-            z[4 * q + 1] = (u01(r.y) >= p.drop_p) ? z[4 * q + 1] * p.drop_scale : 0.0f;
-            z[4 * q + 2] = (u01(r.z) >= p.drop_p) ? z[4 * q + 2] * p.drop_scale : 0.0f;
-            z[4 * q + 3] = (u01(r.w) >= p.drop_p) ? z[4 * q + 3] * p.drop_scale : 0.0f;
-          }
-        }
-        if (p.C) {
-          if (p.c_dtype == TGCN_F32) {
-            float* c = reinterpret_cast<float*>(p.C) + lrow * p.ldc + c0;
-#pragma unroll
-            for (int q = 0; q < E / 4; ++q)
-              *reinterpret_cast<float4*>(c + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
-          } else {
-            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + lrow * p.ldc + c0;
-#pragma unroll
-            for (int q = 0; q < E / 2; ++q)
-              *reinterpret_cast<__nv_bfloat162*>(c + 2 * q) = __floats2bfloat162_rn(z[2 * q], z[2 * q + 1]);
-          }
-        }
-        if (need_proj) {
-#pragma unroll
-          for (int i = 0; i < E; ++i) {
-            float zi = z[i];
-            // the projection consumes exactly what the next layer would read back
-            if (p.C && p.c_dtype == TGCN_BF16) zi = __bfloat162float(__float2bfloat16_rn(zi));
-            smem_row[c0 + i] = zi;
-          }
+        for (int q = 0; q < E / 4; ++q) {
+          uint64_t e4 = ((uint64_t)row * (uint64_t)F + (uint64_t)(c0 + 4 * q)) >> 2;
+          uint4 r = philox_quad(e4, p.philox_seed, ph_off);
+          z[4 * q + 0] = (u01(r.x) >= p.drop_p) ? z[4 * q + 0] * p.drop_scale : 0.0f;
+          z[4 * q + 1] = (u01(r.y) >= p.drop_p) ? z[4 * q + 1] * p.drop_scale : 0.0f;
+          z[4 * q + 2] = (u01(r.z) >= p.drop_p) ? z[4 * q + 2] * p.drop_scale : 0.0f;
+          z[4 * q + 3] = (u01(r.w) >= p.drop_p) ? z[4 * q + 3] * p.drop_scale : 0.0f;
         }
       }
+      if (p.C) {
+        if (p.c_dtype == TGCN_F32) {
+          float* c = reinterpret_cast<float*>(p.C) + lrow * p.ldc + c0;
+#pragma unroll
+          for (int q = 0; q < E / 4; ++q)
+            *reinterpret_cast<float4*>(c + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+        } else {
+          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + lrow * p.ldc + c0;
+#pragma unroll
+          for (int q = 0; q < E / 2; ++q)
+            *reinterpret_cast<__nv_bfloat162*>(c + 2 * q) = __floats2bfloat162_rn(z[2 * q], z[2 * q + 1]);
+          // the projection consumes exactly what the next layer would read back
+#pragma unroll
+          for (int i = 0; i < E; ++i) z[i] = __bfloat162float(__float2bfloat16_rn(z[i]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < E; ++i) z[i] = 0.0f;     // lanes outside the row contribute nothing to the projection
     }
   }
-  if (need_proj) {
-    __syncwarp();
-    const float* W = p.wproj_in_smem ? smem_w : p.W_proj;
+  if constexpr (PROJ) {
+    // P[row, m] = sum_c z[c] * W[c, m].  Every lane multiplies ITS columns (still in registers) into
+    // 16 outputs at a time; a transposing butterfly (16 shuffles) then leaves output m0 + lane/2 in
+    // every lane pair.
     const int M = p.n_proj;
-    for (int m = lane; m < M; m += 32) {
-      float s0 = 0.f, s1 = 0.f;
-      int c = 0;
-      for (; c + 1 < F; c += 2) {
-        s0 = fmaf(smem_row[c], W[(int64_t)c * M + m], s0);
-        s1 = fmaf(smem_row[c + 1], W[(int64_t)(c + 1) * M + m], s1);
+    const int Ms = p.wproj_in_smem ? ((M + 3) & ~3) : M;      // row stride of W (padded in shared memory)
+    const float* W = p.wproj_in_smem ? smem_w : p.W_proj;
+    for (int m0 = 0; m0 < M; m0 += 16) {
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = 0.0f;
+      const int mc = min(16, M - m0);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int c0 = (lane + v * LPR) * E;
+        if (lane < LPR && c0 < F) {
+#pragma unroll
+          for (int i = 0; i < E; ++i) {
+            const float zi = acc[v][i];
+            const float* wr = W + (int64_t)(c0 + i) * Ms + m0;
+            if (p.wproj_in_smem) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                if (j < mc) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(wr + j);
+                  o[j] = fmaf(zi, w4.x, o[j]); o[j + 1] = fmaf(zi, w4.y, o[j + 1]);
+                  o[j + 2] = fmaf(zi, w4.z, o[j + 2]); o[j + 3] = fmaf(zi, w4.w, o[j + 3]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (j < mc) o[j] = fmaf(zi, __ldg(wr + j), o[j]);
+            }
+          }
+        }
       }
-      if (c < F) s0 = fmaf(smem_row[c], W[(int64_t)c * M + m], s0);
-      p.P[lrow * p.ldp + m] = s0 + s1;
+#pragma unroll
+      for (int off = 16; off >= 2; off >>= 1) {      // 16 values -> 1 value per lane (8+4+2+1 shuffles)
+        const bool upper = (lane & off) != 0;
+        const int half = off >> 1;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+          const float send = upper ? o[j] : o[j + half];
+          const float keep = upper ? o[j + half] : o[j];
+          o[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      o[0] += __shfl_xor_sync(0xffffffffu, o[0], 1);
+      const int m = lane >> 1;
+      if ((lane & 1) == 0 && m < mc) p.P[lrow * p.ldp + m0 + m] = o[0];
     }
-    __syncwarp();
   }
 }
 
-template <typename TB, int LPR, int VPL>
+template <typename TB, int LPR, int VPL, bool PROJ>
 __global__ void __launch_bounds__(256) k_spmm(const SpmmParams p) {
   constexpr int E = Vec<TB>::E;
   constexpr int NZP = 32 / LPR;          // non-zeros processed side by side in a warp
@@ -146,13 +175,12 @@ __global__ void __launch_bounds__(256) k_spmm(const SpmmParams p) {
   const int warps_per_block = blockDim.x >> 5;
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  float* smem_w = smem;                                   // [F * n_proj] when staged
-  float* smem_row = nullptr;
-  if (p.P) {
-    const int wfloats = p.wproj_in_smem ? ((p.F * p.n_proj + 3) & ~3) : 0;
-    smem_row = smem + wfloats + wib * ((p.F + 3) & ~3);
-    if (p.wproj_in_smem) {
-      for (int i = threadIdx.x; i < p.F * p.n_proj; i += blockDim.x) smem_w[i] = p.W_proj[i];
+  float* smem_w = smem;                                   // [F][pad4(n_proj)] (+32 floats slack) when staged
+  if (PROJ && p.wproj_in_smem) {
+    const int Ms = (p.n_proj + 3) & ~3;
+    for (int i = threadIdx.x; i < p.F * Ms + 32; i += blockDim.x) {
+      const int c = i / Ms, m = i - c * Ms;
+      smem_w[i] = (c < p.F && m < p.n_proj) ? p.W_proj[c * p.n_proj + m] : 0.0f;
     }
     __syncthreads();
   }
@@ -234,23 +262,22 @@ __global__ void __launch_bounds__(256) k_spmm(const SpmmParams p) {
     }
     return;
   }
-  row_epilogue<LPR, VPL, E>(p, ch.x, lane, acc, smem_row, smem_w);
+  row_epilogue<LPR, VPL, E, PROJ>(p, ch.x, lane, acc, smem_w);
 }
 
 // one warp per split row: add its partial rows in slot order, then the same epilogue
-template <int LPR, int VPL, int E>
+template <int LPR, int VPL, int E, bool PROJ>
 __global__ void __launch_bounds__(256) k_spmm_fixup(const SpmmParams p) {
   extern __shared__ __align__(16) float smem[];
   const int warps_per_block = blockDim.x >> 5;
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  float* smem_w = smem;
-  float* smem_row = nullptr;
-  if (p.P) {
-    const int wfloats = p.wproj_in_smem ? ((p.F * p.n_proj + 3) & ~3) : 0;
-    smem_row = smem + wfloats + wib * ((p.F + 3) & ~3);
-    if (p.wproj_in_smem) {
-      for (int i = threadIdx.x; i < p.F * p.n_proj; i += blockDim.x) smem_w[i] = p.W_proj[i];
+  float* smem_w = smem;                                   // [F][pad4(n_proj)] (+32 floats slack) when staged
+  if (PROJ && p.wproj_in_smem) {
+    const int Ms = (p.n_proj + 3) & ~3;
+    for (int i = threadIdx.x; i < p.F * Ms + 32; i += blockDim.x) {
+      const int c = i / Ms, m = i - c * Ms;
+      smem_w[i] = (c < p.F && m < p.n_proj) ? p.W_proj[c * p.n_proj + m] : 0.0f;
     }
     __syncthreads();
   }
@@ -279,7 +306,7 @@ __global__ void __launch_bounds__(256) k_spmm_fixup(const SpmmParams p) {
       }
     }
   }
-  row_epilogue<LPR, VPL, E>(p, row, lane, acc, smem_row, smem_w);
+  row_epilogue<LPR, VPL, E, PROJ>(p, row, lane, acc, smem_w);
 }
 
 // ---- spmm plan: chunk list ------------------------------------------------------------
@@ -349,25 +376,31 @@ __global__ void __launch_bounds__(1024) k_plan(const int32_t* __restrict__ rowpt
   if (tid == 0) { counts[0] = s_base[0]; counts[1] = s_base[1]; counts[2] = s_base[2]; counts[3] = s_maxlen; }
 }
 
-template <typename TB, int LPR, int VPL>
-static int launch_spmm(const SpmmParams& p, cudaStream_t stream) {
+template <typename TB, int LPR, int VPL, bool PROJ>
+static int launch_spmm_t(const SpmmParams& p, cudaStream_t stream) {
   constexpr int E = Vec<TB>::E;
   const int threads = 256, wpb = threads / 32;
   size_t smem = 0;
-  if (p.P) smem = ((p.wproj_in_smem ? ((p.F * p.n_proj + 3) & ~3) : 0) + wpb * ((p.F + 3) & ~3)) * sizeof(float);
+  if (PROJ && p.wproj_in_smem) smem = ((size_t)p.F * ((p.n_proj + 3) & ~3) + 32) * sizeof(float);
   if (smem > 48 * 1024) {
-    TGCN_CUDA(cudaFuncSetAttribute(k_spmm<TB, LPR, VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TGCN_CUDA(cudaFuncSetAttribute(k_spmm_fixup<LPR, VPL, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TGCN_CUDA(cudaFuncSetAttribute(k_spmm<TB, LPR, VPL, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TGCN_CUDA(cudaFuncSetAttribute(k_spmm_fixup<LPR, VPL, E, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (p.n_chunks > 0) {
-    k_spmm<TB, LPR, VPL><<<(unsigned)cdiv(p.n_chunks, wpb), threads, smem, stream>>>(p);
+    k_spmm<TB, LPR, VPL, PROJ><<<(unsigned)cdiv(p.n_chunks, wpb), threads, smem, stream>>>(p);
     TGCN_LAUNCH_CHECK();
   }
   if (p.n_split_rows > 0) {
-    k_spmm_fixup<LPR, VPL, E><<<(unsigned)cdiv(p.n_split_rows, wpb), threads, smem, stream>>>(p);
+    k_spmm_fixup<LPR, VPL, E, PROJ><<<(unsigned)cdiv(p.n_split_rows, wpb), threads, smem, stream>>>(p);
     TGCN_LAUNCH_CHECK();
   }
   return TGCN_OK;
+}
+
+template <typename TB, int LPR, int VPL>
+static int launch_spmm(const SpmmParams& p, cudaStream_t stream) {
+  if (p.P) return launch_spmm_t<TB, LPR, VPL, true>(p, stream);
+  return launch_spmm_t<TB, LPR, VPL, false>(p, stream);
 }
 
 template <typename TB>
@@ -447,7 +480,7 @@ extern "C" int tgcn_spmm(const tgcn_spmm_args* a, void* stream_) {
   p.keep_mask = a->keep_mask; p.ldmask = a->ldmask;
   p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset; p.philox_offset_dev = a->philox_offset_dev;
   p.W_proj = a->W_proj; p.n_proj = a->n_proj; p.P = a->P; p.ldp = a->ldp;
-  p.wproj_in_smem = (p.P && (size_t)p.F * p.n_proj * sizeof(float) <= 96 * 1024) ? 1 : 0;
+  p.wproj_in_smem = (p.P && (size_t)p.F * ((p.n_proj + 3) & ~3) * sizeof(float) <= 64 * 1024) ? 1 : 0;
   if (a->b_dtype == TGCN_F32) return dispatch_spmm<float>(p, stream);
   return dispatch_spmm<__nv_bfloat16>(p, stream);
 }

@@ -17,7 +17,7 @@ import torch
 
 from . import _native
 
-DEFAULT_CHUNK_NNZ = 512
+DEFAULT_CHUNK_NNZ = 2048
 
 
 def _stream() -> int:
@@ -68,9 +68,9 @@ class GraphCSR:
 
     # ---- SpMM plan ----
     def plan(self, row_begin: int = 0, row_end: Optional[int] = None,
-             chunk_nnz: int = DEFAULT_CHUNK_NNZ) -> SpmmPlan:
+             chunk_nnz: int = DEFAULT_CHUNK_NNZ, sort_chunks: bool = True) -> SpmmPlan:
         row_end = self.n_nodes if row_end is None else row_end
-        key = (row_begin, row_end, chunk_nnz)
+        key = (row_begin, row_end, chunk_nnz, sort_chunks)
         p = self._plans.get(key)
         if p is not None:
             return p
@@ -86,7 +86,13 @@ class GraphCSR:
                                              chunks.data_ptr(), cap, split.data_ptr(), counts.data_ptr(),
                                              None, 0, _stream()))
             n_chunks, n_slots, n_split, max_len = (int(v) for v in counts.cpu().tolist())
-        p = SpmmPlan(row_begin, row_end, chunk_nnz, chunks[:n_chunks], n_chunks, split[:max(n_split, 0)],
+        chunks = chunks[:n_chunks]
+        if sort_chunks and n_chunks > 1:
+            # longest chunks first, neighbours of similar length: the 8 warps of a CTA finish together
+            # (no idle warps holding an SM slot) and the tail of the grid is made of short rows
+            lens = chunks[:, 2] - chunks[:, 1]
+            chunks = chunks[torch.argsort(lens, descending=True, stable=True)].contiguous()
+        p = SpmmPlan(row_begin, row_end, chunk_nnz, chunks, n_chunks, split[:max(n_split, 0)],
                      n_split, n_slots, max_len)
         self._plans[key] = p
         return p

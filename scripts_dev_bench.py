@@ -25,8 +25,10 @@ t = time.time(); gr2 = upload_graph(ei, ea, N); torch.cuda.synchronize(); print(
 print("nnz", gr.nnz)
 from pytextgcn_b200.synthetic import SHAPES
 H, C = SHAPES[shape].hidden, SHAPES[shape].n_classes
-for chunk in (256, 512, 1024, 4096):
-    plan = gr.plan(chunk_nnz=chunk)
+import itertools
+for chunk, srt in itertools.product((256, 512, 1024, 2048), (False, True)):
+    plan = gr.plan(chunk_nnz=chunk, sort_chunks=srt)
+    print("sorted" if srt else "unsorted", end=" ")
     print("chunk", chunk, "n_chunks", plan.n_chunks, "split rows", plan.n_split_rows, "slots", plan.n_slots, "max", plan.max_row_nnz)
     for F in (H, ops.pad4(C)):
         B = torch.randn(N, F, device=dev)
