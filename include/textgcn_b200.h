@@ -120,6 +120,7 @@ typedef struct {
   int32_t drop_mode; float drop_p; const uint8_t* keep_mask; int64_t ldmask;
   uint64_t philox_seed; uint64_t philox_offset;
   const int64_t* philox_offset_dev;   /* optional device counter added to philox_offset (CUDA-graph replays) */
+  int64_t philox_row_offset;          /* added to the CSR row id in the Philox element index (row shards: global id of local row 0) */
   const float* W_proj; int32_t n_proj; float* P; int64_t ldp;       /* optional projection */
 } tgcn_spmm_args;
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);

@@ -31,7 +31,7 @@ class SpmmArgs(C.Structure):
         ("bias", c_void), ("bias_len", C.c_int32),
         ("act", C.c_int32),
         ("drop_mode", C.c_int32), ("drop_p", C.c_float), ("keep_mask", c_void), ("ldmask", C.c_int64),
-        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_offset_dev", c_void),
+        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_offset_dev", c_void), ("philox_row_offset", C.c_int64),
         ("W_proj", c_void), ("n_proj", C.c_int32), ("P", c_void), ("ldp", C.c_int64),
     ]
 

@@ -27,7 +27,7 @@ struct SpmmParams {
   const float* __restrict__ bias; int32_t bias_len;
   int32_t act;
   int32_t drop_mode; float drop_p; float drop_scale; const uint8_t* __restrict__ keep_mask; int64_t ldmask;
-  uint64_t philox_seed; uint64_t philox_offset; const int64_t* __restrict__ philox_offset_dev;
+  uint64_t philox_seed; uint64_t philox_offset; const int64_t* __restrict__ philox_offset_dev; int64_t philox_row_offset;
   const float* __restrict__ W_proj; int32_t n_proj; float* P; int64_t ldp;
   int32_t wproj_in_smem;
 };
@@ -83,7 +83,7 @@ __device__ __forceinline__ void row_epilogue(const SpmmParams& p, int64_t row, i
       } else if (p.drop_mode == TGCN_DROP_PHILOX) {
 #pragma unroll
         for (int q = 0; q < E / 4; ++q) {
-          uint64_t e4 = ((uint64_t)row * (uint64_t)F + (uint64_t)(c0 + 4 * q)) >> 2;
+          uint64_t e4 = ((uint64_t)(row + p.philox_row_offset) * (uint64_t)F + (uint64_t)(c0 + 4 * q)) >> 2;
           uint4 r = philox_quad(e4, p.philox_seed, ph_off);
           z[4 * q + 0] = (u01(r.x) >= p.drop_p) ? z[4 * q + 0] * p.drop_scale : 0.0f;
           z[4 * q + 1] = (u01(r.y) >= p.drop_p) ? z[4 * q + 1] * p.drop_scale : 0.0f;
@@ -478,7 +478,7 @@ extern "C" int tgcn_spmm(const tgcn_spmm_args* a, void* stream_) {
   p.drop_mode = (a->drop_mode != TGCN_DROP_NONE && a->drop_p > 0.0f) ? a->drop_mode : TGCN_DROP_NONE;
   p.drop_p = a->drop_p; p.drop_scale = 1.0f / (1.0f - a->drop_p);
   p.keep_mask = a->keep_mask; p.ldmask = a->ldmask;
-  p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset; p.philox_offset_dev = a->philox_offset_dev;
+  p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset; p.philox_offset_dev = a->philox_offset_dev; p.philox_row_offset = a->philox_row_offset;
   p.W_proj = a->W_proj; p.n_proj = a->n_proj; p.P = a->P; p.ldp = a->ldp;
   p.wproj_in_smem = (p.P && (size_t)p.F * ((p.n_proj + 3) & ~3) * sizeof(float) <= 64 * 1024) ? 1 : 0;
   if (a->b_dtype == TGCN_F32) return dispatch_spmm<float>(p, stream);

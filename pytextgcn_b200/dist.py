@@ -1,0 +1,365 @@
+"""Multi-GPU TextGCN: 1D row partition of A_hat with NCCL all-gathers between layers
+(BASELINE.json north_star "row-partitioned across the 8 GPUs of one box").
+
+Partition.  Rows (= nodes) are dealt to the P ranks in snake order of decreasing nnz, so every
+rank owns ceil(N/P) rows AND (almost exactly) nnz/P non-zeros -- word rows are ~5x heavier than
+document rows, so contiguous ranges cannot balance both.  Nodes are renumbered so that rank r
+owns the contiguous id range [r*n_loc, (r+1)*n_loc) of a padded id space of N_pad = P*n_loc
+ids: every all-gather is then a plain equal-count ncclAllGather straight into the operand
+buffer the next SpMM reads, no packing kernels.  Because X = I, W1's rows are nodes: W1, its
+gradient and its Adam state are sharded by the same partition with no extra traffic.
+
+Per train step (rank r owns rows R_r):
+    all_gather(W1[R_r])  -> SpMM(F=H) + bias/dropout + fused projection   (big: N*H*4 bytes)
+    all_gather(P[R_r])   -> SpMM(F=C) + bias -> masked NLL (global divisor) (small)
+    all_gather(dZ2[R_r]) -> SpMM(F=C)                                     (small)
+    dense backward on R_r -> all_reduce(dW2, db1, db2)                     (tiny)
+    all_gather(dZ1[R_r]) -> SpMM(F=H) = dW1[R_r]                           (big)
+    Adam on the W1 shard (local) and on the replicated small parameters (identical on all ranks)
+A_hat is symmetric for TextGCN graphs, so the backward needs no transpose / reduce-scatter.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .graph import GraphCSR
+
+
+# --------------------------------------------------------------------------------------
+# host-side partition logic (device-agnostic torch ops; covered by the gloo CPU tests)
+# --------------------------------------------------------------------------------------
+class RowPartition:
+    """Snake-order row partition + node renumbering."""
+
+    def __init__(self, row_nnz: torch.Tensor, world: int):
+        n = int(row_nnz.numel())
+        self.n, self.world = n, world
+        self.n_loc = (n + world - 1) // world
+        self.n_pad = self.n_loc * world
+        dev = row_nnz.device
+        order = torch.sort(row_nnz.to(torch.int64), descending=True, stable=True).indices   # heavy rows first
+        k = torch.arange(n, device=dev)
+        blk, pos = k // world, k % world
+        rank = torch.where(blk % 2 == 0, pos, world - 1 - pos)          # snake: 0..P-1, P-1..0, ...
+        new_of_sorted = rank * self.n_loc + blk
+        self.new_id = torch.empty(n, dtype=torch.int64, device=dev)
+        self.new_id[order] = new_of_sorted                                # old id -> new (padded) id
+        self.old_id = torch.full((self.n_pad,), -1, dtype=torch.int64, device=dev)
+        self.old_id[self.new_id] = torch.arange(n, device=dev)           # new id -> old id, -1 = padding
+        self.row_nnz = row_nnz
+
+    def rows_of(self, rank: int) -> torch.Tensor:
+        """Old ids of the rows rank owns, in local order (-1 for padding rows)."""
+        return self.old_id[rank * self.n_loc:(rank + 1) * self.n_loc]
+
+    def nnz_of(self, rank: int) -> int:
+        r = self.rows_of(rank)
+        return int(self.row_nnz[r[r >= 0]].sum().item())
+
+    def to_new(self, x: torch.Tensor, fill=0) -> torch.Tensor:
+        """Permute a per-node tensor [N, ...] into the padded new numbering [N_pad, ...]."""
+        out = torch.full((self.n_pad,) + tuple(x.shape[1:]), fill, dtype=x.dtype, device=x.device)
+        out[self.new_id.to(x.device)] = x
+        return out
+
+    def to_old(self, x: torch.Tensor) -> torch.Tensor:
+        """Inverse of to_new for a [N_pad, ...] tensor."""
+        return x[self.new_id.to(x.device)]
+
+
+def shard_csr(rowptr: torch.Tensor, colidx: torch.Tensor, val: torch.Tensor, part: RowPartition, rank: int):
+    """Rows of rank `rank` out of the global CSR, columns renumbered into the padded id space.
+    Returns (rowptr_loc int32[n_loc+1], colidx_loc int32, val_loc fp32).  Entry order inside a row
+    is kept."""
+    dev = rowptr.device
+    rows = part.rows_of(rank).to(dev)
+    valid = rows >= 0
+    safe = rows.clamp_min(0)
+    rp = rowptr.to(torch.int64)
+    counts = torch.where(valid, rp[safe + 1] - rp[safe], torch.zeros_like(safe))
+    loc_rowptr = torch.zeros(part.n_loc + 1, dtype=torch.int64, device=dev)
+    loc_rowptr[1:] = torch.cumsum(counts, 0)
+    total = int(loc_rowptr[-1].item())
+    starts_loc = torch.repeat_interleave(loc_rowptr[:-1], counts)
+    starts_glob = torch.repeat_interleave(rp[safe], counts)
+    idx = torch.arange(total, device=dev) - starts_loc + starts_glob
+    new_id = part.new_id.to(dev)
+    col_loc = new_id[colidx[idx].to(torch.int64)].to(torch.int32)
+    return loc_rowptr.to(torch.int32), col_loc.contiguous(), val[idx].contiguous()
+
+
+def shard_graph(graph: GraphCSR, part: RowPartition, rank: int) -> GraphCSR:
+    rp, ci, v = shard_csr(graph.rowptr, graph.colidx, graph.val, part, rank)
+    g = GraphCSR(part.n_loc, rp, ci, v, None, None, n_cols=part.n_pad)
+    g._symmetric = True      # the shard is only ever used as rows of the (symmetric) global matrix
+    return g
+
+
+# --------------------------------------------------------------------------------------
+# distributed trainer (one process per GPU, torch.distributed over NCCL)
+# --------------------------------------------------------------------------------------
+class DistTextGCNTrainer:
+    """Row-partitioned counterpart of TextGCNTrainer.  Every rank builds the same global graph
+    (same synthetic generator / same Data), keeps its row shard, and owns W1[R_r] + Adam state."""
+
+    def __init__(self, g, n_classes: int, hidden: int, dropout: float, lr: float, amsgrad: bool,
+                 rank: int, world: int, dev: torch.device, seed: int = 0, betas=(0.9, 0.999), eps: float = 1e-8,
+                 graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None):
+        import torch.distributed as dist
+        from . import ops
+        from .graph import upload_graph
+        self.dist, self.ops = dist, ops
+        self.rank, self.world, self.dev = rank, world, dev
+        n = int(g.x.shape[0])
+        if int(g.x.shape[1]) != n:
+            raise NotImplementedError("the row-partitioned trainer handles x = I (no hierarchy features)")
+        if hidden % 4 != 0:
+            raise NotImplementedError("hidden width must be a multiple of 4")
+        self.n, self.H, self.C, self.Cp = n, hidden, n_classes, ops.pad4(n_classes)
+        self.p, self.lr, self.amsgrad, self.betas, self.eps, self.seed = dropout, lr, amsgrad, betas, eps, seed
+        full = graph if graph is not None else upload_graph(g.edge_index.to(dev), g.edge_attr.to(dev), n)
+        if not full.is_symmetric():
+            raise NotImplementedError("the row-partitioned trainer needs a symmetric A_hat (Text2GraphTransformer graphs are)")
+        row_nnz = (full.rowptr[1:] - full.rowptr[:-1]).to(torch.int64)
+        self.part = RowPartition(row_nnz, world)
+        self.shard = shard_graph(full, self.part, rank)
+        self.nnz_global = full.nnz
+        del full
+        self.plan = self.shard.plan()
+        nl, npad, H, Cp = self.part.n_loc, self.part.n_pad, hidden, self.Cp
+        f32 = dict(dtype=torch.float32, device=dev)
+        # parameters: same init on every rank (same seed), W1 kept in the NEW row order
+        gen = torch.Generator().manual_seed(seed)
+        if init_weights is None:
+            a1, a2 = (6.0 / (n + H)) ** 0.5, (6.0 / (H + n_classes)) ** 0.5
+            W1 = (torch.rand(n, H, generator=gen) * 2 - 1) * a1
+            W2 = (torch.rand(H, n_classes, generator=gen) * 2 - 1) * a2
+            b1, b2 = torch.zeros(H), torch.zeros(n_classes)
+        else:
+            W1, b1, W2, b2 = (init_weights[k].detach().cpu().float() for k in
+                              ("layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias"))
+        self.W1_full = self.part.to_new(W1).to(dev).contiguous()            # [N_pad, H]; rows of other ranks are gathered
+        lo = rank * nl
+        self.W1_loc = self.W1_full[lo:lo + nl]                               # view: this rank's shard (authoritative)
+        self.b1, self.W2, self.b2 = b1.to(dev), W2.to(dev).contiguous(), b2.to(dev)
+        self.small = torch.zeros(H + H * n_classes + n_classes, **f32)       # packed grads of b1, W2, b2 (one all-reduce)
+        self.g_b1 = self.small[:H]
+        self.g_W2 = self.small[H:H + H * n_classes].view(H, n_classes)
+        self.g_b2 = self.small[H + H * n_classes:]
+        self.g_W1 = torch.zeros((nl, H), **f32)
+        def state(t):
+            return [torch.zeros_like(t), torch.zeros_like(t), torch.zeros_like(t) if amsgrad else None]
+        self.st = [state(self.W1_loc), state(self.b1), state(self.W2), state(self.b2)]
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        # activations
+        self.H1d = torch.empty((nl, H), **f32)
+        self.P_full = torch.zeros((npad, Cp), **f32)
+        self.P_loc = self.P_full[lo:lo + nl]
+        self.Z2 = torch.zeros((nl, Cp), **f32)
+        self.dZ2_full = torch.zeros((npad, Cp), **f32)
+        self.dZ2_loc = self.dZ2_full[lo:lo + nl]
+        self.G2 = torch.zeros((nl, Cp), **f32)
+        self.dZ1_full = torch.zeros((npad, H), **f32)
+        self.dZ1_loc = self.dZ1_full[lo:lo + nl]
+        self.loss_part = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.loss_buf = torch.zeros(2, **f32)
+        self.stats = torch.zeros(6, dtype=torch.float64, device=dev)         # packed scalars for one all-reduce
+        self.pred = torch.zeros(nl, dtype=torch.int32, device=dev)
+        self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._nll_ws = torch.empty(2 * ((nl * 4 + 255) // 256 * 256), dtype=torch.uint8, device=dev)
+        self._db_ws = None
+        # labels / masks in the new order, local slices
+        y_new = self.part.to_new(g.y.cpu(), 0)
+        tm_new = self.part.to_new(g.train_mask.cpu(), False)
+        vm_new = self.part.to_new(g.val_mask.cpu(), False)
+        self.y = y_new[lo:lo + nl].to(dev).contiguous()
+        self.train_mask = tm_new[lo:lo + nl].to(dev).contiguous()
+        self.val_mask = vm_new[lo:lo + nl].to(dev).contiguous()
+        self.n_train, self.n_val = int(g.train_mask.sum()), int(g.val_mask.sum())
+        self.w1_stale = True          # W1_full rows of the other ranks need a gather
+        self.collective_bytes_per_step = 0
+
+    # ---- collectives ----
+    def _all_gather(self, full: torch.Tensor, loc: torch.Tensor) -> None:
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(full, loc)      # in place: loc is the rank-th slice of full
+
+    def _gather_w1(self) -> None:
+        if self.w1_stale:
+            self._all_gather(self.W1_full, self.W1_loc)
+            self.w1_stale = False
+
+    def _forward(self, training: bool) -> None:
+        ops = self.ops
+        self._gather_w1()
+        drop = training and self.p > 0
+        ops.spmm(self.shard, self.W1_full, F=self.H, plan=self.plan, out=self.H1d, bias=self.b1,
+                 drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
+                 philox_offset_dev=self.step_dev if drop else None, W_proj=self.W2, P=self.P_loc,
+                 row_id_offset=self.rank * self.part.n_loc)
+        self._all_gather(self.P_full, self.P_loc)
+        ops.spmm(self.shard, self.P_full, F=self.Cp, plan=self.plan, out=self.Z2, bias=self.b2)
+
+    def train_step(self) -> None:
+        ops, dist = self.ops, self.dist
+        self._forward(True)
+        ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2_loc,
+                       loss_out=self.loss_buf, workspace=self._nll_ws, partial=self.loss_part)
+        self._all_gather(self.dZ2_full, self.dZ2_loc)
+        ops.spmm(self.shard, self.dZ2_full, F=self.Cp, plan=self.plan, out=self.G2)
+        drop = self.p > 0
+        r = ops.dense_bwd(self.G2, self.H1d, self.W2, self.dZ2_loc, H=self.H, n_classes=self.C,
+                          drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
+                          philox_offset_dev=self.step_dev if drop else None, row_offset=self.rank * self.part.n_loc,
+                          dZ1=self.dZ1_loc, workspace=self._db_ws, dW2=self.g_W2, db_hidden=self.g_b1, db_out=self.g_b2)
+        self._db_ws = r["workspace"]
+        if self.world > 1:
+            dist.all_reduce(self.small)
+        self._all_gather(self.dZ1_full, self.dZ1_loc)
+        ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1)
+        ops.increment_step(self.step_dev)
+        kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad,
+                  step_dev=self.step_dev)
+        ops.adam_step(self.W1_loc, self.g_W1, *self.st[0], **kw)
+        ops.adam_step(self.b1, self.g_b1.contiguous(), *self.st[1], **kw)
+        ops.adam_step(self.W2, self.g_W2, *self.st[2], **kw)
+        ops.adam_step(self.b2, self.g_b2.contiguous(), *self.st[3], **kw)
+        self.w1_stale = True
+
+    def eval_step(self) -> None:
+        ops = self.ops
+        self._forward(False)
+        ops.masked_nll(self.Z2, self.C, self.y, self.val_mask, max(self.n_val, 1), want_grad=False,
+                       loss_out=self.loss_buf, workspace=self._nll_ws, pred=self.pred, correct=self.correct,
+                       partial=self.loss_part)
+
+    def epoch_stats(self) -> Dict[str, float]:
+        """Global (all-reduced) train loss of the last train step is not kept here; this returns the
+        val loss / accuracy of the last eval_step."""
+        s = torch.stack([self.loss_part[0], self.correct[0].double()])
+        if self.world > 1:
+            self.dist.all_reduce(s)
+        v = s.cpu().tolist()
+        return dict(val_loss=v[0] / max(self.n_val, 1), acc_val=v[1] / max(self.n_val, 1))
+
+    def train_loss(self) -> float:
+        s = self.loss_part[:1].clone()
+        if self.world > 1:
+            self.dist.all_reduce(s)
+        return float(s.item()) / self.n_train
+
+    def gathered_parameters(self) -> Dict[str, torch.Tensor]:
+        """Parameters in the ORIGINAL node order (reference layout: layers.{i}.weight (in,out), bias)."""
+        self._gather_w1()
+        return {"layers.0.weight": self.part.to_old(self.W1_full), "layers.0.bias": self.b1,
+                "layers.1.weight": self.W2, "layers.1.bias": self.b2}
+
+    def logits_old_order(self) -> torch.Tensor:
+        """All-gathered logits of the last forward, original node order (host-facing helper)."""
+        full = torch.zeros((self.part.n_pad, self.Cp), dtype=torch.float32, device=self.dev)
+        self._all_gather(full, self.Z2.contiguous())
+        return self.part.to_old(full)[:, :self.C]
+
+    def bytes_per_train_step(self) -> int:
+        """Bytes each rank RECEIVES per train step (+ the W1 gather that precedes the forward)."""
+        P, nl = self.world, self.part.n_loc
+        big = (P - 1) * nl * self.H * 4
+        small = (P - 1) * nl * self.Cp * 4
+        return 2 * big + 2 * small + 2 * self.small.numel() * 4
+
+
+# --------------------------------------------------------------------------------------
+# bench entry for N > 1 (called by bench.py under torchrun)
+# --------------------------------------------------------------------------------------
+def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: torch.device):
+    import numpy as np
+    import torch.distributed as dist
+    from . import _native
+    from .synthetic import SHAPES, make_graph
+    lib = _native.load()
+    shape = SHAPES[args.workload]
+    K, W = args.steps, max(args.warmup, 3)
+    g = make_graph(shape, seed=args.seed)          # same graph on every rank (same seed)
+    n = int(g.x.shape[0])
+    tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad,
+                            rank, world, dev, seed=args.seed)
+
+    def epoch():
+        tr.train_step()
+        tr.eval_step()
+
+    for _ in range(W):
+        epoch()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = None
+    if rank == 0:
+        from bench import ClockSampler
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+    l0 = lib.tgcn_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev0.record()
+    for _ in range(K):
+        epoch()
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = int(lib.tgcn_launch_count() - l0)
+    ms_per_step = float(ms.item()) / K
+
+    # e2e: labels/masks from pinned host memory each epoch, losses + local argmax read back
+    nl = tr.part.n_loc
+    y_pin, tm_pin, vm_pin = tr.y.cpu().pin_memory(), tr.train_mask.cpu().pin_memory(), tr.val_mask.cpu().pin_memory()
+    pred_pin = torch.empty(nl, dtype=torch.int32).pin_memory()
+
+    def epoch_e2e():
+        tr.y.copy_(y_pin, non_blocking=True)
+        tr.train_mask.copy_(tm_pin, non_blocking=True)
+        tr.val_mask.copy_(vm_pin, non_blocking=True)
+        tr.train_step()
+        tr.eval_step()
+        pred_pin.copy_(tr.pred, non_blocking=True)
+        return tr.epoch_stats()                      # all-reduce + D2H of the global val loss / accuracy
+    for _ in range(2):
+        epoch_e2e()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        last = epoch_e2e()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / K], device=dev, dtype=torch.float64)
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    nnz_loc = torch.tensor([tr.shard.nnz], device=dev, dtype=torch.float64)
+    nnz_all = [torch.zeros_like(nnz_loc) for _ in range(world)]
+    dist.all_gather(nnz_all, nnz_loc)
+    if rank == 0:
+        from bench import METRIC, UNIT, workload_config
+        clocks = sampler.stop()
+        cfg = workload_config(shape, g)
+        cfg["parallelism"] = f"1D row partition x{world} (snake order by nnz), NCCL all_gather_into_tensor between layers"
+        line = {
+            "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+            "e2e": {"value": 1e3 / float(e2e.item()), "unit": UNIT, "h2d_bytes_per_step": int(nl * 10) * world,
+                    "d2h_bytes_per_step": int(nl * 4 + 16) * world, "ms_per_step": float(e2e.item())},
+            "gpu_launches": launches,
+            "extra": {"nnz_per_rank": [int(t.item()) for t in nnz_all], "rows_per_rank": nl,
+                      "collective_bytes_received_per_rank_per_train_step": tr.bytes_per_train_step(),
+                      "last_epoch": last, "cuda_graph": False},
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -52,8 +52,9 @@ class GraphCSR:
     """Device-resident CSR of A_hat = D^-1/2 (A+I) D^-1/2, rows = target nodes."""
 
     def __init__(self, n_nodes: int, rowptr: torch.Tensor, colidx: torch.Tensor, val: torch.Tensor,
-                 dis: torch.Tensor, edge_slot: Optional[torch.Tensor] = None):
-        self.n_nodes = n_nodes
+                 dis: Optional[torch.Tensor], edge_slot: Optional[torch.Tensor] = None, n_cols: Optional[int] = None):
+        self.n_nodes = n_nodes                     # rows of this CSR
+        self.n_cols = n_nodes if n_cols is None else n_cols   # > n_nodes for a row shard (1D partition)
         self.rowptr = rowptr
         self.colidx = colidx
         self.val = val

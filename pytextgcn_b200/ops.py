@@ -47,7 +47,7 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
          out_dtype: Optional[torch.dtype] = None, plan: Optional[SpmmPlan] = None,
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          drop_mode: int = DROP_NONE, drop_p: float = 0.0, keep_mask: Optional[torch.Tensor] = None,
-         philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[torch.Tensor] = None,
+         philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0,
          W_proj: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
          want_out: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """C = epi(A_hat[rows of plan] @ B[:, :F]) (+ P = C @ W_proj).  See tgcn_spmm.
@@ -62,8 +62,8 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
     n_out = plan.row_end - plan.row_begin
     if B.dim() != 2 or B.stride(1) != 1:
         raise RuntimeError("spmm: B must be a 2-D row-major tensor")
-    if B.shape[0] < graph.n_nodes:
-        raise RuntimeError(f"spmm: B has {B.shape[0]} rows, the graph has {graph.n_nodes} nodes")
+    if B.shape[0] < graph.n_cols:
+        raise RuntimeError(f"spmm: B has {B.shape[0]} rows, the graph has {graph.n_cols} columns")
     a = _native.SpmmArgs()
     a.rowptr, a.colidx, a.val = graph.rowptr.data_ptr(), graph.colidx.data_ptr(), graph.val.data_ptr()
     a.chunks, a.n_chunks = plan.chunks.data_ptr(), plan.n_chunks
@@ -92,6 +92,7 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
         a.keep_mask, a.ldmask = keep_mask.data_ptr(), keep_mask.stride(0)
     a.philox_seed, a.philox_offset = philox_seed & (2**64 - 1), philox_offset & (2**64 - 1)
     a.philox_offset_dev = _native.ptr(philox_offset_dev)
+    a.philox_row_offset = int(row_id_offset)
     if W_proj is not None:
         if W_proj.dtype != torch.float32 or not W_proj.is_contiguous() or W_proj.shape[0] != F:
             raise RuntimeError("spmm: W_proj must be a contiguous fp32 [F, n_proj] tensor")
@@ -108,7 +109,8 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
                *, want_grad: bool = True, dZ: Optional[torch.Tensor] = None, want_pred: bool = False,
                want_correct: bool = False, loss_out: Optional[torch.Tensor] = None,
                workspace: Optional[torch.Tensor] = None, pred: Optional[torch.Tensor] = None,
-               correct: Optional[torch.Tensor] = None, want_partial: bool = False):
+               correct: Optional[torch.Tensor] = None, want_partial: bool = False,
+               partial: Optional[torch.Tensor] = None):
     """Masked mean cross-entropy over rows of Z (+ gradient / argmax / #correct).  See tgcn_masked_nll.
     Returns dict(loss=[2] fp32 (mean nll, count), dZ, pred, correct, partial)."""
     _need_cuda(Z, y, mask, dZ)
@@ -123,7 +125,8 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
     dev = Z.device
     if loss_out is None:
         loss_out = torch.empty(2, dtype=torch.float32, device=dev)
-    partial = torch.empty(2, dtype=torch.float64, device=dev) if want_partial else None
+    if partial is None and want_partial:
+        partial = torch.empty(2, dtype=torch.float64, device=dev)
     if want_grad and dZ is None:
         dZ = torch.zeros((n, pad4(n_classes)), dtype=torch.float32, device=dev)
     if pred is None and want_pred:

@@ -1,0 +1,144 @@
+"""Host-side logic of the multi-GPU path on CPU: the snake row partition, CSR sharding into the
+padded id space, and -- under a real 2-process gloo group -- the exact collective sequence of
+DistTextGCNTrainer (all_gather_into_tensor between layers, all_reduce of the small gradients)
+with the local SpMMs emulated by torch CPU index ops, checked against the single-process oracle."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import rel_err
+from oracle import gcn_oracle as O
+from pytextgcn_b200.dist import RowPartition, shard_csr
+from pytextgcn_b200.synthetic import make_graph, GraphShape
+
+SHAPE = GraphShape("t", 300, 257, 5000, 14, 5, 16)     # N = 557: not divisible by 2 or 4 -> padding rows
+
+
+def _global_csr(g):
+    n = int(g.x.shape[0])
+    rowptr, col, val, dis, _ = O.csr_from_gcn_norm(g.edge_index, g.edge_attr, n)
+    return n, rowptr, col, val
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_partition_balances_rows_and_nnz(world):
+    g = make_graph(SHAPE, seed=0)
+    n, rowptr, col, val = _global_csr(g)
+    row_nnz = rowptr[1:] - rowptr[:-1]
+    part = RowPartition(row_nnz, world)
+    assert part.n_pad == part.n_loc * world and part.n_pad >= n
+    # bijection between old ids and the non-padding new ids
+    assert torch.equal(torch.sort(part.new_id).values, torch.sort(part.old_id[part.old_id >= 0] * 0 +
+                                                                 torch.nonzero(part.old_id >= 0).view(-1)).values)
+    assert torch.equal(part.old_id[part.new_id], torch.arange(n))
+    nnz = [part.nnz_of(r) for r in range(world)]
+    assert sum(nnz) == int(row_nnz.sum())
+    assert max(nnz) - min(nnz) <= 2 * int(row_nnz.max())            # snake order: imbalance bounded by ~one heavy row
+    x = torch.randn(n, 3)
+    assert torch.equal(part.to_old(part.to_new(x)), x)
+
+
+def _local_spmm(rp, ci, v, B):
+    rows = torch.repeat_interleave(torch.arange(rp.numel() - 1), (rp[1:] - rp[:-1]).long())
+    out = torch.zeros(rp.numel() - 1, B.shape[1], dtype=B.dtype)
+    out.index_add_(0, rows, v.to(B.dtype).view(-1, 1) * B[ci.long()])
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_spmm_equals_global(world):
+    g = make_graph(SHAPE, seed=1)
+    n, rowptr, col, val = _global_csr(g)
+    part = RowPartition(rowptr[1:] - rowptr[:-1], world)
+    B = torch.randn(n, 8, dtype=torch.float64)
+    ref = _local_spmm(rowptr, col, val, B)
+    Bn = part.to_new(B)
+    outs = []
+    for r in range(world):
+        rp, ci, v = shard_csr(rowptr, col, val, part, r)
+        assert rp.numel() == part.n_loc + 1 and int(ci.max()) < part.n_pad
+        outs.append(_local_spmm(rp, ci, v, Bn))
+    assert rel_err(part.to_old(torch.cat(outs)), ref) < 1e-12
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        g = make_graph(SHAPE, seed=2)
+        n, rowptr, col, val = _global_csr(g)
+        H, C = SHAPE.hidden, SHAPE.n_classes
+        part = RowPartition(rowptr[1:] - rowptr[:-1], world)
+        rp, ci, v = shard_csr(rowptr, col, val, part, rank)
+        nl, lo = part.n_loc, rank * part.n_loc
+        W1 = torch.randn(n, H, dtype=torch.float64) * 0.2
+        b1 = torch.randn(H, dtype=torch.float64) * 0.1
+        W2 = torch.randn(H, C, dtype=torch.float64) * 0.2
+        b2 = torch.randn(C, dtype=torch.float64) * 0.1
+        y = part.to_new(g.y)[lo:lo + nl]
+        tm = part.to_new(g.train_mask, False)[lo:lo + nl]
+        n_train = int(g.train_mask.sum())
+        # --- the collective sequence of DistTextGCNTrainer.train_step (dropout off) ---
+        W1_full = torch.zeros(part.n_pad, H, dtype=torch.float64)
+        W1_full[lo:lo + nl] = part.to_new(W1)[lo:lo + nl]                      # only the own shard is valid
+        dist.all_gather_into_tensor(W1_full, W1_full[lo:lo + nl].clone())
+        H1 = _local_spmm(rp, ci, v, W1_full) + b1
+        P_full = torch.zeros(part.n_pad, C, dtype=torch.float64)
+        dist.all_gather_into_tensor(P_full, (H1 @ W2).contiguous())
+        Z2 = _local_spmm(rp, ci, v, P_full) + b2
+        logp = torch.log_softmax(Z2, dim=1)
+        dZ2 = torch.zeros_like(Z2)
+        rows = torch.nonzero(tm).view(-1)
+        dZ2[rows] = torch.exp(logp[rows])
+        dZ2[rows, y[rows]] -= 1.0
+        dZ2 /= n_train
+        loss_part = -logp[rows, y[rows]].sum().view(1)
+        dZ2_full = torch.zeros(part.n_pad, C, dtype=torch.float64)
+        dist.all_gather_into_tensor(dZ2_full, dZ2.contiguous())
+        G2 = _local_spmm(rp, ci, v, dZ2_full)
+        small = torch.cat([(G2 @ W2.T).sum(0), (H1.T @ G2).reshape(-1), dZ2.sum(0)])   # db1, dW2, db2
+        dist.all_reduce(small)
+        dist.all_reduce(loss_part)
+        dZ1_full = torch.zeros(part.n_pad, H, dtype=torch.float64)
+        dist.all_gather_into_tensor(dZ1_full, (G2 @ W2.T).contiguous())
+        gW1_loc = _local_spmm(rp, ci, v, dZ1_full)
+        gW1_full = torch.zeros(part.n_pad, H, dtype=torch.float64)
+        dist.all_gather_into_tensor(gW1_full, gW1_loc.contiguous())
+        if rank == 0:
+            # --- single-process oracle ---
+            Wr = [W1.clone().requires_grad_(), W2.clone().requires_grad_()]
+            br = [b1.clone().requires_grad_(), b2.clone().requires_grad_()]
+            z = O.gcn_forward(g.x.double(), g.edge_index, g.edge_attr.double(), Wr, br)
+            loss = O.masked_cross_entropy(z, g.y, g.train_mask)
+            loss.backward()
+            res = dict(loss=abs(loss_part.item() / n_train - loss.item()),
+                       gW1=rel_err(part.to_old(gW1_full), Wr[0].grad),
+                       db1=rel_err(small[:H], br[0].grad), dW2=rel_err(small[H:H + H * C].view(H, C), Wr[1].grad),
+                       db2=rel_err(small[H + H * C:], br[1].grad))
+            q.put(res)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_collective_sequence_matches_oracle():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # fp64 emulation: only the edge values (fp32 A_hat) limit the agreement
+    assert res["loss"] < 1e-6
+    for k in ("gW1", "db1", "dW2", "db2"):
+        assert res[k] < 1e-5, (k, res[k])

@@ -1,0 +1,63 @@
+"""GPU tests of the row-partitioned trainer.  world_size 1 runs everywhere (it exercises the node
+renumbering, padding rows and the sharded kernels' row offsets); the 2-rank NCCL run needs >= 2
+GPUs and is skipped on a single-GPU box (the CPU/gloo version of it is tests/test_dist_cpu.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import gcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_world_size_one_matches_oracle(cuda):
+    from pytextgcn_b200.dist import DistTextGCNTrainer
+    from pytextgcn_b200.synthetic import make_graph, GraphShape
+    shape = GraphShape("t", 700, 555, 12000, 20, 6, 64)
+    g = make_graph(shape, seed=3)
+    n = int(g.x.shape[0])
+    torch.manual_seed(0)
+    ref = O.OracleGCN(n, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=0.0)
+    init = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, 0.0, 0.01, True, 0, 1, cuda, seed=0, init_weights=init)
+    opt = torch.optim.Adam(ref.parameters(), lr=0.01, amsgrad=True)
+    for step in range(3):
+        out_ref = O.reference_epoch(ref, g, opt)
+        tr.train_step()
+        assert abs(tr.train_loss() - out_ref[0]) < 1e-5 * max(1, abs(out_ref[0]))
+        assert rel_err(tr.part.to_old(tr.g_W1), ref.layers[0].weight.grad) < 2e-5 * (step + 1)
+        assert rel_err(tr.g_W2, ref.layers[1].weight.grad) < 2e-5 * (step + 1)
+        tr.eval_step()
+        st = tr.epoch_stats()
+        assert abs(st["val_loss"] - out_ref[1]) < 1e-4 * max(1, abs(out_ref[1]))
+        assert abs(st["acc_val"] - out_ref[3]) < 0.02
+    z = tr.logits_old_order()
+    ref.eval()
+    with torch.no_grad():
+        assert rel_err(z, ref(g)) < 1e-4
+
+
+def test_dropout_mask_consistent_between_forward_and_backward_on_a_shard(cuda):
+    from pytextgcn_b200.dist import DistTextGCNTrainer
+    from pytextgcn_b200.synthetic import make_graph, GraphShape
+    shape = GraphShape("t", 400, 333, 6000, 20, 6, 32)
+    g = make_graph(shape, seed=4)
+    tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, 0.5, 0.0, False, 0, 1, cuda, seed=5)
+    for _ in range(3):
+        tr.train_step()
+        dropped = tr.H1d == 0
+        assert torch.all(tr.dZ1_loc[dropped] == 0)
+        assert abs((~dropped).float().mean().item() - 0.5) < 0.02
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_nccl_matches_oracle():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29633", os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "DIST_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
