@@ -188,6 +188,8 @@ class DistTextGCNTrainer:
     def _all_gather(self, full: torch.Tensor, loc: torch.Tensor) -> None:
         if self.world > 1:
             self.dist.all_gather_into_tensor(full, loc)      # in place: loc is the rank-th slice of full
+        elif full.data_ptr() != loc.data_ptr():
+            full[:loc.shape[0]].copy_(loc)
 
     def _gather_w1(self) -> None:
         if self.w1_stale:
