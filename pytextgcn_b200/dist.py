@@ -109,7 +109,8 @@ class DistTextGCNTrainer:
 
     def __init__(self, g, n_classes: int, hidden: int, dropout: float, lr: float, amsgrad: bool,
                  rank: int, world: int, dev: torch.device, seed: int = 0, betas=(0.9, 0.999), eps: float = 1e-8,
-                 graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None):
+                 graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None,
+                 use_cuda_graph: bool = False):
         import torch.distributed as dist
         from . import ops
         from .graph import upload_graph
@@ -182,7 +183,11 @@ class DistTextGCNTrainer:
         self.val_mask = vm_new[lo:lo + nl].to(dev).contiguous()
         self.n_train, self.n_val = int(g.train_mask.sum()), int(g.val_mask.sum())
         self.w1_stale = True          # W1_full rows of the other ranks need a gather
-        self.collective_bytes_per_step = 0
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._eager_epochs = 0
+        self.graph_error = None
+        self.launches_per_epoch = 0
 
     # ---- collectives ----
     def _all_gather(self, full: torch.Tensor, loc: torch.Tensor) -> None:
@@ -240,6 +245,44 @@ class DistTextGCNTrainer:
                        loss_out=self.loss_buf, workspace=self._nll_ws, pred=self.pred, correct=self.correct,
                        partial=self.loss_part)
 
+    def epoch(self) -> None:
+        """train_step + eval_step; after two eager epochs the pair is captured (kernels AND the NCCL
+        collectives) in one CUDA graph and replayed -- at 8 ranks the ~60 launches of an epoch would
+        otherwise cost more host time than the GPUs need to run them."""
+        if not self.use_cuda_graph:
+            self.train_step()
+            self.eval_step()
+            return
+        if self._graph is not None:
+            self._graph.replay()
+            return
+        if self._eager_epochs < 2:
+            from . import _native
+            lib = _native.load()
+            c0 = lib.tgcn_launch_count()
+            self.train_step()
+            self.eval_step()
+            self.launches_per_epoch = int(lib.tgcn_launch_count() - c0)
+            self._eager_epochs += 1
+            return
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+        try:
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                self.train_step()
+                self.eval_step()
+            self._graph = gph
+        except Exception as e:      # capture of the collectives not supported in this stack: stay eager
+            self.use_cuda_graph = False
+            self.graph_error = repr(e)
+            torch.cuda.synchronize(self.dev)
+            self.train_step()
+            self.eval_step()
+            return
+        self._graph.replay()
+
     def epoch_stats(self) -> Dict[str, float]:
         """Global (all-reduced) train loss of the last train step is not kept here; this returns the
         val loss / accuracy of the last eval_step."""
@@ -275,6 +318,34 @@ class DistTextGCNTrainer:
         return 2 * big + 2 * small + 2 * self.small.numel() * 4
 
 
+def shutdown(trainer: Optional["DistTextGCNTrainer"] = None) -> None:
+    """Orderly exit of a rank.  Graphs that captured NCCL collectives must be released before the
+    communicator is torn down (destroy_process_group with such a graph alive hangs with NCCL 2.28 /
+    torch 2.11); if teardown still stalls, leave without it -- the work is done and flushed."""
+    import gc
+    import sys
+    import threading
+    import torch.distributed as dist
+    if trainer is not None:
+        trainer._graph = None
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    done = threading.Event()
+
+    def _destroy():
+        try:
+            dist.destroy_process_group()
+        finally:
+            done.set()
+    t = threading.Thread(target=_destroy, daemon=True)
+    t.start()
+    if not done.wait(timeout=20):
+        os._exit(0)
+
+
 # --------------------------------------------------------------------------------------
 # bench entry for N > 1 (called by bench.py under torchrun)
 # --------------------------------------------------------------------------------------
@@ -289,11 +360,8 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
     g = make_graph(shape, seed=args.seed)          # same graph on every rank (same seed)
     n = int(g.x.shape[0])
     tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad,
-                            rank, world, dev, seed=args.seed)
-
-    def epoch():
-        tr.train_step()
-        tr.eval_step()
+                            rank, world, dev, seed=args.seed, use_cuda_graph=not getattr(args, "no_cuda_graph", False))
+    epoch = tr.epoch
 
     for _ in range(W):
         epoch()
@@ -317,6 +385,8 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = int(lib.tgcn_launch_count() - l0)
+    if tr._graph is not None:
+        launches = tr.launches_per_epoch * K
     ms_per_step = float(ms.item()) / K
 
     # e2e: labels/masks from pinned host memory each epoch, losses + local argmax read back
@@ -328,8 +398,7 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
         tr.y.copy_(y_pin, non_blocking=True)
         tr.train_mask.copy_(tm_pin, non_blocking=True)
         tr.val_mask.copy_(vm_pin, non_blocking=True)
-        tr.train_step()
-        tr.eval_step()
+        tr.epoch()
         pred_pin.copy_(tr.pred, non_blocking=True)
         return tr.epoch_stats()                      # all-reduce + D2H of the global val loss / accuracy
     for _ in range(2):
@@ -360,8 +429,7 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
             "gpu_launches": launches,
             "extra": {"nnz_per_rank": [int(t.item()) for t in nnz_all], "rows_per_rank": nl,
                       "collective_bytes_received_per_rank_per_train_step": tr.bytes_per_train_step(),
-                      "last_epoch": last, "cuda_graph": False},
+                      "last_epoch": last, "cuda_graph": tr._graph is not None, "cuda_graph_error": tr.graph_error},
         }
         print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
+    shutdown(tr)
