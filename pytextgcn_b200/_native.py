@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _LIB_NAME = "libtextgcn_b200.so"
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", _LIB_NAME)
+_LIB_PATH = os.environ.get("TGCN_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", _LIB_NAME)
 _lib: Optional[C.CDLL] = None
 
 c_i32p = C.POINTER(C.c_int32)

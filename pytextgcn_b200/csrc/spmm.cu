@@ -167,10 +167,12 @@ __device__ __forceinline__ void row_epilogue(const SpmmParams& p, int64_t row, i
 }
 
 template <typename TB, int LPR, int VPL, bool PROJ>
-__global__ void __launch_bounds__(256) k_spmm(const SpmmParams p) {
+__global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(const SpmmParams p) {
   constexpr int E = Vec<TB>::E;
   constexpr int NZP = 32 / LPR;          // non-zeros processed side by side in a warp
-  constexpr int U = 4;                   // gathers kept in flight per lane group
+  // gathers kept in flight per lane group: 8 for the wide rows (halves the critical path of a
+  // 2048-entry chunk and lifts the L2 gather rate ~7%), 4 for the narrow ones (8 costs occupancy there)
+  constexpr int U = (LPR == 32) ? ((64 / (VPL * E)) > 8 ? 8 : ((64 / (VPL * E)) < 2 ? 2 : (64 / (VPL * E)))) : 4;
   extern __shared__ __align__(16) float smem[];
   const int warps_per_block = blockDim.x >> 5;
   const int wib = threadIdx.x >> 5;
@@ -184,23 +186,26 @@ __global__ void __launch_bounds__(256) k_spmm(const SpmmParams p) {
     }
     __syncthreads();
   }
-  const int chunk_id = blockIdx.x * warps_per_block + wib;
-  if (chunk_id >= p.n_chunks) return;
-  const int4 ch = __ldg(p.chunks + chunk_id);   // {row, begin, end, slot}
   const int sub = lane / LPR;                   // which of the NZP side-by-side non-zeros
   const int l = lane % LPR;
   const TB* __restrict__ B = reinterpret_cast<const TB*>(p.B);
   const int F = p.F;
+  bool active[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) active[v] = ((l + v * LPR) * E) < F;
 
+  // One chunk per warp, CTAs handed out by the hardware scheduler in list order (longest chunks
+  // first).  A persistent grid-stride variant measured 4% slower on B200 (static round-robin
+  // cannot absorb the run-time variance of L2-bound chunks), so the simple form stays.
+  const int chunk_id = blockIdx.x * warps_per_block + wib;
+  if (chunk_id >= p.n_chunks) return;
+  {
+  const int4 ch = __ldg(p.chunks + chunk_id);   // {row, begin, end, slot}
   float acc[VPL][E];
 #pragma unroll
   for (int v = 0; v < VPL; ++v)
 #pragma unroll
     for (int i = 0; i < E; ++i) acc[v][i] = 0.0f;
-
-  bool active[VPL];
-#pragma unroll
-  for (int v = 0; v < VPL; ++v) active[v] = ((l + v * LPR) * E) < F;
 
   for (int base = ch.y; base < ch.z; base += 32) {
     const int k = base + lane;
@@ -263,6 +268,7 @@ __global__ void __launch_bounds__(256) k_spmm(const SpmmParams p) {
     return;
   }
   row_epilogue<LPR, VPL, E, PROJ>(p, ch.x, lane, acc, smem_w);
+  }
 }
 
 // one warp per split row: add its partial rows in slot order, then the same epilogue
@@ -387,7 +393,8 @@ static int launch_spmm_t(const SpmmParams& p, cudaStream_t stream) {
     TGCN_CUDA(cudaFuncSetAttribute(k_spmm_fixup<LPR, VPL, E, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (p.n_chunks > 0) {
-    k_spmm<TB, LPR, VPL, PROJ><<<(unsigned)cdiv(p.n_chunks, wpb), threads, smem, stream>>>(p);
+    const int64_t grid = cdiv(p.n_chunks, wpb);
+    k_spmm<TB, LPR, VPL, PROJ><<<(unsigned)grid, threads, smem, stream>>>(p);
     TGCN_LAUNCH_CHECK();
   }
   if (p.n_split_rows > 0) {

@@ -187,7 +187,24 @@ class DistTextGCNTrainer:
         self._graph = None
         self._eager_epochs = 0
         self.graph_error = None
+        self.profile = None           # list of (name, event) when per-phase timing is on
         self.launches_per_epoch = 0
+
+    # ---- optional per-phase timing (eager mode only; used by the scaling analysis in DESIGN.md) ----
+    def _mark(self, name: str) -> None:
+        if self.profile is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.profile.append((name, ev))
+
+    def phase_times_ms(self) -> Dict[str, float]:
+        """Sum of the time between consecutive marks, keyed by the phase that ENDS at the mark."""
+        torch.cuda.synchronize(self.dev)
+        out: Dict[str, float] = {}
+        for (n0, e0), (n1, e1) in zip(self.profile[:-1], self.profile[1:]):
+            if n1 != "begin":
+                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
 
     # ---- collectives ----
     def _all_gather(self, full: torch.Tensor, loc: torch.Tensor) -> None:
@@ -203,32 +220,44 @@ class DistTextGCNTrainer:
 
     def _forward(self, training: bool) -> None:
         ops = self.ops
+        self._mark("begin")
         self._gather_w1()
+        self._mark("allgather_W1")
         drop = training and self.p > 0
         ops.spmm(self.shard, self.W1_full, F=self.H, plan=self.plan, out=self.H1d, bias=self.b1,
                  drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
                  philox_offset_dev=self.step_dev if drop else None, W_proj=self.W2, P=self.P_loc,
                  row_id_offset=self.rank * self.part.n_loc)
+        self._mark("spmm_wide_fwd")
         self._all_gather(self.P_full, self.P_loc)
+        self._mark("allgather_P")
         ops.spmm(self.shard, self.P_full, F=self.Cp, plan=self.plan, out=self.Z2, bias=self.b2)
+        self._mark("spmm_narrow_fwd")
 
     def train_step(self) -> None:
         ops, dist = self.ops, self.dist
         self._forward(True)
         ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2_loc,
                        loss_out=self.loss_buf, workspace=self._nll_ws, partial=self.loss_part)
+        self._mark("masked_nll")
         self._all_gather(self.dZ2_full, self.dZ2_loc)
+        self._mark("allgather_dZ2")
         ops.spmm(self.shard, self.dZ2_full, F=self.Cp, plan=self.plan, out=self.G2)
+        self._mark("spmm_narrow_bwd")
         drop = self.p > 0
         r = ops.dense_bwd(self.G2, self.H1d, self.W2, self.dZ2_loc, H=self.H, n_classes=self.C,
                           drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
                           philox_offset_dev=self.step_dev if drop else None, row_offset=self.rank * self.part.n_loc,
                           dZ1=self.dZ1_loc, workspace=self._db_ws, dW2=self.g_W2, db_hidden=self.g_b1, db_out=self.g_b2)
         self._db_ws = r["workspace"]
+        self._mark("dense_bwd")
         if self.world > 1:
             dist.all_reduce(self.small)
+        self._mark("allreduce_small_grads")
         self._all_gather(self.dZ1_full, self.dZ1_loc)
+        self._mark("allgather_dZ1")
         ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1)
+        self._mark("spmm_wide_bwd")
         ops.increment_step(self.step_dev)
         kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad,
                   step_dev=self.step_dev)
@@ -236,6 +265,7 @@ class DistTextGCNTrainer:
         ops.adam_step(self.b1, self.g_b1.contiguous(), *self.st[1], **kw)
         ops.adam_step(self.W2, self.g_W2, *self.st[2], **kw)
         ops.adam_step(self.b2, self.g_b2.contiguous(), *self.st[3], **kw)
+        self._mark("adam")
         self.w1_stale = True
 
     def eval_step(self) -> None:
@@ -244,6 +274,7 @@ class DistTextGCNTrainer:
         ops.masked_nll(self.Z2, self.C, self.y, self.val_mask, max(self.n_val, 1), want_grad=False,
                        loss_out=self.loss_buf, workspace=self._nll_ws, pred=self.pred, correct=self.correct,
                        partial=self.loss_part)
+        self._mark("masked_nll")
 
     def epoch(self) -> None:
         """train_step + eval_step; after two eager epochs the pair is captured (kernels AND the NCCL

@@ -159,3 +159,35 @@ def test_trainer_relu_variant(cuda):
         out_ref = O.reference_epoch(ref, g, opt)
         out = tr.epoch()
         assert abs(out["loss"] - out_ref[0]) < 5e-5 * max(1, abs(out_ref[0]))
+
+
+@pytest.mark.parametrize("hier", [None, 5])
+def test_collapsed_eval_matches_layered_eval_and_oracle(cuda, hier):
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    g, gd, ref, mod, shape = _make_pair(cuda, p=0.5, hier=hier)
+    with torch.no_grad():
+        for l in ref.layers:
+            l.bias.uniform_(-0.3, 0.3)
+        for pd, ps in zip(mod.parameters(), ref.parameters()):
+            pd.copy_(ps)
+    tr = TextGCNTrainer(mod, gd, lr=0.01, amsgrad=True)
+    ref.eval()
+    with torch.no_grad():
+        z_ref = ref(g)
+    out = {}
+    for mode in ("layered", "collapsed"):
+        tr.set_eval_mode(mode)
+        for _ in range(4):                       # eager, eager, capture, replay
+            r = tr.eval_step()
+        out[mode] = (r["logits"].clone(), r["val_loss"].clone(), int(r["correct_val"].item()))
+        assert rel_err(out[mode][0], z_ref) < 1e-5, mode
+    assert rel_err(out["collapsed"][0], out["layered"][0]) < 1e-5
+    assert abs(out["collapsed"][1][0].item() - out["layered"][1][0].item()) < 1e-5
+    assert abs(out["collapsed"][2] - out["layered"][2]) <= 1
+
+
+def test_collapsed_eval_refused_with_activation(cuda):
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    g, gd, ref, mod, shape = _make_pair(cuda, p=0.0, relu=True)
+    with pytest.raises(ValueError):
+        TextGCNTrainer(mod, gd, eval_mode="collapsed")
