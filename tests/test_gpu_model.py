@@ -192,3 +192,30 @@ def test_philox_training_forward_backward_consistent(cuda):
     assert rel_err(z, z_ref) < TOL
     for pr, pm in zip(ref.parameters(), mod.parameters()):
         assert rel_err(pm.grad, pr.grad) < TOL
+
+
+def test_cuda_path_against_committed_golden_vectors(cuda):
+    """Same fixture as tests/test_oracle.py::test_oracle_reproduces_committed_golden_vectors, CUDA side."""
+    import os
+    import numpy as np
+    from pytextgcn_b200 import GCN
+    from pytextgcn_b200.graph import upload_graph
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "gcn_karate.npz"))
+    g = karate_graph().to(cuda)
+    csr = upload_graph(g.edge_index, g.edge_attr, 34)
+    assert np.array_equal(csr.rowptr.cpu().numpy(), z["rowptr"].astype(np.int32))
+    assert np.array_equal(csr.colidx.cpu().numpy(), z["colidx"].astype(np.int32))
+    assert np.array_equal(csr.val.cpu().numpy().view(np.int32), z["val"].view(np.int32))
+    assert np.array_equal(csr.dis.cpu().numpy().view(np.int32), z["dis"].view(np.int32))
+    mod = GCN(34, 4, n_hidden_gcn=64, dropout=0.5)
+    with torch.no_grad():
+        for p, k in zip(mod.parameters(), ("W1", "b1", "W2", "b2")):
+            p.copy_(torch.from_numpy(z[k]))
+    mod = mod.to(cuda).train()
+    mod.drop_mask_override = [torch.from_numpy(z["keep"]).to(cuda)]
+    out = mod(g)
+    loss = torch.nn.functional.cross_entropy(out[g.train_mask], g.y[g.train_mask])
+    loss.backward()
+    assert rel_err(out, torch.from_numpy(z["logits"])) < TOL and abs(loss.item() - float(z["loss"])) < 1e-5
+    for p, k in zip(mod.parameters(), ("gW1", "gb1", "gW2", "gb2")):
+        assert rel_err(p.grad, torch.from_numpy(z[k])) < TOL

@@ -134,3 +134,24 @@ def test_reference_epoch_runs_and_learns():
     assert losses[-1] < losses[0]
     assert [n for n, _ in gcn.named_parameters()] == ["layers.0.weight", "layers.0.bias",
                                                       "layers.1.weight", "layers.1.bias"]
+
+
+def test_oracle_reproduces_committed_golden_vectors():
+    """tests/golden/gcn_karate.npz (made by oracle/make_golden.py): pins the oracle's numbers -- CSR of A_hat
+    bit for bit, logits / loss / gradients to fp32 round-off -- against drift of torch or of this file."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "gcn_karate.npz"))
+    ei, ea = torch.from_numpy(z["edge_index"]), torch.from_numpy(z["edge_attr"])
+    rowptr, col, val, dis, _ = O.csr_from_gcn_norm(ei, ea, 34)
+    assert np.array_equal(rowptr.numpy(), z["rowptr"]) and np.array_equal(col.numpy(), z["colidx"])
+    assert np.array_equal(val.numpy().view(np.int32), z["val"].view(np.int32))
+    assert np.array_equal(dis.numpy().view(np.int32), z["dis"].view(np.int32))
+    g = karate_graph()
+    W = [torch.from_numpy(z["W1"]).requires_grad_(), torch.from_numpy(z["W2"]).requires_grad_()]
+    b = [torch.from_numpy(z["b1"]).requires_grad_(), torch.from_numpy(z["b2"]).requires_grad_()]
+    out = O.gcn_forward(g.x, ei, ea, W, b, p=0.5, training=True, drop_masks=[torch.from_numpy(z["keep"])])
+    loss = O.masked_cross_entropy(out, torch.from_numpy(z["y"]), torch.from_numpy(z["train_mask"]))
+    loss.backward()
+    assert rel_err(out, torch.from_numpy(z["logits"])) < 1e-6 and abs(loss.item() - float(z["loss"])) < 1e-6
+    for t, k in ((W[0], "gW1"), (b[0], "gb1"), (W[1], "gW2"), (b[1], "gb2")):
+        assert rel_err(t.grad, torch.from_numpy(z[k])) < 1e-6
