@@ -135,6 +135,62 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
       }
     }
 
+    // ---- dZ1 rows, narrow hidden layer (H <= 32): lane = (row q = lane/8, hidden quad hq = lane%8), so
+    //      all 32 lanes work on the warp's 4 rows (the general mapping below would leave 24 idle) ----
+    if (do_rows && p.dZ1 && HQ <= 8) {
+      const int rb = wid * 4, q = lane >> 3, hq = lane & 7;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (hq < HQ) {
+        for (int c = 0; c < C; ++c) {
+          const float g = G2t[c * DB_ROWS + rb + q];
+          float4 w;
+          if (p.w2_in_smem) {
+            w = *reinterpret_cast<const float4*>(W2t + c * H + 4 * hq);
+          } else {
+            const float* wp = p.W2 + (int64_t)(4 * hq) * C + c;
+            w = make_float4(__ldg(wp), __ldg(wp + C), __ldg(wp + 2 * C), __ldg(wp + 3 * C));
+          }
+          v[0] = fmaf(g, w.x, v[0]); v[1] = fmaf(g, w.y, v[1]); v[2] = fmaf(g, w.z, v[2]); v[3] = fmaf(g, w.w, v[3]);
+        }
+      }
+      const int r = rb + q;
+      const int64_t row = r0 + r;
+      if (row < p.n_rows && hq < HQ) {
+        if (p.act == TGCN_ACT_RELU) {
+          const float4 hv = *reinterpret_cast<const float4*>(Hs + r * H + 4 * hq);
+          v[0] = hv.x > 0.0f ? v[0] * p.drop_scale : 0.0f; v[1] = hv.y > 0.0f ? v[1] * p.drop_scale : 0.0f;
+          v[2] = hv.z > 0.0f ? v[2] * p.drop_scale : 0.0f; v[3] = hv.w > 0.0f ? v[3] * p.drop_scale : 0.0f;
+        } else if (p.drop_mode == TGCN_DROP_MASK) {
+          const uint8_t* m = p.keep_mask + row * p.ldmask + 4 * hq;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = m[i] ? v[i] * p.drop_scale : 0.0f;
+        } else if (p.drop_mode == TGCN_DROP_PHILOX) {
+          const uint64_t e4 = ((uint64_t)(row + p.row_offset) * (uint64_t)H + (uint64_t)(4 * hq)) >> 2;
+          const uint4 rr = philox_quad(e4, p.philox_seed, ph_off);
+          v[0] = (u01(rr.x) >= p.drop_p) ? v[0] * p.drop_scale : 0.0f;
+          v[1] = (u01(rr.y) >= p.drop_p) ? v[1] * p.drop_scale : 0.0f;
+          v[2] = (u01(rr.z) >= p.drop_p) ? v[2] * p.drop_scale : 0.0f;
+          v[3] = (u01(rr.w) >= p.drop_p) ? v[3] * p.drop_scale : 0.0f;
+        }
+        if (p.dz1_dtype == TGCN_F32) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dZ1) + row * p.lddz1 + 4 * hq) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dZ1) + row * p.lddz1 + 4 * hq);
+          o[0] = __floats2bfloat162_rn(v[0], v[1]);
+          o[1] = __floats2bfloat162_rn(v[2], v[3]);
+        }
+      } else {
+        v[0] = v[1] = v[2] = v[3] = 0.0f;
+      }
+      // db_hidden: add the 4 rows of this warp (lanes hq, hq+8, hq+16, hq+24), fixed order
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float t = v[i];
+        t += __shfl_down_sync(0xffffffffu, t, 16);
+        t += __shfl_down_sync(0xffffffffu, t, 8);
+        if (lane < 8) dbh[0][i] += t;
+      }
+    } else
     // ---- dZ1 rows: warp `wid` owns rows 4*wid .. 4*wid+3; lane owns hidden quads lane + 32k ----
     if (do_rows && p.dZ1) {
       float dz[4][KQ][4];

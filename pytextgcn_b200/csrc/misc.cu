@@ -112,43 +112,44 @@ __global__ void __launch_bounds__(256) k_hier_forward(const float* __restrict__ 
   }
 }
 
-// dW1[N:, :] = F^T G1[docs]: each CTA owns a contiguous block of documents and keeps a private
-// (c_prev x H) accumulator in shared memory; partials are summed in CTA order afterwards.
+// dW1[N:, :] = F^T G1[docs].  Every WARP owns a strided subset of the documents and a private
+// (c_prev x H) accumulator in shared memory (no block barrier per document); lanes cover H, the
+// non-zeros of the F row are found by ballot (one-hot rows: a single update).  Per-warp partials are
+// added in warp order at the end, per-CTA partials in CTA order by k_reduce_parts: deterministic.
 __global__ void __launch_bounds__(256) k_hier_backward(const float* __restrict__ G1, int64_t ldg, int64_t n_vocab, int64_t n_docs,
                                                        const float* __restrict__ Fd, int64_t ldf, int c_prev, int H,
-                                                       float* __restrict__ part) {
+                                                       float* __restrict__ part, int warps_with_acc) {
   extern __shared__ __align__(16) float smem[];
-  float* acc = smem;                         // [c_prev * H]
-  float* fval = acc + c_prev * H;            // [c_prev] compacted non-zero values of the current F row
-  int* fidx = reinterpret_cast<int*>(fval + c_prev);
-  __shared__ int s_nnz;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < c_prev * H; i += blockDim.x) acc[i] = 0.0f;
-  const int64_t per = (n_docs + gridDim.x - 1) / gridDim.x;
-  const int64_t d0 = (int64_t)blockIdx.x * per, d1 = min(n_docs, d0 + per);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nw = warps_with_acc;                 // warps that own an accumulator (smem permitting)
+  const int sz = c_prev * H;
+  for (int i = tid; i < nw * sz; i += blockDim.x) smem[i] = 0.0f;
   __syncthreads();
-  for (int64_t d = d0; d < d1; ++d) {
-    if (tid < 32) {   // warp 0 compacts the non-zeros of F[d, :] in column order
-      int cnt = 0;
+  if (wid < nw) {
+    float* acc = smem + wid * sz;
+    const int64_t stride = (int64_t)gridDim.x * nw;
+    for (int64_t d = (int64_t)blockIdx.x * nw + wid; d < n_docs; d += stride) {
+      const float* g = G1 + (n_vocab + d) * ldg;
       for (int c0 = 0; c0 < c_prev; c0 += 32) {
-        const int c = c0 + tid;
+        const int c = c0 + lane;
         const float f = (c < c_prev) ? Fd[d * ldf + c] : 0.0f;
-        const unsigned b = __ballot_sync(0xffffffffu, f != 0.0f);
-        if (f != 0.0f) { const int pos = cnt + __popc(b & ((1u << tid) - 1)); fval[pos] = f; fidx[pos] = c; }
-        cnt += __popc(b);
+        unsigned m = __ballot_sync(0xffffffffu, f != 0.0f);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const float fv = __shfl_sync(0xffffffffu, f, src);
+          float* a = acc + (c0 + src) * H;
+          for (int h = lane; h < H; h += 32) a[h] = fmaf(fv, g[h], a[h]);
+        }
       }
-      if (tid == 0) s_nnz = cnt;
     }
-    __syncthreads();
-    const int work = s_nnz * H;
-    const float* g = G1 + (n_vocab + d) * ldg;
-    for (int i = tid; i < work; i += blockDim.x) {
-      const int k = i / H, h = i - k * H;
-      acc[fidx[k] * H + h] = fmaf(fval[k], g[h], acc[fidx[k] * H + h]);
-    }
-    __syncthreads();
   }
-  for (int i = tid; i < c_prev * H; i += blockDim.x) part[(int64_t)blockIdx.x * c_prev * H + i] = acc[i];
+  __syncthreads();
+  for (int i = tid; i < sz; i += blockDim.x) {
+    float s = 0.0f;
+    for (int w = 0; w < nw; ++w) s += smem[w * sz + i];
+    part[(int64_t)blockIdx.x * sz + i] = s;
+  }
 }
 
 __global__ void k_reduce_parts(const float* __restrict__ part, int n_parts, int64_t n, float* __restrict__ out) {
@@ -245,10 +246,13 @@ extern "C" int tgcn_hier_backward(const float* G1, int64_t ldg, int64_t N, int64
     set_error("hier_backward workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
     return TGCN_EWORKSPACE;
   }
-  size_t smem = ((size_t)c_prev * H + 2 * (size_t)c_prev) * sizeof(float);
-  TGCN_CHECK_ARG(smem <= 227 * 1024, "hier_backward: c_prev*H too large for shared memory");
+  const size_t sz_bytes = (size_t)c_prev * H * sizeof(float);
+  TGCN_CHECK_ARG(sz_bytes <= 200 * 1024, "hier_backward: c_prev*H too large for shared memory");
+  int nw = (int)std::min<size_t>(8, (200 * 1024) / sz_bytes);
+  if (nw < 1) nw = 1;
+  const size_t smem = (size_t)nw * sz_bytes;
   if (smem > 48 * 1024) TGCN_CUDA(cudaFuncSetAttribute(k_hier_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_hier_backward<<<grid, 256, smem, stream>>>(G1, ldg, n_vocab, n_docs, Fdoc, ldf, c_prev, H, (float*)workspace);
+  k_hier_backward<<<grid, 256, smem, stream>>>(G1, ldg, n_vocab, n_docs, Fdoc, ldf, c_prev, H, (float*)workspace, nw);
   TGCN_LAUNCH_CHECK();
   const int T = 256;
   k_reduce_parts<<<(unsigned)cdiv((int64_t)c_prev * H, T), T, 0, stream>>>((const float*)workspace, grid, (int64_t)c_prev * H, dW_tail);

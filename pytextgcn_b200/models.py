@@ -129,9 +129,12 @@ class _GCN2Function(torch.autograd.Function):
         P = torch.zeros((n, Cp), dtype=torch.float32, device=W1.device) if Cp != C else \
             torch.empty((n, Cp), dtype=torch.float32, device=W1.device)
         # layer 1: propagation + bias + (act) + dropout, layer 2's thin projection fused in the epilogue
-        H1d, P = ops.spmm(graph, B1, F=Hp, bias=b1, act=act, drop_mode=drop.mode, drop_p=drop.p,
+        fuse = C <= ops.FUSED_PROJ_MAX_CLASSES
+        H1d, _ = ops.spmm(graph, B1, F=Hp, bias=b1, act=act, drop_mode=drop.mode, drop_p=drop.p,
                           keep_mask=drop.mask, philox_seed=drop.seed, philox_offset=drop.offset,
-                          W_proj=W2p, P=P)
+                          W_proj=W2p if fuse else None, P=P if fuse else None)
+        if not fuse:
+            ops.project(H1d, W2p, K=Hp, out=P)
         # layer 2: propagation of the projected rows + bias
         Z2, _ = ops.spmm(graph, P, F=Cp, bias=b2)
         ctx.graph, ctx.feat, ctx.act, ctx.drop = graph, feat, act, drop

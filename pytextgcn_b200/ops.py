@@ -14,6 +14,9 @@ from .graph import GraphCSR, SpmmPlan
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU = 0, 1
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
+# The register-butterfly projection in the SpMM epilogue pays off for thin class counts (TextGCN: 6..64);
+# beyond that the stand-alone row kernel (tgcn_project) is cheaper than widening every SpMM warp's tail.
+FUSED_PROJ_MAX_CLASSES = 64
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 

@@ -157,10 +157,13 @@ class TextGCNTrainer:
         else:
             B1 = W1[:self.n]
         drop = training and self.p > 0.0
+        fuse = self.C <= ops.FUSED_PROJ_MAX_CLASSES
         ops.spmm(self.graph, B1, F=self.H, plan=self.plan, out=self.H1d, bias=b1, act=self.act,
                  drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p,
                  philox_seed=self.seed, philox_offset=0, philox_offset_dev=self.step_dev if drop else None,
-                 W_proj=W2, P=self.P)
+                 W_proj=W2 if fuse else None, P=self.P if fuse else None)
+        if not fuse:
+            ops.project(self.H1d, W2, K=self.H, out=self.P)
         ops.spmm(self.graph, self.P, F=self.Cp, plan=self.plan, out=self.Z2, bias=b2)
         return k + 2 + 2 * (1 if self.plan.n_split_rows else 0)
 

@@ -57,7 +57,8 @@ def test_karate_like_reference_unit_test(cuda, relu):
     _run_pair(g, 4, 64, 0.5, relu, cuda)
 
 
-@pytest.mark.parametrize("hidden,classes,p", [(200, 20, 0.5), (100, 64, 0.7), (32, 9, 0.5), (64, 6, 0.0), (30, 5, 0.5)])
+@pytest.mark.parametrize("hidden,classes,p", [(200, 20, 0.5), (100, 64, 0.7), (32, 9, 0.5), (64, 6, 0.0), (30, 5, 0.5),
+                                              (32, 70, 0.5), (32, 219, 0.5)])   # > 64 classes: stand-alone projection kernel
 def test_textgcn_shapes(cuda, hidden, classes, p):
     from pytextgcn_b200.synthetic import make_graph, GraphShape
     g = make_graph(GraphShape("t", 900, 700, 12000, 25, classes, hidden), seed=hidden)

@@ -191,3 +191,29 @@ def test_collapsed_eval_refused_with_activation(cuda):
     g, gd, ref, mod, shape = _make_pair(cuda, p=0.0, relu=True)
     with pytest.raises(ValueError):
         TextGCNTrainer(mod, gd, eval_mode="collapsed")
+
+
+def test_trainer_many_classes_narrow_hidden_with_hierarchy(cuda):
+    """DBPedia per-level form (perlevel_dbpedia.py:140-141,186): hidden 32, 219 classes, x = [I | onehot(70)]:
+    un-fused projection, narrow-hidden dense backward, per-warp hierarchy-gradient kernel."""
+    from pytextgcn_b200 import GCN
+    from pytextgcn_b200.synthetic import make_graph, GraphShape
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    shape = GraphShape("t", 600, 900, 8000, 12, 219, 32)
+    g = make_graph(shape, seed=2, hierarchy_classes=70)
+    n, in_ch = int(g.x.shape[0]), int(g.x.shape[1])
+    torch.manual_seed(0)
+    ref = O.OracleGCN(in_ch, 219, n_hidden_gcn=32, dropout=0.0)
+    mod = GCN(in_ch, 219, n_hidden_gcn=32, dropout=0.0)
+    with torch.no_grad():
+        for pd, ps in zip(mod.parameters(), ref.parameters()):
+            pd.copy_(ps)
+    mod = mod.to(cuda)
+    tr = TextGCNTrainer(mod, g.clone().to(cuda), lr=0.01, amsgrad=False)
+    opt = torch.optim.Adam(ref.parameters(), lr=0.01)
+    for step in range(3):
+        out_ref = O.reference_epoch(ref, g, opt)
+        out = tr.epoch()
+        for gbuf, pr in zip(tr.grads, ref.parameters()):
+            assert rel_err(gbuf, pr.grad) < 2e-5 * (step + 1)
+        assert abs(out["loss"] - out_ref[0]) < 1e-5 * max(1, abs(out_ref[0])) * (step + 1)
