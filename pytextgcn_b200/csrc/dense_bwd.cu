@@ -305,33 +305,42 @@ __global__ void k_reduce_partials(const float* __restrict__ part, int n_parts, i
   out[i] = s;
 }
 
-// thin projection P = X W, one warp per row, W staged in shared memory when it fits
+// thin projection P = X W: a warp takes 4 rows per step (row values staged transposed [k][4] in shared
+// memory so one 16-byte broadcast read feeds 4 FMAs per weight read); W staged in shared memory when it fits
+constexpr int PJ_ROWS = 4;
 __global__ void __launch_bounds__(256) k_project(const void* __restrict__ X, int64_t ldx, int x_dtype, int64_t n_rows, int K,
                                                  const float* __restrict__ W, int M, float* __restrict__ P, int64_t ldp,
                                                  int w_in_smem) {
   extern __shared__ __align__(16) float smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Kp = (K + 3) & ~3;
   float* Ws = smem;
-  float* rowbuf = smem + (w_in_smem ? ((K * M + 3) & ~3) : 0) + wid * Kp;
+  float* rowbuf = smem + (w_in_smem ? ((K * M + 3) & ~3) : 0) + wid * (K * PJ_ROWS);   // [K][4]
   if (w_in_smem) {
     for (int i = threadIdx.x; i < K * M; i += blockDim.x) Ws[i] = W[i];
   }
   __syncthreads();
   const float* Wp = w_in_smem ? Ws : W;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid; row < n_rows; row += warps) {
-    for (int k = lane; k < K; k += 32) rowbuf[k] = load_h(X, x_dtype, row * ldx + k);
+  const int64_t n_groups = (n_rows + PJ_ROWS - 1) / PJ_ROWS;
+  for (int64_t grp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid; grp < n_groups; grp += warps) {
+    const int64_t row0 = grp * PJ_ROWS;
+    for (int i = lane; i < K * PJ_ROWS; i += 32) {
+      const int r = i / K, k = i - r * K;                       // coalesced along k within a row
+      const int64_t row = row0 + r;
+      rowbuf[k * PJ_ROWS + r] = (row < n_rows) ? load_h(X, x_dtype, row * ldx + k) : 0.0f;
+    }
     __syncwarp();
     for (int m = lane; m < M; m += 32) {
-      float s0 = 0.f, s1 = 0.f;
-      int k = 0;
-      for (; k + 1 < K; k += 2) {
-        s0 = fmaf(rowbuf[k], Wp[(int64_t)k * M + m], s0);
-        s1 = fmaf(rowbuf[k + 1], Wp[(int64_t)(k + 1) * M + m], s1);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float w = Wp[(int64_t)k * M + m];
+        const float4 x = *reinterpret_cast<const float4*>(rowbuf + k * PJ_ROWS);
+        s0 = fmaf(x.x, w, s0); s1 = fmaf(x.y, w, s1); s2 = fmaf(x.z, w, s2); s3 = fmaf(x.w, w, s3);
       }
-      if (k < K) s0 = fmaf(rowbuf[k], Wp[(int64_t)k * M + m], s0);
-      P[row * ldp + m] = s0 + s1;
+      if (row0 + 0 < n_rows) P[(row0 + 0) * ldp + m] = s0;
+      if (row0 + 1 < n_rows) P[(row0 + 1) * ldp + m] = s1;
+      if (row0 + 2 < n_rows) P[(row0 + 2) * ldp + m] = s2;
+      if (row0 + 3 < n_rows) P[(row0 + 3) * ldp + m] = s3;
     }
     __syncwarp();
   }
@@ -404,7 +413,7 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
   const int gy = (CB + cb_per_y - 1) / cb_per_y;
   const size_t smem_rest = ((size_t)DB_ROWS * H + 3 * (size_t)DB_ROWS * Cp + (size_t)(DB_THREADS / 32) * H) * sizeof(float);
   const size_t smem_w2 = (size_t)H * C * sizeof(float);
-  p.w2_in_smem = (smem_rest + smem_w2 <= 110 * 1024) ? 1 : 0;     // keep 2 CTAs per SM
+  p.w2_in_smem = (smem_rest + smem_w2 <= 220 * 1024) ? 1 : 0;     // strided global reads of W2 are far slower than losing the 2nd CTA/SM
   size_t smem = smem_rest + (p.w2_in_smem ? smem_w2 : 0);
   TGCN_CHECK_ARG(smem <= 227 * 1024, "dense_bwd: H=%d C=%d needs %zu bytes of shared memory (> 227 KB)", H, C, smem);
   const int kq = (H / 4 + 31) / 32;
@@ -441,11 +450,10 @@ extern "C" int tgcn_project(const void* X, int64_t ldx, int32_t x_dtype, int64_t
   TGCN_CHECK_ARG(X && W && P, "project: null pointer");
   TGCN_CHECK_ARG(n_rows > 0 && K > 0 && M > 0 && ldx >= K && ldp >= M, "project: bad shape");
   const int threads = 256, wpb = threads / 32;
-  const int Kp = (K + 3) & ~3;
   const int w_in_smem = ((size_t)K * M * 4 <= 96 * 1024) ? 1 : 0;
-  size_t smem = ((w_in_smem ? ((K * M + 3) & ~3) : 0) + (size_t)wpb * Kp) * sizeof(float);
+  size_t smem = ((w_in_smem ? ((K * M + 3) & ~3) : 0) + (size_t)wpb * K * PJ_ROWS) * sizeof(float);
   if (smem > 48 * 1024) TGCN_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)std::min<int64_t>(cdiv(n_rows, wpb), (int64_t)sm_count() * 8);
+  const int grid = (int)std::min<int64_t>(cdiv(cdiv(n_rows, PJ_ROWS), wpb), (int64_t)sm_count() * 8);
   k_project<<<grid, threads, smem, stream>>>(X, ldx, x_dtype, n_rows, K, W, M, P, ldp, w_in_smem);
   TGCN_LAUNCH_CHECK();
   return TGCN_OK;

@@ -59,20 +59,10 @@ __global__ void __launch_bounds__(256) k_masked_nll(const float* __restrict__ Z,
   }
 }
 
-// fixed-order reduction of the per-row terms (deterministic): one CTA, fp64 accumulators
-__global__ void __launch_bounds__(1024) k_nll_reduce(const float* __restrict__ row_nll, const int32_t* __restrict__ row_hit,
-                                                     const uint8_t* __restrict__ mask, int64_t n_rows, int64_t n_mask_total,
-                                                     float* __restrict__ loss_out, double* __restrict__ partial_out,
-                                                     int32_t* __restrict__ correct_out) {
-  __shared__ double s_sum[1024];
-  __shared__ int s_cnt[1024];
-  __shared__ int s_hit[1024];
-  double s = 0.0; int cnt = 0, hit = 0;
-  for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
-    s += (double)row_nll[r];
-    cnt += mask ? (mask[r] != 0) : 1;
-    if (row_hit) hit += row_hit[r];
-  }
+// fixed-order reduction of the per-row terms (deterministic, fp64): stage 1 = NLL_PARTS CTAs over contiguous
+// slices, stage 2 = one CTA adding the slice partials in slice order.
+constexpr int NLL_PARTS = 64;
+__device__ __forceinline__ void block_reduce3(double& s, int& cnt, int& hit, double* s_sum, int* s_cnt, int* s_hit) {
   s_sum[threadIdx.x] = s; s_cnt[threadIdx.x] = cnt; s_hit[threadIdx.x] = hit;
   __syncthreads();
   for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
@@ -83,12 +73,37 @@ __global__ void __launch_bounds__(1024) k_nll_reduce(const float* __restrict__ r
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    const double n = n_mask_total > 0 ? (double)n_mask_total : (double)s_cnt[0];
-    if (loss_out) { loss_out[0] = (float)(s_sum[0] / n); loss_out[1] = (float)s_cnt[0]; }
-    if (partial_out) { partial_out[0] = s_sum[0]; partial_out[1] = (double)s_cnt[0]; }
-    if (correct_out) correct_out[0] = s_hit[0];
+  s = s_sum[0]; cnt = s_cnt[0]; hit = s_hit[0];
+}
+
+__global__ void __launch_bounds__(256) k_nll_partial(const float* __restrict__ row_nll, const int32_t* __restrict__ row_hit,
+                                                     const uint8_t* __restrict__ mask, int64_t n_rows,
+                                                     double* __restrict__ part_sum, int32_t* __restrict__ part_cnt) {
+  __shared__ double s_sum[256];
+  __shared__ int s_cnt[256];
+  __shared__ int s_hit[256];
+  const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(n_rows, r0 + per);
+  double s = 0.0; int cnt = 0, hit = 0;
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    s += (double)row_nll[r];
+    cnt += mask ? (mask[r] != 0) : 1;
+    if (row_hit) hit += row_hit[r];
   }
+  block_reduce3(s, cnt, hit, s_sum, s_cnt, s_hit);
+  if (threadIdx.x == 0) { part_sum[blockIdx.x] = s; part_cnt[2 * blockIdx.x] = cnt; part_cnt[2 * blockIdx.x + 1] = hit; }
+}
+
+__global__ void __launch_bounds__(NLL_PARTS) k_nll_final(const double* __restrict__ part_sum, const int32_t* __restrict__ part_cnt,
+                                                         int n_parts, int64_t n_mask_total, float* __restrict__ loss_out,
+                                                         double* __restrict__ partial_out, int32_t* __restrict__ correct_out) {
+  if (threadIdx.x != 0) return;
+  double s = 0.0; int cnt = 0, hit = 0;
+  for (int i = 0; i < n_parts; ++i) { s += part_sum[i]; cnt += part_cnt[2 * i]; hit += part_cnt[2 * i + 1]; }
+  const double n = n_mask_total > 0 ? (double)n_mask_total : (double)cnt;
+  if (loss_out) { loss_out[0] = (float)(s / n); loss_out[1] = (float)cnt; }
+  if (partial_out) { partial_out[0] = s; partial_out[1] = (double)cnt; }
+  if (correct_out) correct_out[0] = hit;
 }
 
 __global__ void k_count_mask(const uint8_t* __restrict__ mask, int64_t n, int32_t* __restrict__ out) {
@@ -110,7 +125,7 @@ using namespace tgcn;
 
 extern "C" int tgcn_masked_nll_workspace_bytes(int64_t n_rows, size_t* bytes_out) {
   TGCN_CHECK_ARG(bytes_out != nullptr && n_rows >= 0, "masked_nll_workspace_bytes: bad arguments");
-  *bytes_out = align_up((size_t)n_rows * 4, 256) * 2;
+  *bytes_out = align_up((size_t)n_rows * 4, 256) * 2 + 4096;   // row terms + row hits + slice partials
   return TGCN_OK;
 }
 
@@ -124,7 +139,7 @@ extern "C" int tgcn_masked_nll(const float* Z, int64_t ldz, int64_t n_rows, int3
   TGCN_CHECK_ARG(n_rows > 0 && C > 0 && ldz >= C, "masked_nll: bad shape");
   TGCN_CHECK_ARG(dZ == nullptr || lddz >= C, "masked_nll: lddz < C");
   TGCN_CHECK_ARG(dZ == nullptr || n_mask_total > 0, "masked_nll: the gradient needs the global mask count (n_mask_total > 0)");
-  size_t need = align_up((size_t)n_rows * 4, 256) * 2;
+  size_t need = align_up((size_t)n_rows * 4, 256) * 2 + 4096;
   if (!workspace || workspace_bytes < need) {
     set_error("masked_nll workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
     return TGCN_EWORKSPACE;
@@ -136,8 +151,14 @@ extern "C" int tgcn_masked_nll(const float* Z, int64_t ldz, int64_t n_rows, int3
   k_masked_nll<<<(unsigned)cdiv(n_rows * 32, T), T, 0, stream>>>(Z, ldz, n_rows, C, y, mask, inv_n, dZ, lddz, pred_out, row_nll,
                                                                   correct_out ? row_hit : nullptr);
   TGCN_LAUNCH_CHECK();
-  k_nll_reduce<<<1, 1024, 0, stream>>>(row_nll, correct_out ? row_hit : nullptr, mask, n_rows, n_mask_total, loss_out,
-                                       partial_out, correct_out);
+  // slice partials live in the last 4 KB of the caller's workspace (nothing is allocated here)
+  static_assert(NLL_PARTS * (sizeof(double) + 2 * sizeof(int32_t)) <= 4096, "partials must fit the tail pad");
+  double* part_sum = (double*)((char*)workspace + 2 * align_up((size_t)n_rows * 4, 256));
+  int32_t* part_cnt = (int32_t*)(part_sum + NLL_PARTS);
+  const int parts = (int)std::min<int64_t>(NLL_PARTS, std::max<int64_t>(1, n_rows / 1024));
+  k_nll_partial<<<parts, 256, 0, stream>>>(row_nll, correct_out ? row_hit : nullptr, mask, n_rows, part_sum, part_cnt);
+  TGCN_LAUNCH_CHECK();
+  k_nll_final<<<1, NLL_PARTS, 0, stream>>>(part_sum, part_cnt, parts, n_mask_total, loss_out, partial_out, correct_out);
   TGCN_LAUNCH_CHECK();
   return TGCN_OK;
 }

@@ -103,9 +103,16 @@ __global__ void __launch_bounds__(256) k_hier_forward(const float* __restrict__ 
     float s = (h < H) ? W1[row * ldw + h] : 0.0f;
     if (row >= n_vocab) {
       const float* f = Fd + (row - n_vocab) * ldf;
-      for (int c = 0; c < c_prev; ++c) {
-        const float fc = f[c];                       // warp-uniform
-        if (fc != 0.0f && h < H) s = fmaf(fc, tail[(int64_t)c * ldw + h], s);
+      for (int c0 = 0; c0 < c_prev; c0 += 32) {      // lanes read 32 features at once; non-zeros found by ballot
+        const int c = c0 + lane;
+        const float fv = (c < c_prev) ? f[c] : 0.0f;
+        unsigned msk = __ballot_sync(0xffffffffu, fv != 0.0f);
+        while (msk) {
+          const int src = __ffs(msk) - 1;
+          msk &= msk - 1;
+          const float fc = __shfl_sync(0xffffffffu, fv, src);
+          if (h < H) s = fmaf(fc, tail[(int64_t)(c0 + src) * ldw + h], s);
+        }
       }
     }
     if (h < H) XW[row * ldxw + h] = s;

@@ -172,7 +172,7 @@ class DistTextGCNTrainer:
         self.stats = torch.zeros(6, dtype=torch.float64, device=dev)         # packed scalars for one all-reduce
         self.pred = torch.zeros(nl, dtype=torch.int32, device=dev)
         self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._nll_ws = torch.empty(2 * ((nl * 4 + 255) // 256 * 256), dtype=torch.uint8, device=dev)
+        self._nll_ws = torch.empty(2 * ((nl * 4 + 255) // 256 * 256) + 4096, dtype=torch.uint8, device=dev)
         self._db_ws = None
         # labels / masks in the new order, local slices
         y_new = self.part.to_new(g.y.cpu(), 0)

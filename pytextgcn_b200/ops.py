@@ -136,7 +136,7 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
         pred = torch.empty(n, dtype=torch.int32, device=dev)
     if correct is None and want_correct:
         correct = torch.zeros(1, dtype=torch.int32, device=dev)
-    need = 2 * ((n * 4 + 255) // 256 * 256)        # == tgcn_masked_nll_workspace_bytes(n)
+    need = 2 * ((n * 4 + 255) // 256 * 256) + 4096  # == tgcn_masked_nll_workspace_bytes(n)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

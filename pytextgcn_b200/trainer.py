@@ -79,7 +79,7 @@ class TextGCNTrainer:
         self.correct_val = torch.zeros(1, dtype=torch.int32, device=dev)
         self.correct_train = torch.zeros(1, dtype=torch.int32, device=dev)
         self.hier_tail = torch.empty((self.in_ch - n, H), **f32) if self.feat.Fdoc is not None else None
-        self._nll_ws = torch.empty(2 * ((n * 4 + 255) // 256 * 256), dtype=torch.uint8, device=dev)
+        self._nll_ws = torch.empty(2 * ((n * 4 + 255) // 256 * 256) + 4096, dtype=torch.uint8, device=dev)
         self._db_ws = None
         self.logits = self.Z2[:, :self.C]
         self.Q = torch.zeros((n, Cp), **f32)          # collapsed eval: X W1 W2
