@@ -325,8 +325,7 @@ def run_own_arm(args):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         ops.spmm(graph, Bop, F=F, plan=tr.plan, out=out, bias=gcn.layers[0].bias.data, drop_mode=ops.DROP_PHILOX,
-                 drop_p=shape.dropout, philox_seed=args.seed, philox_offset_dev=tr.step_dev,
-                 W_proj=gcn.layers[1].weight.data, P=tr.P)
+                 drop_p=shape.dropout, philox_seed=args.seed, philox_offset_dev=tr.step_dev)
         b.record()
         # the rest of a step runs between two launches of this kernel (evicts L2: > 1 GB streamed)
         tr.eval_step()
@@ -339,7 +338,7 @@ def run_own_arm(args):
     prof = load_profile_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": prof.get("dram_bytes_per_launch"),
-                "kernel": "k_spmm<float,32,2> (layer-1 propagation, F=%d, fused bias+dropout+projection)" % F,
+                "kernel": "k_spmm<float,32,2,false> (layer-1 propagation of the train step, F=%d, fused bias + Philox dropout epilogue)" % F,
                 "kernel_ms": k_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
                 "note": "algorithmic bytes count each dense row once; the kernel is bound by L2->SM gather bandwidth "
                         "(nnz*F*4 = %.1f GB per launch), see DESIGN.md" % (graph.nnz * F * 4 / 1e9),

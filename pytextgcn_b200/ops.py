@@ -14,9 +14,14 @@ from .graph import GraphCSR, SpmmPlan
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU = 0, 1
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
-# The register-butterfly projection in the SpMM epilogue pays off for thin class counts (TextGCN: 6..64);
-# beyond that the stand-alone row kernel (tgcn_project) is cheaper than widening every SpMM warp's tail.
-FUSED_PROJ_MAX_CLASSES = 64
+# Layer 2's thin projection can run inside the layer-1 SpMM epilogue (tgcn_spmm W_proj/P, register
+# butterfly) or as the stand-alone 4-row register-blocked kernel (tgcn_project).  Measured on B200
+# (ms/epoch, fused vs stand-alone): 20NG-shape 3.97 vs 3.83, Amazon-shape (64 classes) 2.67 vs 1.93,
+# R8 0.704 vs 0.699 -- the epilogue's per-lane weight-row reads are bank-conflicted and serialise the
+# tail of every row warp, while the stand-alone kernel re-reads H1d (L2-resident) for ~40 us.  So the
+# shipped default is stand-alone; classes <= this threshold use the fused epilogue (0 = never).
+import os as _os
+FUSED_PROJ_MAX_CLASSES = int(_os.environ.get("TGCN_FUSED_PROJ_MAX_CLASSES", "0"))
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
