@@ -425,6 +425,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", dest="no_cuda_graph", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -194,6 +194,20 @@ int tgcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    int64_t step, const int64_t* step_dev, void* stream);
 int tgcn_increment_step(int64_t* step_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (6) Exchange step of the 1D row partition over NVLink peer memory.  Replaces the
+ * ncclAllGather between layers: the local slice [src, src+bytes) is stored into every peer's
+ * symmetric buffer at dst_offset_bytes (peer_bases_host: HOST array of `world` device pointers, the
+ * peer mappings of the same symmetric allocation), or once through the NVSwitch multicast mapping
+ * of that allocation when multicast_base != NULL (multimem.st: the switch replicates).  The caller
+ * follows it with a cross-rank barrier before any rank reads.  tgcn_sum_slots adds `n_slots`
+ * vectors in slot order (the all-reduce of the small gradients: every rank pushes its vector into
+ * slot `rank` of every peer, then sums the slots locally -- bit-identical on all ranks).
+ */
+int tgcn_peer_push(const void* src, void* const* peer_bases_host, int32_t world, int32_t rank, int64_t bytes,
+                   int64_t dst_offset_bytes, void* multicast_base, void* stream);
+int tgcn_sum_slots(const float* slots, int32_t n_slots, int64_t slot_stride, int64_t n, float* out, void* stream);
+
 /* Utility kernels the host uses on the path */
 int tgcn_count_mask(const uint8_t* mask, int64_t n, int32_t* count_out, void* stream);
 int tgcn_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -101,6 +101,57 @@ def shard_graph(graph: GraphCSR, part: RowPartition, rank: int) -> GraphCSR:
 
 
 # --------------------------------------------------------------------------------------
+# exchange over NVLink peer memory (symmetric allocations + multicast / peer stores + barrier)
+# --------------------------------------------------------------------------------------
+class PeerExchange:
+    """Symmetric buffers whose peer (and, with NVSwitch multicast, multicast) mappings are handed to
+    `tgcn_peer_push`.  An exchange = push my slice into every rank's buffer + device-side barrier;
+    it replaces ncclAllGather between layers and runs on the compute stream (graph-capturable)."""
+
+    def __init__(self, group, rank: int, world: int, dev: torch.device):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem, self.C = symm_mem, C
+        self.group, self.rank, self.world, self.dev = group, rank, world, dev
+        self.handles = {}
+        self.peer_arrays = {}
+        self.multicast = {}
+        self._barrier_hdl = None
+
+    def alloc(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        t = self.symm_mem.empty(tuple(shape), dtype=dtype, device=self.dev)
+        hdl = self.symm_mem.rendezvous(t, self.group)
+        t.zero_()
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.handles[name] = hdl
+        self.peer_arrays[name] = (self.C.c_void_p * self.world)(*ptrs)
+        mc = 0
+        try:
+            mc = int(hdl.multicast_ptr)
+        except Exception:
+            mc = 0
+        self.multicast[name] = mc
+        if self._barrier_hdl is None:
+            self._barrier_hdl = hdl
+        return t
+
+    def barrier(self) -> None:
+        self._barrier_hdl.barrier(channel=0)
+
+    def push(self, name: str, src: torch.Tensor, dst_offset_bytes: int) -> None:
+        """Store `src` (a contiguous slice living in MY copy of buffer `name`) into every peer's copy at
+        the same offset, then barrier.  After it returns (in stream order) all ranks see all slices."""
+        from . import _native
+        lib = _native.load()
+        with torch.cuda.device(self.dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            _native.check(lib.tgcn_peer_push(src.data_ptr(), self.peer_arrays[name], self.world, self.rank,
+                                             src.numel() * src.element_size(), dst_offset_bytes,
+                                             self.multicast[name] or None, stream))
+        self.barrier()
+
+
+# --------------------------------------------------------------------------------------
 # distributed trainer (one process per GPU, torch.distributed over NCCL)
 # --------------------------------------------------------------------------------------
 class DistTextGCNTrainer:
@@ -110,7 +161,7 @@ class DistTextGCNTrainer:
     def __init__(self, g, n_classes: int, hidden: int, dropout: float, lr: float, amsgrad: bool,
                  rank: int, world: int, dev: torch.device, seed: int = 0, betas=(0.9, 0.999), eps: float = 1e-8,
                  graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None,
-                 use_cuda_graph: bool = False):
+                 use_cuda_graph: bool = False, exchange: str = "peer"):
         import torch.distributed as dist
         from . import ops
         from .graph import upload_graph
@@ -134,6 +185,23 @@ class DistTextGCNTrainer:
         self.plan = self.shard.plan()
         nl, npad, H, Cp = self.part.n_loc, self.part.n_pad, hidden, self.Cp
         f32 = dict(dtype=torch.float32, device=dev)
+        # exchange buffers: symmetric (peer-mapped) allocations when the NVLink path is available
+        self.exchange, self.exchange_error, self.px = "nccl", None, None
+        if world > 1 and exchange == "peer":
+            try:
+                self.px = PeerExchange(dist.group.WORLD, rank, world, dev)
+                self.exchange = "peer"
+            except Exception as e:          # symmetric memory not available in this stack: NCCL collectives
+                self.exchange_error = repr(e)
+
+        def xbuf(name, shape):
+            if self.px is not None:
+                try:
+                    return self.px.alloc(name, shape)
+                except Exception as e:
+                    self.exchange_error = repr(e)
+                    self.px, self.exchange = None, "nccl"
+            return torch.zeros(tuple(shape), **f32)
         # parameters: same init on every rank (same seed), W1 kept in the NEW row order
         gen = torch.Generator().manual_seed(seed)
         if init_weights is None:
@@ -144,14 +212,21 @@ class DistTextGCNTrainer:
         else:
             W1, b1, W2, b2 = (init_weights[k].detach().cpu().float() for k in
                               ("layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias"))
-        self.W1_full = self.part.to_new(W1).to(dev).contiguous()            # [N_pad, H]; rows of other ranks are gathered
+        self.W1_full = xbuf("W1", (npad, H))                                # [N_pad, H]; rows of other ranks are gathered
+        self.W1_full.copy_(self.part.to_new(W1).to(dev))
         lo = rank * nl
         self.W1_loc = self.W1_full[lo:lo + nl]                               # view: this rank's shard (authoritative)
         self.b1, self.W2, self.b2 = b1.to(dev), W2.to(dev).contiguous(), b2.to(dev)
-        self.small = torch.zeros(H + H * n_classes + n_classes, **f32)       # packed grads of b1, W2, b2 (one all-reduce)
-        self.g_b1 = self.small[:H]
-        self.g_W2 = self.small[H:H + H * n_classes].view(H, n_classes)
-        self.g_b2 = self.small[H + H * n_classes:]
+        n_small = H + H * n_classes + n_classes                              # packed grads of b1, W2, b2 (one exchange)
+        self.n_small = n_small
+        self.n_small_pad = (n_small + 3) // 4 * 4
+        self.small_slots = xbuf("small", (world, self.n_small_pad))          # slot r = rank r's partial sums
+        self.small_local = self.small_slots[rank]                             # dense_bwd writes my slot in place
+        self.small = torch.zeros(self.n_small_pad, **f32)                     # summed over ranks
+        def views(buf):
+            return buf[:H], buf[H:H + H * n_classes].view(H, n_classes), buf[H + H * n_classes:n_small]
+        self.l_b1, self.l_W2, self.l_b2 = views(self.small_local)             # local partials (kernel outputs)
+        self.g_b1, self.g_W2, self.g_b2 = views(self.small)                   # global gradients (Adam inputs)
         self.g_W1 = torch.zeros((nl, H), **f32)
         def state(t):
             return [torch.zeros_like(t), torch.zeros_like(t), torch.zeros_like(t) if amsgrad else None]
@@ -159,13 +234,13 @@ class DistTextGCNTrainer:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         # activations
         self.H1d = torch.empty((nl, H), **f32)
-        self.P_full = torch.zeros((npad, Cp), **f32)
+        self.P_full = xbuf("P", (npad, Cp))
         self.P_loc = self.P_full[lo:lo + nl]
         self.Z2 = torch.zeros((nl, Cp), **f32)
-        self.dZ2_full = torch.zeros((npad, Cp), **f32)
+        self.dZ2_full = xbuf("dZ2", (npad, Cp))
         self.dZ2_loc = self.dZ2_full[lo:lo + nl]
         self.G2 = torch.zeros((nl, Cp), **f32)
-        self.dZ1_full = torch.zeros((npad, H), **f32)
+        self.dZ1_full = xbuf("dZ1", (npad, H))
         self.dZ1_loc = self.dZ1_full[lo:lo + nl]
         self.loss_part = torch.zeros(2, dtype=torch.float64, device=dev)
         self.loss_buf = torch.zeros(2, **f32)
@@ -207,15 +282,33 @@ class DistTextGCNTrainer:
         return out
 
     # ---- collectives ----
-    def _all_gather(self, full: torch.Tensor, loc: torch.Tensor) -> None:
+    def _all_gather(self, full: torch.Tensor, loc: torch.Tensor, name: Optional[str] = None) -> None:
         if self.world > 1:
-            self.dist.all_gather_into_tensor(full, loc)      # in place: loc is the rank-th slice of full
+            if self.px is not None and name is not None:
+                self.px.push(name, loc, loc.data_ptr() - full.data_ptr())   # peer stores + barrier
+            else:
+                self.dist.all_gather_into_tensor(full, loc)  # in place: loc is the rank-th slice of full
         elif full.data_ptr() != loc.data_ptr():
             full[:loc.shape[0]].copy_(loc)
 
+    def _all_reduce_small(self) -> None:
+        """self.small = sum over ranks of the packed (db1, dW2, db2) partials."""
+        if self.world == 1:
+            self.small.copy_(self.small_local)
+        elif self.px is not None:
+            from . import _native
+            lib = _native.load()
+            self.px.push("small", self.small_local, self.rank * self.n_small_pad * 4)
+            with torch.cuda.device(self.dev):
+                _native.check(lib.tgcn_sum_slots(self.small_slots.data_ptr(), self.world, self.n_small_pad, self.n_small_pad,
+                                                 self.small.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        else:
+            self.small.copy_(self.small_local)
+            self.dist.all_reduce(self.small)
+
     def _gather_w1(self) -> None:
         if self.w1_stale:
-            self._all_gather(self.W1_full, self.W1_loc)
+            self._all_gather(self.W1_full, self.W1_loc, "W1")
             self.w1_stale = False
 
     def _forward(self, training: bool) -> None:
@@ -229,7 +322,7 @@ class DistTextGCNTrainer:
                  philox_offset_dev=self.step_dev if drop else None, W_proj=self.W2, P=self.P_loc,
                  row_id_offset=self.rank * self.part.n_loc)
         self._mark("spmm_wide_fwd")
-        self._all_gather(self.P_full, self.P_loc)
+        self._all_gather(self.P_full, self.P_loc, "P")
         self._mark("allgather_P")
         ops.spmm(self.shard, self.P_full, F=self.Cp, plan=self.plan, out=self.Z2, bias=self.b2)
         self._mark("spmm_narrow_fwd")
@@ -240,7 +333,7 @@ class DistTextGCNTrainer:
         ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2_loc,
                        loss_out=self.loss_buf, workspace=self._nll_ws, partial=self.loss_part)
         self._mark("masked_nll")
-        self._all_gather(self.dZ2_full, self.dZ2_loc)
+        self._all_gather(self.dZ2_full, self.dZ2_loc, "dZ2")
         self._mark("allgather_dZ2")
         ops.spmm(self.shard, self.dZ2_full, F=self.Cp, plan=self.plan, out=self.G2)
         self._mark("spmm_narrow_bwd")
@@ -248,13 +341,12 @@ class DistTextGCNTrainer:
         r = ops.dense_bwd(self.G2, self.H1d, self.W2, self.dZ2_loc, H=self.H, n_classes=self.C,
                           drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
                           philox_offset_dev=self.step_dev if drop else None, row_offset=self.rank * self.part.n_loc,
-                          dZ1=self.dZ1_loc, workspace=self._db_ws, dW2=self.g_W2, db_hidden=self.g_b1, db_out=self.g_b2)
+                          dZ1=self.dZ1_loc, workspace=self._db_ws, dW2=self.l_W2, db_hidden=self.l_b1, db_out=self.l_b2)
         self._db_ws = r["workspace"]
         self._mark("dense_bwd")
-        if self.world > 1:
-            dist.all_reduce(self.small)
+        self._all_reduce_small()
         self._mark("allreduce_small_grads")
-        self._all_gather(self.dZ1_full, self.dZ1_loc)
+        self._all_gather(self.dZ1_full, self.dZ1_loc, "dZ1")
         self._mark("allgather_dZ1")
         ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1)
         self._mark("spmm_wide_bwd")
@@ -346,7 +438,7 @@ class DistTextGCNTrainer:
         P, nl = self.world, self.part.n_loc
         big = (P - 1) * nl * self.H * 4
         small = (P - 1) * nl * self.Cp * 4
-        return 2 * big + 2 * small + 2 * self.small.numel() * 4
+        return 2 * big + 2 * small + 2 * self.n_small_pad * 4
 
 
 def shutdown(trainer: Optional["DistTextGCNTrainer"] = None) -> None:
@@ -391,7 +483,8 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
     g = make_graph(shape, seed=args.seed)          # same graph on every rank (same seed)
     n = int(g.x.shape[0])
     tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad,
-                            rank, world, dev, seed=args.seed, use_cuda_graph=not getattr(args, "no_cuda_graph", False))
+                            rank, world, dev, seed=args.seed, use_cuda_graph=not getattr(args, "no_cuda_graph", False),
+                            exchange=getattr(args, "exchange", "peer"))
     epoch = tr.epoch
 
     for _ in range(W):
@@ -450,7 +543,9 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
         from bench import METRIC, UNIT, workload_config
         clocks = sampler.stop()
         cfg = workload_config(shape, g)
-        cfg["parallelism"] = f"1D row partition x{world} (snake order by nnz), NCCL all_gather_into_tensor between layers"
+        cfg["parallelism"] = (f"1D row partition x{world} (snake order by nnz); exchange between layers: " +
+                              ("peer stores into symmetric buffers over NVLink + device barrier" if tr.exchange == "peer"
+                               else "NCCL all_gather_into_tensor"))
         line = {
             "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -460,7 +555,9 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
             "gpu_launches": launches,
             "extra": {"nnz_per_rank": [int(t.item()) for t in nnz_all], "rows_per_rank": nl,
                       "collective_bytes_received_per_rank_per_train_step": tr.bytes_per_train_step(),
-                      "last_epoch": last, "cuda_graph": tr._graph is not None, "cuda_graph_error": tr.graph_error},
+                      "last_epoch": last, "cuda_graph": tr._graph is not None, "cuda_graph_error": tr.graph_error,
+                      "exchange": tr.exchange, "exchange_error": tr.exchange_error,
+                      "multicast": bool(tr.px is not None and any(tr.px.multicast.values()))},
         }
         print(json.dumps(line), flush=True)
     shutdown(tr)
