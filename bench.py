@@ -426,6 +426,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", dest="no_cuda_graph", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--no-fused-stores", dest="no_fused_stores", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -139,6 +139,7 @@ int tgcn_masked_nll(const float* Z, int64_t ldz, int64_t n_rows, int32_t n_class
                     const int64_t* y, const uint8_t* mask, int64_t n_mask_total,
                     float* loss_out, double* partial_out,
                     float* dZ, int64_t lddz, int32_t* pred_out, int32_t* correct_out,
+                    void* dZ_mirror_mc /* multicast mapping of dZ or NULL: see (6) */,
                     void* workspace, size_t workspace_bytes, void* stream);
 int tgcn_masked_nll_workspace_bytes(int64_t n_rows, size_t* bytes_out);
 
@@ -159,6 +160,7 @@ typedef struct {
   int32_t act; int32_t drop_mode; float drop_p; const uint8_t* keep_mask; int64_t ldmask;
   uint64_t philox_seed; uint64_t philox_offset; const int64_t* philox_offset_dev;
   void* dZ1; int64_t lddz1; int32_t dz1_dtype;      /* out [n_rows, H] */
+  void* dZ1_mirror_mc;                              /* multicast mapping of dZ1 (fp32) or NULL: see (6) */
   float* dW2; float* db_hidden; float* db_out;      /* out [H*C], [H], [C] */
 } tgcn_dense_bwd_args;
 int tgcn_dense_bwd(const tgcn_dense_bwd_args* args, void* workspace, size_t workspace_bytes, void* stream);
@@ -167,7 +169,7 @@ int tgcn_dense_bwd_workspace_bytes(int32_t H, int32_t C, size_t* bytes_out);
 /* Thin projection P = X W (X [n,K] fp32/bf16, W [K,M]); replaces torch.matmul(x, weight) of a
  * hidden->classes layer when it is not fused into the producing SpMM. */
 int tgcn_project(const void* X, int64_t ldx, int32_t x_dtype, int64_t n_rows, int32_t K,
-                 const float* W, int32_t M, float* P, int64_t ldp, void* stream);
+                 const float* W, int32_t M, float* P, int64_t ldp, void* P_mirror_mc, void* stream);
 
 /* Hierarchy-feature prologue/epilogue for X = [I | F] (text2graph.py:237-241;
  * perlevel_dbpedia.py:140-141):  XW[r,:] = W1[r,:] (+ F[r-n_vocab,:] @ W1[N:, :] on doc rows);
@@ -191,7 +193,7 @@ int tgcn_hier_backward_workspace_bytes(int32_t c_prev, int32_t H, size_t* bytes_
  */
 int tgcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
                    int64_t n, float lr, float beta1, float beta2, float eps, int32_t amsgrad,
-                   int64_t step, const int64_t* step_dev, void* stream);
+                   int64_t step, const int64_t* step_dev, void* param_mirror_mc, void* stream);
 int tgcn_increment_step(int64_t* step_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -200,7 +202,10 @@ int tgcn_increment_step(int64_t* step_dev, void* stream);
  * symmetric buffer at dst_offset_bytes (peer_bases_host: HOST array of `world` device pointers, the
  * peer mappings of the same symmetric allocation), or once through the NVSwitch multicast mapping
  * of that allocation when multicast_base != NULL (multimem.st: the switch replicates).  The caller
- * follows it with a cross-rank barrier before any rank reads.  tgcn_sum_slots adds `n_slots`
+ * follows it with a cross-rank barrier before any rank reads.  The producer kernels of the exchanged
+ * buffers (tgcn_adam_step -> W1, tgcn_project -> P, tgcn_masked_nll -> dZ2, tgcn_dense_bwd -> dZ1)
+ * take an optional `*_mirror_mc` pointer: the multicast mapping of their output, to which they repeat
+ * every store with multimem.st -- compute and exchange in ONE kernel, only the barrier remains.  tgcn_sum_slots adds `n_slots`
  * vectors in slot order (the all-reduce of the small gradients: every rank pushes its vector into
  * slot `rank` of every peer, then sums the slots locally -- bit-identical on all ranks).
  */

@@ -49,6 +49,7 @@ class DenseBwdArgs(C.Structure):
         ("keep_mask", c_void), ("ldmask", C.c_int64),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_offset_dev", c_void),
         ("dZ1", c_void), ("lddz1", C.c_int64), ("dz1_dtype", C.c_int32),
+        ("dZ1_mirror_mc", c_void),
         ("dW2", c_void), ("db_hidden", c_void), ("db_out", c_void),
     ]
 
@@ -68,20 +69,20 @@ SIGNATURES = {
     "tgcn_spmm_plan_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "tgcn_spmm": (C.c_int, [C.POINTER(SpmmArgs), c_void]),
     "tgcn_masked_nll": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int32, c_void, c_void, C.c_int64,
-                                  c_void, c_void, c_void, C.c_int64, c_void, c_void,
+                                  c_void, c_void, c_void, C.c_int64, c_void, c_void, c_void,
                                   c_void, C.c_size_t, c_void]),
     "tgcn_masked_nll_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "tgcn_dense_bwd": (C.c_int, [C.POINTER(DenseBwdArgs), c_void, C.c_size_t, c_void]),
     "tgcn_dense_bwd_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "tgcn_project": (C.c_int, [c_void, C.c_int64, C.c_int32, C.c_int64, C.c_int32, c_void, C.c_int32,
-                               c_void, C.c_int64, c_void]),
+                               c_void, C.c_int64, c_void, c_void]),
     "tgcn_hier_forward": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int64, c_void, C.c_int64, C.c_int32,
                                     C.c_int32, c_void, C.c_int64, c_void]),
     "tgcn_hier_backward": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int64, c_void, C.c_int64, C.c_int32,
                                      C.c_int32, c_void, c_void, C.c_size_t, c_void]),
     "tgcn_hier_backward_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "tgcn_adam_step": (C.c_int, [c_void, c_void, c_void, c_void, c_void, C.c_int64, C.c_float, C.c_float,
-                                 C.c_float, C.c_float, C.c_int32, C.c_int64, c_void, c_void]),
+                                 C.c_float, C.c_float, C.c_int32, C.c_int64, c_void, c_void, c_void]),
     "tgcn_increment_step": (C.c_int, [c_void, c_void]),
     "tgcn_peer_push": (C.c_int, [c_void, c_void, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_void, c_void]),
     "tgcn_sum_slots": (C.c_int, [c_void, C.c_int32, C.c_int64, C.c_int64, c_void, c_void]),

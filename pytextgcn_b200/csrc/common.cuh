@@ -70,6 +70,16 @@ __device__ __forceinline__ uint4 philox_quad(uint64_t e4, uint64_t seed, uint64_
 // uniform in [0,1) from 32 random bits, 24-bit mantissa (same convention as curand_uniform shifted)
 __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
 
+// Stores through an NVSwitch multicast mapping (one store, replicated to every rank's copy of a
+// symmetric buffer).  Used by producer kernels to fuse the exchange step of the row partition into
+// their own output stores (SASS: STG.E[.128].STRONG.SYS on the multicast address).
+__device__ __forceinline__ void multimem_st_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void multimem_st_f32(float* addr, float a) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

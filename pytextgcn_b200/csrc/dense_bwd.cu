@@ -27,6 +27,7 @@ struct DenseBwdParams {
   int32_t act, drop_mode; float drop_p, drop_scale; const uint8_t* __restrict__ keep_mask; int64_t ldmask;
   uint64_t philox_seed, philox_offset; const int64_t* __restrict__ philox_offset_dev;
   void* dZ1; int64_t lddz1; int32_t dz1_dtype;
+  float* dZ1_mirror;   // multicast mapping of dZ1 (fp32 only) or NULL
   // workspace partials
   float* part_dW2;   // [n_cta_x][H*C]
   float* part_dbh;   // [n_cta_x][H]
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
         }
         if (p.dz1_dtype == TGCN_F32) {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dZ1) + row * p.lddz1 + 4 * hq) = make_float4(v[0], v[1], v[2], v[3]);
+          if (p.dZ1_mirror) multimem_st_v4(p.dZ1_mirror + row * p.lddz1 + 4 * hq, v[0], v[1], v[2], v[3]);
         } else {
           __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dZ1) + row * p.lddz1 + 4 * hq);
           o[0] = __floats2bfloat162_rn(v[0], v[1]);
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
           for (int i = 0; i < 4; ++i) dbh[k][i] += v[i];
           if (p.dz1_dtype == TGCN_F32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dZ1) + row * p.lddz1 + 4 * hq) = make_float4(v[0], v[1], v[2], v[3]);
+          if (p.dZ1_mirror) multimem_st_v4(p.dZ1_mirror + row * p.lddz1 + 4 * hq, v[0], v[1], v[2], v[3]);
           } else {
             __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dZ1) + row * p.lddz1 + 4 * hq);
             o[0] = __floats2bfloat162_rn(v[0], v[1]);
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
     __syncthreads();
   }
 
+  if (p.dZ1_mirror) __threadfence_system();
   // ---- per-CTA partials ----
   float* my_dw = p.part_dW2 + (int64_t)blockIdx.x * H * C;
 #pragma unroll
@@ -310,7 +314,7 @@ __global__ void k_reduce_partials(const float* __restrict__ part, int n_parts, i
 constexpr int PJ_ROWS = 4;
 __global__ void __launch_bounds__(256) k_project(const void* __restrict__ X, int64_t ldx, int x_dtype, int64_t n_rows, int K,
                                                  const float* __restrict__ W, int M, float* __restrict__ P, int64_t ldp,
-                                                 int w_in_smem) {
+                                                 int w_in_smem, float* __restrict__ mirror) {
   extern __shared__ __align__(16) float smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* Ws = smem;
@@ -337,13 +341,14 @@ __global__ void __launch_bounds__(256) k_project(const void* __restrict__ X, int
         const float4 x = *reinterpret_cast<const float4*>(rowbuf + k * PJ_ROWS);
         s0 = fmaf(x.x, w, s0); s1 = fmaf(x.y, w, s1); s2 = fmaf(x.z, w, s2); s3 = fmaf(x.w, w, s3);
       }
-      if (row0 + 0 < n_rows) P[(row0 + 0) * ldp + m] = s0;
-      if (row0 + 1 < n_rows) P[(row0 + 1) * ldp + m] = s1;
-      if (row0 + 2 < n_rows) P[(row0 + 2) * ldp + m] = s2;
-      if (row0 + 3 < n_rows) P[(row0 + 3) * ldp + m] = s3;
+      if (row0 + 0 < n_rows) { P[(row0 + 0) * ldp + m] = s0; if (mirror) multimem_st_f32(mirror + (row0 + 0) * ldp + m, s0); }
+      if (row0 + 1 < n_rows) { P[(row0 + 1) * ldp + m] = s1; if (mirror) multimem_st_f32(mirror + (row0 + 1) * ldp + m, s1); }
+      if (row0 + 2 < n_rows) { P[(row0 + 2) * ldp + m] = s2; if (mirror) multimem_st_f32(mirror + (row0 + 2) * ldp + m, s2); }
+      if (row0 + 3 < n_rows) { P[(row0 + 3) * ldp + m] = s3; if (mirror) multimem_st_f32(mirror + (row0 + 3) * ldp + m, s3); }
     }
     __syncwarp();
   }
+  if (mirror) __threadfence_system();
 }
 
 struct DbLayout { size_t off_dw, off_dbh, off_dbo, total; int n_cta; };
@@ -397,6 +402,7 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
   p.keep_mask = a->keep_mask; p.ldmask = a->ldmask;
   p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset; p.philox_offset_dev = a->philox_offset_dev;
   p.dZ1 = a->dZ1; p.lddz1 = a->lddz1; p.dz1_dtype = a->dz1_dtype;
+  p.dZ1_mirror = (a->dz1_dtype == TGCN_F32) ? (float*)a->dZ1_mirror_mc : nullptr;
   p.part_dW2 = (float*)((char*)workspace + L.off_dw);
   p.part_dbh = (float*)((char*)workspace + L.off_dbh);
   p.part_dbo = (float*)((char*)workspace + L.off_dbo);
@@ -445,7 +451,7 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
 }
 
 extern "C" int tgcn_project(const void* X, int64_t ldx, int32_t x_dtype, int64_t n_rows, int32_t K,
-                            const float* W, int32_t M, float* P, int64_t ldp, void* stream_) {
+                            const float* W, int32_t M, float* P, int64_t ldp, void* P_mirror_mc, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   TGCN_CHECK_ARG(X && W && P, "project: null pointer");
   TGCN_CHECK_ARG(n_rows > 0 && K > 0 && M > 0 && ldx >= K && ldp >= M, "project: bad shape");
@@ -454,7 +460,7 @@ extern "C" int tgcn_project(const void* X, int64_t ldx, int32_t x_dtype, int64_t
   size_t smem = ((w_in_smem ? ((K * M + 3) & ~3) : 0) + (size_t)wpb * K * PJ_ROWS) * sizeof(float);
   if (smem > 48 * 1024) TGCN_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(cdiv(cdiv(n_rows, PJ_ROWS), wpb), (int64_t)sm_count() * 8);
-  k_project<<<grid, threads, smem, stream>>>(X, ldx, x_dtype, n_rows, K, W, M, P, ldp, w_in_smem);
+  k_project<<<grid, threads, smem, stream>>>(X, ldx, x_dtype, n_rows, K, W, M, P, ldp, w_in_smem, (float*)P_mirror_mc);
   TGCN_LAUNCH_CHECK();
   return TGCN_OK;
 }

@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(256) k_masked_nll(const float* __restrict__ Z,
                                                     const int64_t* __restrict__ y, const uint8_t* __restrict__ mask,
                                                     float inv_n, float* __restrict__ dZ, int64_t lddz,
                                                     int32_t* __restrict__ pred, float* __restrict__ row_nll,
-                                                    int32_t* __restrict__ row_hit) {
+                                                    int32_t* __restrict__ row_hit, float* __restrict__ dZ_mirror) {
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) k_masked_nll(const float* __restrict__ Z,
   const bool need_fwd = m || pred;
   const float* z = Z + row * ldz;
   if (!need_fwd) {
-    if (dZ) for (int c = lane; c < C; c += 32) dZ[row * lddz + c] = 0.0f;
+    if (dZ) for (int c = lane; c < C; c += 32) { dZ[row * lddz + c] = 0.0f; if (dZ_mirror) multimem_st_f32(dZ_mirror + row * lddz + c, 0.0f); }
     if (lane == 0) { row_nll[row] = 0.0f; if (row_hit) row_hit[row] = 0; }
     return;
   }
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) k_masked_nll(const float* __restrict__ Z,
   }
   if (pred && lane == 0) pred[row] = arg;
   if (!m) {
-    if (dZ) for (int c = lane; c < C; c += 32) dZ[row * lddz + c] = 0.0f;
+    if (dZ) for (int c = lane; c < C; c += 32) { dZ[row * lddz + c] = 0.0f; if (dZ_mirror) multimem_st_f32(dZ_mirror + row * lddz + c, 0.0f); }
     if (lane == 0) { row_nll[row] = 0.0f; if (row_hit) row_hit[row] = 0; }
     return;
   }
@@ -54,8 +54,11 @@ __global__ void __launch_bounds__(256) k_masked_nll(const float* __restrict__ Z,
   if (dZ) {
     for (int c = lane; c < C; c += 32) {
       float pr = expf(z[c] - lse);
-      dZ[row * lddz + c] = (pr - (c == (int)yi ? 1.0f : 0.0f)) * inv_n;
+      const float gz = (pr - (c == (int)yi ? 1.0f : 0.0f)) * inv_n;
+      dZ[row * lddz + c] = gz;
+      if (dZ_mirror) multimem_st_f32(dZ_mirror + row * lddz + c, gz);
     }
+    if (dZ_mirror) __threadfence_system();
   }
 }
 
@@ -132,7 +135,7 @@ extern "C" int tgcn_masked_nll_workspace_bytes(int64_t n_rows, size_t* bytes_out
 extern "C" int tgcn_masked_nll(const float* Z, int64_t ldz, int64_t n_rows, int32_t C,
                                const int64_t* y, const uint8_t* mask, int64_t n_mask_total,
                                float* loss_out, double* partial_out, float* dZ, int64_t lddz,
-                               int32_t* pred_out, int32_t* correct_out,
+                               int32_t* pred_out, int32_t* correct_out, void* dZ_mirror_mc,
                                void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   TGCN_CHECK_ARG(Z && y, "masked_nll: Z / y null");
@@ -149,7 +152,7 @@ extern "C" int tgcn_masked_nll(const float* Z, int64_t ldz, int64_t n_rows, int3
   const float inv_n = n_mask_total > 0 ? 1.0f / (float)n_mask_total : 0.0f;
   const int T = 256;
   k_masked_nll<<<(unsigned)cdiv(n_rows * 32, T), T, 0, stream>>>(Z, ldz, n_rows, C, y, mask, inv_n, dZ, lddz, pred_out, row_nll,
-                                                                  correct_out ? row_hit : nullptr);
+                                                                  correct_out ? row_hit : nullptr, dZ ? (float*)dZ_mirror_mc : nullptr);
   TGCN_LAUNCH_CHECK();
   // slice partials live in the last 4 KB of the caller's workspace (nothing is allocated here)
   static_assert(NLL_PARTS * (sizeof(double) + 2 * sizeof(int32_t)) <= 4096, "partials must fit the tail pad");

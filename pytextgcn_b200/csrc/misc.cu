@@ -33,7 +33,7 @@ int sm_count() {
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, float* __restrict__ vmax, int64_t n, float lr,
                                               float b1, float b2, float eps, int amsgrad, int64_t step_host,
-                                              const int64_t* __restrict__ step_dev) {
+                                              const int64_t* __restrict__ step_dev, float* __restrict__ mirror) {
   __shared__ float s_hyp[2];
   if (threadIdx.x == 0) {
     const double t = (double)(step_dev ? *step_dev : step_host);
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
   const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n >> 2;
-  const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)(vmax ? vmax : p)) & 15) == 0);
+  const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)(vmax ? vmax : p) | (uintptr_t)(mirror ? mirror : p)) & 15) == 0);
   int64_t start_tail = 0;
   if (vec) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
         pp[k] = pp[k] - step_size * (mm[k] / denom);
       }
       reinterpret_cast<float4*>(p)[i] = P;
+      if (mirror) multimem_st_v4(mirror + 4 * i, P.x, P.y, P.z, P.w);   // updated rows land in every rank's copy
       reinterpret_cast<float4*>(m)[i] = M;
       reinterpret_cast<float4*>(v)[i] = V;
       if (amsgrad) reinterpret_cast<float4*>(vmax)[i] = X;
@@ -79,8 +80,11 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
     float vh = vi;
     if (amsgrad) { vh = fmaxf(vmax[i], vi); vmax[i] = vh; }
     m[i] = mi; v[i] = vi;
-    p[i] = p[i] - step_size * (mi / (sqrtf(vh) / bc2s + eps));
+    const float pn = p[i] - step_size * (mi / (sqrtf(vh) / bc2s + eps));
+    p[i] = pn;
+    if (mirror) multimem_st_f32(mirror + i, pn);
   }
+  if (mirror) __threadfence_system();
 }
 
 __global__ void k_increment(int64_t* c) { *c += 1; }
@@ -190,7 +194,7 @@ extern "C" int tgcn_device_info(int* sm, int* major, int* minor) {
 
 extern "C" int tgcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
                               int64_t n, float lr, float beta1, float beta2, float eps, int32_t amsgrad,
-                              int64_t step, const int64_t* step_dev, void* stream_) {
+                              int64_t step, const int64_t* step_dev, void* param_mirror_mc, void* stream_) {
   TGCN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
   TGCN_CHECK_ARG(!amsgrad || max_exp_avg_sq, "adam_step: amsgrad needs max_exp_avg_sq");
   TGCN_CHECK_ARG(n >= 0, "adam_step: n < 0");
@@ -199,7 +203,7 @@ extern "C" int tgcn_adam_step(float* param, const float* grad, float* exp_avg, f
   const int T = 256;
   const int64_t blocks = std::min<int64_t>(cdiv(cdiv(n, 4), T), (int64_t)sm_count() * 8);
   k_adam<<<(unsigned)std::max<int64_t>(blocks, 1), T, 0, (cudaStream_t)stream_>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr,
-                                                                                 beta1, beta2, eps, amsgrad, step, step_dev);
+                                                                                 beta1, beta2, eps, amsgrad, step, step_dev, (float*)param_mirror_mc);
   TGCN_LAUNCH_CHECK();
   return TGCN_OK;
 }

@@ -161,7 +161,7 @@ class DistTextGCNTrainer:
     def __init__(self, g, n_classes: int, hidden: int, dropout: float, lr: float, amsgrad: bool,
                  rank: int, world: int, dev: torch.device, seed: int = 0, betas=(0.9, 0.999), eps: float = 1e-8,
                  graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None,
-                 use_cuda_graph: bool = False, exchange: str = "peer"):
+                 use_cuda_graph: bool = False, exchange: str = "peer", fused_stores: bool = True):
         import torch.distributed as dist
         from . import ops
         from .graph import upload_graph
@@ -234,8 +234,10 @@ class DistTextGCNTrainer:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         # activations
         self.H1d = torch.empty((nl, H), **f32)
-        self.P_full = xbuf("P", (npad, Cp))
-        self.P_loc = self.P_full[lo:lo + nl]
+        self.Pt_full = xbuf("Pt", (npad, Cp))        # projected rows, train forward
+        self.Pt_loc = self.Pt_full[lo:lo + nl]
+        self.Pe_full = xbuf("Pe", (npad, Cp))        # projected rows, eval forward (double buffer)
+        self.Pe_loc = self.Pe_full[lo:lo + nl]
         self.Z2 = torch.zeros((nl, Cp), **f32)
         self.dZ2_full = xbuf("dZ2", (npad, Cp))
         self.dZ2_loc = self.dZ2_full[lo:lo + nl]
@@ -257,7 +259,11 @@ class DistTextGCNTrainer:
         self.train_mask = tm_new[lo:lo + nl].to(dev).contiguous()
         self.val_mask = vm_new[lo:lo + nl].to(dev).contiguous()
         self.n_train, self.n_val = int(g.train_mask.sum()), int(g.val_mask.sum())
-        self.w1_stale = True          # W1_full rows of the other ranks need a gather
+        self.w1_stale = False         # every rank initialised the full W1 identically
+        self._w1_mirrored = False
+        self._pending_reads = set()
+        self.fused_stores = bool(fused_stores and self.px is not None and
+                                 all(self.px.multicast.get(k, 0) for k in ("W1", "Pt", "Pe", "dZ2", "dZ1")))
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._eager_epochs = 0
@@ -282,14 +288,48 @@ class DistTextGCNTrainer:
         return out
 
     # ---- collectives ----
-    def _all_gather(self, full: torch.Tensor, loc: torch.Tensor, name: Optional[str] = None) -> None:
-        if self.world > 1:
-            if self.px is not None and name is not None:
-                self.px.push(name, loc, loc.data_ptr() - full.data_ptr())   # peer stores + barrier
-            else:
-                self.dist.all_gather_into_tensor(full, loc)  # in place: loc is the rank-th slice of full
-        elif full.data_ptr() != loc.data_ptr():
-            full[:loc.shape[0]].copy_(loc)
+    # One-sided stores need two guarantees the two-sided ncclAllGather gave for free:
+    #  (1) visibility: a barrier after the producers, before any rank reads the exchanged buffer;
+    #  (2) no overwrite of a buffer a slower rank may still be reading: at least one barrier must lie
+    #      between a buffer's last consumer and its next producer.  `_pending_reads` tracks (2) on the
+    #      host -- identically on every rank, the control flow is the same -- and inserts an extra
+    #      barrier only when none happened in between (never in the steady-state epoch: P is
+    #      double-buffered between the train and the eval forward for exactly that reason).
+    def _barrier(self) -> None:
+        self.px.barrier()
+        self._pending_reads.clear()
+
+    def _before_write(self, name: str) -> None:
+        if self.px is not None and name in self._pending_reads:
+            self._barrier()
+
+    def _note_read(self, name: str) -> None:
+        if self.px is not None:
+            self._pending_reads.add(name)
+
+    def _mirror(self, name: str, loc: torch.Tensor, full: torch.Tensor) -> Optional[int]:
+        """Multicast address of `loc` inside symmetric buffer `name` (None when the producer cannot fuse)."""
+        if self.px is None or not self.fused_stores:
+            return None
+        return self.px.multicast[name] + (loc.data_ptr() - full.data_ptr())
+
+    def _exchange(self, full: torch.Tensor, loc: torch.Tensor, name: str, produced_with_mirror: bool) -> None:
+        """Make every rank's slice of `name` visible everywhere."""
+        if self.world == 1:
+            if full.data_ptr() != loc.data_ptr():
+                full[:loc.shape[0]].copy_(loc)
+            return
+        if self.px is None:
+            self.dist.all_gather_into_tensor(full, loc)          # in place: loc is the rank-th slice of full
+            return
+        if not produced_with_mirror:                              # separate push kernel (peer or multicast stores)
+            from . import _native
+            lib = _native.load()
+            with torch.cuda.device(self.dev):
+                _native.check(lib.tgcn_peer_push(loc.data_ptr(), self.px.peer_arrays[name], self.world, self.rank,
+                                                 loc.numel() * loc.element_size(), loc.data_ptr() - full.data_ptr(),
+                                                 self.px.multicast[name] or None, torch.cuda.current_stream().cuda_stream))
+        self._barrier()
 
     def _all_reduce_small(self) -> None:
         """self.small = sum over ranks of the packed (db1, dW2, db2) partials."""
@@ -298,17 +338,18 @@ class DistTextGCNTrainer:
         elif self.px is not None:
             from . import _native
             lib = _native.load()
-            self.px.push("small", self.small_local, self.rank * self.n_small_pad * 4)
+            self._exchange(self.small_slots, self.small_local, "small", False)
             with torch.cuda.device(self.dev):
                 _native.check(lib.tgcn_sum_slots(self.small_slots.data_ptr(), self.world, self.n_small_pad, self.n_small_pad,
                                                  self.small.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            self._note_read("small")
         else:
             self.small.copy_(self.small_local)
             self.dist.all_reduce(self.small)
 
     def _gather_w1(self) -> None:
         if self.w1_stale:
-            self._all_gather(self.W1_full, self.W1_loc, "W1")
+            self._exchange(self.W1_full, self.W1_loc, "W1", self._w1_mirrored)
             self.w1_stale = False
 
     def _forward(self, training: bool) -> None:
@@ -319,41 +360,59 @@ class DistTextGCNTrainer:
         drop = training and self.p > 0
         ops.spmm(self.shard, self.W1_full, F=self.H, plan=self.plan, out=self.H1d, bias=self.b1,
                  drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
-                 philox_offset_dev=self.step_dev if drop else None, W_proj=self.W2, P=self.P_loc,
-                 row_id_offset=self.rank * self.part.n_loc)
+                 philox_offset_dev=self.step_dev if drop else None, row_id_offset=self.rank * self.part.n_loc)
+        self._note_read("W1")
         self._mark("spmm_wide_fwd")
-        self._all_gather(self.P_full, self.P_loc, "P")
+        pname = "Pt" if training else "Pe"                       # double-buffered, see _pending_reads
+        P_full, P_loc = (self.Pt_full, self.Pt_loc) if training else (self.Pe_full, self.Pe_loc)
+        self._before_write(pname)
+        mir = self._mirror(pname, P_loc, P_full)
+        ops.project(self.H1d, self.W2, K=self.H, out=P_loc, mirror=mir)     # layer 2's thin X W, stored to all ranks
+        self._exchange(P_full, P_loc, pname, mir is not None)
         self._mark("allgather_P")
-        ops.spmm(self.shard, self.P_full, F=self.Cp, plan=self.plan, out=self.Z2, bias=self.b2)
+        ops.spmm(self.shard, P_full, F=self.Cp, plan=self.plan, out=self.Z2, bias=self.b2)
+        self._note_read(pname)
         self._mark("spmm_narrow_fwd")
 
     def train_step(self) -> None:
-        ops, dist = self.ops, self.dist
+        ops = self.ops
         self._forward(True)
+        self._before_write("dZ2")
+        mir = self._mirror("dZ2", self.dZ2_loc, self.dZ2_full)
         ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2_loc,
-                       loss_out=self.loss_buf, workspace=self._nll_ws, partial=self.loss_part)
+                       loss_out=self.loss_buf, workspace=self._nll_ws, partial=self.loss_part, dZ_mirror=mir)
         self._mark("masked_nll")
-        self._all_gather(self.dZ2_full, self.dZ2_loc, "dZ2")
+        self._exchange(self.dZ2_full, self.dZ2_loc, "dZ2", mir is not None)
         self._mark("allgather_dZ2")
         ops.spmm(self.shard, self.dZ2_full, F=self.Cp, plan=self.plan, out=self.G2)
+        self._note_read("dZ2")
         self._mark("spmm_narrow_bwd")
         drop = self.p > 0
+        self._before_write("dZ1")
+        self._before_write("small")
+        mir = self._mirror("dZ1", self.dZ1_loc, self.dZ1_full)
         r = ops.dense_bwd(self.G2, self.H1d, self.W2, self.dZ2_loc, H=self.H, n_classes=self.C,
                           drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
                           philox_offset_dev=self.step_dev if drop else None, row_offset=self.rank * self.part.n_loc,
-                          dZ1=self.dZ1_loc, workspace=self._db_ws, dW2=self.l_W2, db_hidden=self.l_b1, db_out=self.l_b2)
+                          dZ1=self.dZ1_loc, workspace=self._db_ws, dW2=self.l_W2, db_hidden=self.l_b1, db_out=self.l_b2,
+                          dZ1_mirror=mir)
         self._db_ws = r["workspace"]
         self._mark("dense_bwd")
-        self._all_reduce_small()
+        self._all_reduce_small()          # its barrier also publishes the mirrored dZ1 stores
         self._mark("allreduce_small_grads")
-        self._all_gather(self.dZ1_full, self.dZ1_loc, "dZ1")
+        if not (mir is not None and self.px is not None):
+            self._exchange(self.dZ1_full, self.dZ1_loc, "dZ1", False)
         self._mark("allgather_dZ1")
         ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1)
+        self._note_read("dZ1")
         self._mark("spmm_wide_bwd")
         ops.increment_step(self.step_dev)
         kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad,
                   step_dev=self.step_dev)
-        ops.adam_step(self.W1_loc, self.g_W1, *self.st[0], **kw)
+        self._before_write("W1")
+        mir = self._mirror("W1", self.W1_loc, self.W1_full)
+        ops.adam_step(self.W1_loc, self.g_W1, *self.st[0], param_mirror=mir, **kw)    # updated rows go to every rank
+        self._w1_mirrored = mir is not None
         ops.adam_step(self.b1, self.g_b1.contiguous(), *self.st[1], **kw)
         ops.adam_step(self.W2, self.g_W2, *self.st[2], **kw)
         ops.adam_step(self.b2, self.g_b2.contiguous(), *self.st[3], **kw)
@@ -430,7 +489,10 @@ class DistTextGCNTrainer:
     def logits_old_order(self) -> torch.Tensor:
         """All-gathered logits of the last forward, original node order (host-facing helper)."""
         full = torch.zeros((self.part.n_pad, self.Cp), dtype=torch.float32, device=self.dev)
-        self._all_gather(full, self.Z2.contiguous())
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(full, self.Z2.contiguous())
+        else:
+            full[:self.Z2.shape[0]].copy_(self.Z2)
         return self.part.to_old(full)[:, :self.C]
 
     def bytes_per_train_step(self) -> int:
@@ -484,7 +546,7 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
     n = int(g.x.shape[0])
     tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad,
                             rank, world, dev, seed=args.seed, use_cuda_graph=not getattr(args, "no_cuda_graph", False),
-                            exchange=getattr(args, "exchange", "peer"))
+                            exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False))
     epoch = tr.epoch
 
     for _ in range(W):
@@ -544,7 +606,8 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
         clocks = sampler.stop()
         cfg = workload_config(shape, g)
         cfg["parallelism"] = (f"1D row partition x{world} (snake order by nnz); exchange between layers: " +
-                              ("peer stores into symmetric buffers over NVLink + device barrier" if tr.exchange == "peer"
+                              (("multimem stores fused into the producer kernels + device barrier" if tr.fused_stores else
+                                "peer-store push kernel into symmetric buffers + device barrier") if tr.exchange == "peer"
                                else "NCCL all_gather_into_tensor"))
         line = {
             "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -556,7 +619,7 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
             "extra": {"nnz_per_rank": [int(t.item()) for t in nnz_all], "rows_per_rank": nl,
                       "collective_bytes_received_per_rank_per_train_step": tr.bytes_per_train_step(),
                       "last_epoch": last, "cuda_graph": tr._graph is not None, "cuda_graph_error": tr.graph_error,
-                      "exchange": tr.exchange, "exchange_error": tr.exchange_error,
+                      "exchange": tr.exchange, "exchange_error": tr.exchange_error, "fused_stores": tr.fused_stores,
                       "multicast": bool(tr.px is not None and any(tr.px.multicast.values()))},
         }
         print(json.dumps(line), flush=True)

@@ -118,7 +118,7 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
                want_correct: bool = False, loss_out: Optional[torch.Tensor] = None,
                workspace: Optional[torch.Tensor] = None, pred: Optional[torch.Tensor] = None,
                correct: Optional[torch.Tensor] = None, want_partial: bool = False,
-               partial: Optional[torch.Tensor] = None):
+               partial: Optional[torch.Tensor] = None, dZ_mirror: Optional[int] = None):
     """Masked mean cross-entropy over rows of Z (+ gradient / argmax / #correct).  See tgcn_masked_nll.
     Returns dict(loss=[2] fp32 (mean nll, count), dZ, pred, correct, partial)."""
     _need_cuda(Z, y, mask, dZ)
@@ -148,7 +148,7 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
         _native.check(lib.tgcn_masked_nll(Z.data_ptr(), Z.stride(0), n, n_classes, y.data_ptr(), _native.ptr(mask),
                                           int(n_mask_total), loss_out.data_ptr(), _native.ptr(partial),
                                           _native.ptr(dZ) if want_grad else None, dZ.stride(0) if want_grad else 0,
-                                          _native.ptr(pred), _native.ptr(correct),
+                                          _native.ptr(pred), _native.ptr(correct), dZ_mirror,
                                           workspace.data_ptr(), workspace.numel(), _stream()))
     return dict(loss=loss_out, dZ=dZ if want_grad else None, pred=pred, correct=correct, partial=partial)
 
@@ -159,7 +159,7 @@ def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Option
               philox_offset_dev: Optional[torch.Tensor] = None, row_offset: int = 0, dZ1: Optional[torch.Tensor] = None, dz1_dtype: torch.dtype = torch.float32,
               want_dz1: bool = True, workspace: Optional[torch.Tensor] = None,
               dW2: Optional[torch.Tensor] = None, db_hidden: Optional[torch.Tensor] = None,
-              db_out: Optional[torch.Tensor] = None):
+              db_out: Optional[torch.Tensor] = None, dZ1_mirror: Optional[int] = None):
     """dW2 = H1d^T G2, db_out = colsum(dZ2), dZ1 = (G2 W2^T) * dropout' * act', db_hidden = colsum(dZ1)."""
     _need_cuda(G2, H1d, W2, dZ2, keep_mask, dZ1)
     lib = _native.load()
@@ -184,6 +184,7 @@ def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Option
             width = pad4(H) if dz1_dtype == torch.float32 else pad8(H)
             dZ1 = torch.zeros((n, width), dtype=dz1_dtype, device=dev)
         a.dZ1, a.lddz1, a.dz1_dtype = dZ1.data_ptr(), dZ1.stride(0), _dt(dZ1)
+        a.dZ1_mirror_mc = dZ1_mirror
     if dW2 is None:
         dW2 = torch.empty((H, n_classes), dtype=torch.float32, device=dev)
     if db_hidden is None and want_dz1:
@@ -200,7 +201,8 @@ def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Option
     return dict(dW2=dW2, db_hidden=db_hidden, db_out=db_out, dZ1=dZ1 if want_dz1 else None, workspace=workspace)
 
 
-def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Optional[torch.Tensor] = None,
+            mirror: Optional[int] = None) -> torch.Tensor:
     """P = X[:, :K] @ W (thin hidden->classes projection), P padded to a multiple of 4 columns."""
     _need_cuda(X, W, out)
     lib = _native.load()
@@ -213,7 +215,7 @@ def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Opti
         out = torch.zeros((n, pad4(M)), dtype=torch.float32, device=X.device)
     with torch.cuda.device(X.device):
         _native.check(lib.tgcn_project(X.data_ptr(), X.stride(0), _dt(X), n, K, W.data_ptr(), M,
-                                       out.data_ptr(), out.stride(0), _stream()))
+                                       out.data_ptr(), out.stride(0), mirror, _stream()))
     return out
 
 
@@ -251,7 +253,8 @@ def hier_backward(G1: torch.Tensor, n_nodes: int, n_vocab: int, Fdoc: torch.Tens
 
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
               max_exp_avg_sq: Optional[torch.Tensor], *, lr: float, beta1: float = 0.9, beta2: float = 0.999,
-              eps: float = 1e-8, amsgrad: bool = False, step: int = 0, step_dev: Optional[torch.Tensor] = None) -> None:
+              eps: float = 1e-8, amsgrad: bool = False, step: int = 0, step_dev: Optional[torch.Tensor] = None,
+              param_mirror: Optional[int] = None) -> None:
     """In-place fused Adam/AMSGrad update (torch.optim.Adam semantics, flat_amazon.py:89,106)."""
     _need_cuda(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, step_dev)
     lib = _native.load()
@@ -261,7 +264,7 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, ex
     with torch.cuda.device(param.device):
         _native.check(lib.tgcn_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                          _native.ptr(max_exp_avg_sq), param.numel(), lr, beta1, beta2, eps,
-                                         1 if amsgrad else 0, int(step), _native.ptr(step_dev), _stream()))
+                                         1 if amsgrad else 0, int(step), _native.ptr(step_dev), param_mirror, _stream()))
 
 
 def increment_step(step_dev: torch.Tensor) -> None:

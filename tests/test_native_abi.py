@@ -54,7 +54,7 @@ def test_host_only_calls(lib):
     # argument validation happens before any CUDA call
     assert lib.tgcn_spmm(None, None) != 0
     assert b"args null" in lib.tgcn_last_error()
-    assert lib.tgcn_adam_step(None, None, None, None, None, 4, 0.1, 0.9, 0.999, 1e-8, 0, 1, None, None) != 0
+    assert lib.tgcn_adam_step(None, None, None, None, None, 4, 0.1, 0.9, 0.999, 1e-8, 0, 1, None, None, None) != 0
 
 
 def test_struct_layout_matches_c(lib, tmp_path):
