@@ -1,6 +1,6 @@
 """Developer timing script (not the contract bench): per-kernel CUDA-event timings."""
 import sys, time, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from pytextgcn_b200 import make_graph, ops, GCN
 from pytextgcn_b200.graph import upload_graph
 

@@ -1,5 +1,5 @@
 import os, sys, time, json, torch, torch.distributed as dist
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from pytextgcn_b200.dist import DistTextGCNTrainer, shutdown
 from pytextgcn_b200.synthetic import make_graph, SHAPES
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])

@@ -1,6 +1,6 @@
 """One wide + one narrow SpMM at a named shape, for ncu captures."""
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from pytextgcn_b200 import make_graph, ops
 from pytextgcn_b200.graph import upload_graph
 from pytextgcn_b200.synthetic import SHAPES

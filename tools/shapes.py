@@ -1,6 +1,6 @@
 """Runs the fused trainer on every named benchmark shape and prints ms/epoch."""
 import sys, time, json, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from pytextgcn_b200 import make_graph, GCN, SHAPES
 from pytextgcn_b200.trainer import TextGCNTrainer
 from pytextgcn_b200.graph import upload_graph

@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from pytextgcn_b200 import make_graph, ops
 from pytextgcn_b200.graph import upload_graph
 from pytextgcn_b200.dist import RowPartition, shard_graph
