@@ -91,6 +91,7 @@ int tgcn_csr_from_coo_gcn_norm(const int64_t* edge_src, const int64_t* edge_dst,
 int tgcn_spmm_plan(const int32_t* rowptr, int64_t row_begin, int64_t row_end, int32_t chunk_nnz,
                    int32_t* chunks /* [cap][4] */, int64_t chunk_capacity,
                    int32_t* split_rows /* [cap][3] = {row, first_slot, n_slots} */,
+                   int32_t* slot_owner /* optional [n_slots]: split-row index owning each scratch slot */,
                    int32_t* counts_out, void* workspace, size_t workspace_bytes, void* stream);
 int tgcn_spmm_plan_workspace_bytes(int64_t n_rows, size_t* bytes_out);
 
@@ -110,6 +111,8 @@ typedef struct {
   const int32_t* rowptr; const int32_t* colidx; const float* val;   /* CSR of A_hat */
   const int32_t* chunks; int32_t n_chunks;                           /* plan */
   const int32_t* split_rows; int32_t n_split_rows;
+  const int32_t* slot_owner;    /* from tgcn_spmm_plan; with split_counters: the last-arriving chunk of a split row */
+  int32_t* split_counters;      /* reduces it inside the kernel (int32[n_split_rows], zero once; self-resetting) */
   float* scratch;                                                    /* partial rows */
   const void* B; int64_t ldb; int32_t b_dtype;
   void* C; int64_t ldc; int32_t c_dtype;                             /* may be NULL if only P wanted */

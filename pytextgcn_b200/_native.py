@@ -23,6 +23,7 @@ class SpmmArgs(C.Structure):
         ("rowptr", c_void), ("colidx", c_void), ("val", c_void),
         ("chunks", c_void), ("n_chunks", C.c_int32),
         ("split_rows", c_void), ("n_split_rows", C.c_int32),
+        ("slot_owner", c_void), ("split_counters", c_void),
         ("scratch", c_void),
         ("B", c_void), ("ldb", C.c_int64), ("b_dtype", C.c_int32),
         ("C", c_void), ("ldc", C.c_int64), ("c_dtype", C.c_int32),
@@ -64,7 +65,7 @@ SIGNATURES = {
     "tgcn_csr_from_coo_gcn_norm": (C.c_int, [c_void, c_void, C.c_int64, c_void, C.c_int64, C.c_int64,
                                              c_void, c_void, c_void, c_void, c_void, c_void,
                                              c_void, C.c_size_t, c_void]),
-    "tgcn_spmm_plan": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int32, c_void, C.c_int64, c_void, c_void,
+    "tgcn_spmm_plan": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int32, c_void, C.c_int64, c_void, c_void, c_void,
                                  c_void, C.c_size_t, c_void]),
     "tgcn_spmm_plan_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "tgcn_spmm": (C.c_int, [C.POINTER(SpmmArgs), c_void]),

@@ -19,6 +19,7 @@ struct SpmmParams {
   const int32_t* __restrict__ rowptr; const int32_t* __restrict__ colidx; const float* __restrict__ val;
   const int4* __restrict__ chunks; int32_t n_chunks;
   const int32_t* __restrict__ split_rows; int32_t n_split_rows;
+  const int32_t* __restrict__ slot_owner; int32_t* split_counters;   // both set: the last chunk of a split row reduces it in-kernel
   float* scratch;
   const void* __restrict__ B; int64_t ldb;
   void* C; int64_t ldc; int32_t c_dtype;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
       for (int i = 0; i < E; ++i) acc[v][i] += __shfl_down_sync(0xffffffffu, acc[v][i], o);
 
   if (ch.w >= 0) {
-    // split row: raw fp32 partial, reduced by k_spmm_fixup
+    // split row: raw fp32 partial into the scratch slot of this chunk
     if (lane < LPR) {
       float* s = p.scratch + (int64_t)ch.w * F;
 #pragma unroll
@@ -265,7 +266,38 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
         }
       }
     }
-    return;
+    if (p.split_counters == nullptr) return;          // reduced by k_spmm_fixup afterwards
+    // The chunk that arrives LAST adds the partial rows in slot order (the order is fixed, so the
+    // result does not depend on which chunk that is) and runs the epilogue: no second kernel.
+    const int sr = __ldg(p.slot_owner + ch.w);
+    const int first = __ldg(p.split_rows + 3 * sr + 1), n = __ldg(p.split_rows + 3 * sr + 2);
+    __threadfence();
+    int arrived = 0;
+    if (lane == 0) arrived = atomicAdd(p.split_counters + sr, 1);
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (arrived != n - 1) return;
+    __threadfence();
+    if (lane == 0) p.split_counters[sr] = 0;          // self-resetting: ready for the next launch
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+      for (int i = 0; i < E; ++i) acc[v][i] = 0.0f;
+    if (lane < LPR) {
+      for (int sl = 0; sl < n; ++sl) {
+        const float* src = p.scratch + (int64_t)(first + sl) * F;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c0 = (l + v * LPR) * E;
+          if (c0 < F) {
+#pragma unroll
+            for (int q = 0; q < E / 4; ++q) {
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(src + c0 + 4 * q));   // L2: written by other SMs
+              acc[v][4 * q] += t.x; acc[v][4 * q + 1] += t.y; acc[v][4 * q + 2] += t.z; acc[v][4 * q + 3] += t.w;
+            }
+          }
+        }
+      }
+    }
   }
   row_epilogue<LPR, VPL, E, PROJ>(p, ch.x, lane, acc, smem_w);
   }
@@ -319,7 +351,8 @@ __global__ void __launch_bounds__(256) k_spmm_fixup(const SpmmParams p) {
 // Single CTA, three running prefix sums (chunks, partial slots, split rows) over the rows.
 __global__ void __launch_bounds__(1024) k_plan(const int32_t* __restrict__ rowptr, int64_t row_begin, int64_t row_end,
                                                int32_t chunk_nnz, int4* __restrict__ chunks, int64_t cap,
-                                               int32_t* __restrict__ split_rows, int32_t* __restrict__ counts) {
+                                               int32_t* __restrict__ split_rows, int32_t* __restrict__ slot_owner,
+                                               int32_t* __restrict__ counts) {
   __shared__ int s_warp[3][32];
   __shared__ int s_base[3];
   __shared__ int s_maxlen;
@@ -365,6 +398,7 @@ __global__ void __launch_bounds__(1024) k_plan(const int32_t* __restrict__ rowpt
         for (int c = 0; c < nch; ++c) {
           const int cb = b + c * per, ce = min(b + len, cb + per);
           if (excl[0] + c < cap) chunks[excl[0] + c] = make_int4((int)r, cb, ce, excl[1] + c);
+          if (slot_owner) slot_owner[excl[1] + c] = excl[2];
         }
         split_rows[3 * excl[2]] = (int)r; split_rows[3 * excl[2] + 1] = excl[1]; split_rows[3 * excl[2] + 2] = nch;
       }
@@ -397,7 +431,7 @@ static int launch_spmm_t(const SpmmParams& p, cudaStream_t stream) {
     k_spmm<TB, LPR, VPL, PROJ><<<(unsigned)grid, threads, smem, stream>>>(p);
     TGCN_LAUNCH_CHECK();
   }
-  if (p.n_split_rows > 0) {
+  if (p.n_split_rows > 0 && p.split_counters == nullptr) {
     k_spmm_fixup<LPR, VPL, E, PROJ><<<(unsigned)cdiv(p.n_split_rows, wpb), threads, smem, stream>>>(p);
     TGCN_LAUNCH_CHECK();
   }
@@ -436,15 +470,15 @@ extern "C" int tgcn_spmm_plan_workspace_bytes(int64_t n_rows, size_t* bytes_out)
 }
 
 extern "C" int tgcn_spmm_plan(const int32_t* rowptr, int64_t row_begin, int64_t row_end, int32_t chunk_nnz,
-                              int32_t* chunks, int64_t chunk_capacity, int32_t* split_rows, int32_t* counts_out,
-                              void* workspace, size_t workspace_bytes, void* stream_) {
+                              int32_t* chunks, int64_t chunk_capacity, int32_t* split_rows, int32_t* slot_owner,
+                              int32_t* counts_out, void* workspace, size_t workspace_bytes, void* stream_) {
   (void)workspace; (void)workspace_bytes;
   cudaStream_t stream = (cudaStream_t)stream_;
   TGCN_CHECK_ARG(rowptr && chunks && split_rows && counts_out, "spmm_plan: null pointer");
   TGCN_CHECK_ARG(row_begin >= 0 && row_end >= row_begin, "spmm_plan: bad row range");
   TGCN_CHECK_ARG(chunk_nnz >= 32, "spmm_plan: chunk_nnz must be >= 32");
   k_plan<<<1, 1024, 0, stream>>>(rowptr, row_begin, row_end, chunk_nnz, reinterpret_cast<int4*>(chunks), chunk_capacity,
-                                 split_rows, counts_out);
+                                 split_rows, slot_owner, counts_out);
   TGCN_LAUNCH_CHECK();
   return TGCN_OK;
 }
@@ -477,6 +511,7 @@ extern "C" int tgcn_spmm(const tgcn_spmm_args* a, void* stream_) {
   p.rowptr = a->rowptr; p.colidx = a->colidx; p.val = a->val;
   p.chunks = reinterpret_cast<const int4*>(a->chunks); p.n_chunks = a->n_chunks;
   p.split_rows = a->split_rows; p.n_split_rows = a->n_split_rows;
+  p.slot_owner = a->slot_owner; p.split_counters = (a->slot_owner && a->split_counters) ? a->split_counters : nullptr;
   p.scratch = a->scratch;
   p.B = a->B; p.ldb = a->ldb;
   p.C = a->C; p.ldc = a->ldc; p.c_dtype = a->c_dtype;

@@ -46,6 +46,8 @@ class SpmmPlan:
     n_split_rows: int
     n_slots: int
     max_row_nnz: int
+    slot_owner: Optional[torch.Tensor] = None    # int32 [n_slots]: split-row index of each scratch slot
+    counters: Optional[torch.Tensor] = None      # int32 [n_split_rows], zero; arrival counters (self-resetting)
     _scratch: Dict[int, torch.Tensor] = field(default_factory=dict)
 
     def scratch(self, F: int) -> Optional[torch.Tensor]:
@@ -96,8 +98,9 @@ class GraphCSR:
             chunks = torch.empty((cap, 4), dtype=torch.int32, device=self.device)
             split = torch.empty((max(nnz_range // chunk_nnz + 1, 1), 3), dtype=torch.int32, device=self.device)
             counts = torch.zeros(4, dtype=torch.int32, device=self.device)
+            owner = torch.zeros(cap, dtype=torch.int32, device=self.device)
             _native.check(lib.tgcn_spmm_plan(self.rowptr.data_ptr(), row_begin, row_end, chunk_nnz,
-                                             chunks.data_ptr(), cap, split.data_ptr(), counts.data_ptr(),
+                                             chunks.data_ptr(), cap, split.data_ptr(), owner.data_ptr(), counts.data_ptr(),
                                              None, 0, _stream()))
             n_chunks, n_slots, n_split, max_len = (int(v) for v in counts.cpu().tolist())
         chunks = chunks[:n_chunks]
@@ -107,7 +110,9 @@ class GraphCSR:
             lens = chunks[:, 2] - chunks[:, 1]
             chunks = chunks[torch.argsort(lens, descending=True, stable=True)].contiguous()
         p = SpmmPlan(row_begin, row_end, chunk_nnz, chunks, n_chunks, split[:max(n_split, 0)],
-                     n_split, n_slots, max_len)
+                     n_split, n_slots, max_len,
+                     slot_owner=owner[:max(n_slots, 1)].clone() if n_split else None,
+                     counters=torch.zeros(max(n_split, 1), dtype=torch.int32, device=self.device) if n_split else None)
         self._plans[key] = p
         return p
 

@@ -22,6 +22,8 @@ DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
 # shipped default is stand-alone; classes <= this threshold use the fused epilogue (0 = never).
 import os as _os
 FUSED_PROJ_MAX_CLASSES = int(_os.environ.get("TGCN_FUSED_PROJ_MAX_CLASSES", "0"))
+# split rows: 1 = the last-arriving chunk reduces the partial rows inside the SpMM kernel, 0 = separate fix-up kernel
+FOLD_FIXUP = int(_os.environ.get("TGCN_FOLD_FIXUP", "1"))
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -78,6 +80,8 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
     a.split_rows, a.n_split_rows = (plan.split_rows.data_ptr() if plan.n_split_rows else None), plan.n_split_rows
     scratch = plan.scratch(F)
     a.scratch = _native.ptr(scratch)
+    if plan.n_split_rows and FOLD_FIXUP:
+        a.slot_owner, a.split_counters = _native.ptr(plan.slot_owner), _native.ptr(plan.counters)
     a.B, a.ldb, a.b_dtype = B.data_ptr(), B.stride(0), _dt(B)
     if want_out:
         if out is None:
