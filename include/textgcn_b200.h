@@ -198,6 +198,11 @@ int tgcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    int64_t n, float lr, float beta1, float beta2, float eps, int32_t amsgrad,
                    int64_t step, const int64_t* step_dev, void* param_mirror_mc, void* stream);
 int tgcn_increment_step(int64_t* step_dev, void* stream);
+/* the same update for up to 4 SMALL tensors in one launch (b1, W2, b2); the arrays are HOST arrays of device pointers */
+int tgcn_adam_step_small(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                         float* const* exp_avg_sq, float* const* max_exp_avg_sq, const int64_t* sizes, float lr,
+                         float beta1, float beta2, float eps, int32_t amsgrad, int64_t step, const int64_t* step_dev,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (6) Exchange step of the 1D row partition over NVLink peer memory.  Replaces the

@@ -85,6 +85,8 @@ SIGNATURES = {
     "tgcn_adam_step": (C.c_int, [c_void, c_void, c_void, c_void, c_void, C.c_int64, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_int32, C.c_int64, c_void, c_void, c_void]),
     "tgcn_increment_step": (C.c_int, [c_void, c_void]),
+    "tgcn_adam_step_small": (C.c_int, [C.c_int32, c_void, c_void, c_void, c_void, c_void, c_void, C.c_float, C.c_float,
+                                       C.c_float, C.c_float, C.c_int32, C.c_int64, c_void, c_void]),
     "tgcn_peer_push": (C.c_int, [c_void, c_void, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_void, c_void]),
     "tgcn_sum_slots": (C.c_int, [c_void, C.c_int32, C.c_int64, C.c_int64, c_void, c_void]),
     "tgcn_count_mask": (C.c_int, [c_void, C.c_int64, c_void, c_void]),

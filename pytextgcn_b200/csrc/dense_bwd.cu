@@ -300,13 +300,23 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
   }
 }
 
-// out[i] = sum over CTAs (in CTA order) of part[cta][i]
-__global__ void k_reduce_partials(const float* __restrict__ part, int n_parts, int64_t n, float* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// Reduces the three per-CTA partial arrays in ONE launch: a warp per output element, lanes stride over the
+// CTA partials and a fixed shuffle tree adds the 32 lane sums -- same order every run (deterministic).
+__global__ void __launch_bounds__(256) k_reduce_partials3(const float* __restrict__ p0, int64_t n0, float* __restrict__ o0,
+                                                          const float* __restrict__ p1, int64_t n1, float* __restrict__ o1,
+                                                          const float* __restrict__ p2, int64_t n2, float* __restrict__ o2,
+                                                          int n_parts) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n0 + n1 + n2) return;
+  const float* part; float* out; int64_t n, i;
+  if (w < n0) { part = p0; out = o0; n = n0; i = w; }
+  else if (w < n0 + n1) { part = p1; out = o1; n = n1; i = w - n0; }
+  else { part = p2; out = o2; n = n2; i = w - n0 - n1; }
   float s = 0.0f;
-  for (int c = 0; c < n_parts; ++c) s += part[(int64_t)c * n + i];
-  out[i] = s;
+  for (int c = lane; c < n_parts; c += 32) s += part[(int64_t)c * n + i];
+  s = warp_sum(s);
+  if (lane == 0) out[i] = s;
 }
 
 // thin projection P = X W: a warp takes 4 rows per step (row values staged transposed [k][4] in shared
@@ -386,7 +396,7 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
                  "dense_bwd: TGCN_DROP_MASK needs keep_mask");
   const int H = a->H, C = a->C;
   const int n_tiles = (int)cdiv(a->n_rows, DB_ROWS);
-  const int gx = (int)std::min<int64_t>(db_grid_x(), n_tiles);
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(db_grid_x(), cdiv(n_tiles, 3)));   // >= 3 tiles per CTA
   DbLayout L = db_layout(H, C, db_grid_x());
   if (!workspace || workspace_bytes < L.total) {
     set_error("dense_bwd workspace too small: need %zu bytes, got %zu", L.total, workspace_bytes);
@@ -435,18 +445,12 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
   else TGCN_DB_LAUNCH(4);
 #undef TGCN_DB_LAUNCH
   TGCN_LAUNCH_CHECK();
+  TGCN_CHECK_ARG(a->db_out == nullptr || a->dZ2 != nullptr, "dense_bwd: db_out needs dZ2");
+  const int64_t n0 = (int64_t)H * C, n1 = a->db_hidden ? H : 0, n2 = a->db_out ? C : 0;
   const int T = 256;
-  k_reduce_partials<<<(unsigned)cdiv((int64_t)H * C, T), T, 0, stream>>>(p.part_dW2, gx, (int64_t)H * C, a->dW2);
+  k_reduce_partials3<<<(unsigned)cdiv((n0 + n1 + n2) * 32, T), T, 0, stream>>>(p.part_dW2, n0, a->dW2, p.part_dbh, n1, a->db_hidden,
+                                                                              p.part_dbo, n2, a->db_out, gx);
   TGCN_LAUNCH_CHECK();
-  if (a->db_hidden) {
-    k_reduce_partials<<<(unsigned)cdiv(H, T), T, 0, stream>>>(p.part_dbh, gx, H, a->db_hidden);
-    TGCN_LAUNCH_CHECK();
-  }
-  if (a->db_out) {
-    TGCN_CHECK_ARG(a->dZ2 != nullptr, "dense_bwd: db_out needs dZ2");
-    k_reduce_partials<<<(unsigned)cdiv(C, T), T, 0, stream>>>(p.part_dbo, gx, C, a->db_out);
-    TGCN_LAUNCH_CHECK();
-  }
   return TGCN_OK;
 }
 

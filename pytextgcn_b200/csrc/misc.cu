@@ -87,6 +87,31 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
   if (mirror) __threadfence_system();
 }
 
+// up to 4 small tensors in one launch (b1, W2, b2): blockIdx.y selects the tensor
+struct AdamSmall { float* p[4]; const float* g[4]; float* m[4]; float* v[4]; float* x[4]; int64_t n[4]; };
+__global__ void __launch_bounds__(256) k_adam_small(AdamSmall t, float lr, float b1, float b2, float eps, int amsgrad,
+                                                    int64_t step_host, const int64_t* __restrict__ step_dev) {
+  __shared__ float s_hyp[2];
+  if (threadIdx.x == 0) {
+    const double st = (double)(step_dev ? *step_dev : step_host);
+    s_hyp[0] = (float)((double)lr / (1.0 - pow((double)b1, st)));
+    s_hyp[1] = (float)sqrt(1.0 - pow((double)b2, st));
+  }
+  __syncthreads();
+  const int k = blockIdx.y;
+  float* p = t.p[k]; const float* g = t.g[k]; float* m = t.m[k]; float* v = t.v[k]; float* x = t.x[k];
+  const float step_size = s_hyp[0], bc2s = s_hyp[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n[k]; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = m[i] * b1 + (1.0f - b1) * gi;
+    const float vi = v[i] * b2 + (1.0f - b2) * (gi * gi);
+    float vh = vi;
+    if (amsgrad) { vh = fmaxf(x[i], vi); x[i] = vh; }
+    m[i] = mi; v[i] = vi;
+    p[i] = p[i] - step_size * (mi / (sqrtf(vh) / bc2s + eps));
+  }
+}
+
 __global__ void k_increment(int64_t* c) { *c += 1; }
 
 __global__ void k_cast_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
@@ -204,6 +229,30 @@ extern "C" int tgcn_adam_step(float* param, const float* grad, float* exp_avg, f
   const int64_t blocks = std::min<int64_t>(cdiv(cdiv(n, 4), T), (int64_t)sm_count() * 8);
   k_adam<<<(unsigned)std::max<int64_t>(blocks, 1), T, 0, (cudaStream_t)stream_>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr,
                                                                                  beta1, beta2, eps, amsgrad, step, step_dev, (float*)param_mirror_mc);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_adam_step_small(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                                    float* const* exp_avg_sq, float* const* max_exp_avg_sq, const int64_t* sizes, float lr,
+                                    float beta1, float beta2, float eps, int32_t amsgrad, int64_t step, const int64_t* step_dev,
+                                    void* stream_) {
+  TGCN_CHECK_ARG(n_tensors >= 1 && n_tensors <= 4, "adam_step_small: 1..4 tensors");
+  TGCN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && sizes, "adam_step_small: null pointer");
+  TGCN_CHECK_ARG(!amsgrad || max_exp_avg_sq, "adam_step_small: amsgrad needs max_exp_avg_sq");
+  TGCN_CHECK_ARG(step_dev != nullptr || step >= 1, "adam_step_small: step must be >= 1");
+  AdamSmall t;
+  int64_t nmax = 0;
+  for (int i = 0; i < 4; ++i) {
+    const bool on = i < n_tensors;
+    t.p[i] = on ? params[i] : nullptr; t.g[i] = on ? grads[i] : nullptr; t.m[i] = on ? exp_avg[i] : nullptr;
+    t.v[i] = on ? exp_avg_sq[i] : nullptr; t.x[i] = (on && amsgrad) ? max_exp_avg_sq[i] : nullptr; t.n[i] = on ? sizes[i] : 0;
+    if (on) { TGCN_CHECK_ARG(t.p[i] && t.g[i] && t.m[i] && t.v[i] && (!amsgrad || t.x[i]), "adam_step_small: null tensor"); }
+    nmax = std::max(nmax, t.n[i]);
+  }
+  if (nmax == 0) return TGCN_OK;
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(nmax, 256), 64), n_tensors);
+  k_adam_small<<<grid, 256, 0, (cudaStream_t)stream_>>>(t, lr, beta1, beta2, eps, amsgrad, step, step_dev);
   TGCN_LAUNCH_CHECK();
   return TGCN_OK;
 }

@@ -413,9 +413,8 @@ class DistTextGCNTrainer:
         mir = self._mirror("W1", self.W1_loc, self.W1_full)
         ops.adam_step(self.W1_loc, self.g_W1, *self.st[0], param_mirror=mir, **kw)    # updated rows go to every rank
         self._w1_mirrored = mir is not None
-        ops.adam_step(self.b1, self.g_b1.contiguous(), *self.st[1], **kw)
-        ops.adam_step(self.W2, self.g_W2, *self.st[2], **kw)
-        ops.adam_step(self.b2, self.g_b2.contiguous(), *self.st[3], **kw)
+        ops.adam_step_small([self.b1, self.W2, self.b2], [self.g_b1, self.g_W2, self.g_b2], [s_[0] for s_ in self.st[1:]],
+                            [s_[1] for s_ in self.st[1:]], [s_[2] for s_ in self.st[1:]], **kw)
         self._mark("adam")
         self.w1_stale = True
 

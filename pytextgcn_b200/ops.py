@@ -271,6 +271,23 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, ex
                                          1 if amsgrad else 0, int(step), _native.ptr(step_dev), param_mirror, _stream()))
 
 
+def adam_step_small(params, grads, exp_avg, exp_avg_sq, max_exp_avg_sq, *, lr: float, beta1: float = 0.9, beta2: float = 0.999,
+                    eps: float = 1e-8, amsgrad: bool = False, step: int = 0, step_dev: Optional[torch.Tensor] = None) -> None:
+    """One launch for up to 4 small parameter tensors (biases, W2): same arithmetic as adam_step."""
+    lib = _native.load()
+    k = len(params)
+    _need_cuda(*params, *grads, *exp_avg, *exp_avg_sq, step_dev)
+    for t in list(params) + list(grads) + list(exp_avg) + list(exp_avg_sq) + ([x for x in max_exp_avg_sq] if amsgrad else []):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("adam_step_small: tensors must be contiguous fp32")
+    arr = lambda ts: (C.c_void_p * k)(*[t.data_ptr() for t in ts])
+    sizes = (C.c_int64 * k)(*[p.numel() for p in params])
+    with torch.cuda.device(params[0].device):
+        _native.check(lib.tgcn_adam_step_small(k, arr(params), arr(grads), arr(exp_avg), arr(exp_avg_sq),
+                                               arr(max_exp_avg_sq) if amsgrad else None, sizes, lr, beta1, beta2, eps,
+                                               1 if amsgrad else 0, int(step), _native.ptr(step_dev), _stream()))
+
+
 def increment_step(step_dev: torch.Tensor) -> None:
     lib = _native.load()
     with torch.cuda.device(step_dev.device):

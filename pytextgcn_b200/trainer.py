@@ -191,11 +191,10 @@ class TextGCNTrainer:
             k += 3
         ops.increment_step(self.step_dev)
         k += 1
-        for i, p_ in enumerate(self.params):
-            ops.adam_step(p_.data, self.grads[i], self.exp_avg[i], self.exp_avg_sq[i], self.max_exp_avg_sq[i],
-                          lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad,
-                          step_dev=self.step_dev)
-            k += 1
+        kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad, step_dev=self.step_dev)
+        ops.adam_step(self.params[0].data, self.grads[0], self.exp_avg[0], self.exp_avg_sq[0], self.max_exp_avg_sq[0], **kw)
+        ops.adam_step_small([p_.data for p_ in self.params[1:]], self.grads[1:], self.exp_avg[1:], self.exp_avg_sq[1:],
+                            self.max_exp_avg_sq[1:], **kw)
         return k
 
     def _eval_body(self) -> int:

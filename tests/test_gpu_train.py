@@ -217,3 +217,25 @@ def test_trainer_many_classes_narrow_hidden_with_hierarchy(cuda):
         for gbuf, pr in zip(tr.grads, ref.parameters()):
             assert rel_err(gbuf, pr.grad) < 2e-5 * (step + 1)
         assert abs(out["loss"] - out_ref[0]) < 1e-5 * max(1, abs(out_ref[0])) * (step + 1)
+
+
+@pytest.mark.parametrize("amsgrad", [False, True])
+def test_adam_small_multi_tensor_matches_torch(cuda, amsgrad):
+    from pytextgcn_b200 import ops
+    torch.manual_seed(1)
+    shapes = [(200,), (200, 20), (20,)]
+    refs = [torch.randn(*s).requires_grad_() for s in shapes]
+    opt = torch.optim.Adam(refs, lr=0.05, amsgrad=amsgrad)
+    ps = [r.detach().clone().to(cuda) for r in refs]
+    ms, vs = [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
+    xs = [torch.zeros_like(p) for p in ps]
+    step_dev = torch.zeros(1, dtype=torch.int64, device=cuda)
+    for step in range(4):
+        gs = [torch.randn(*s) for s in shapes]
+        for r, g in zip(refs, gs):
+            r.grad = g.clone()
+        opt.step()
+        ops.increment_step(step_dev)
+        ops.adam_step_small(ps, [g.to(cuda) for g in gs], ms, vs, xs, lr=0.05, amsgrad=amsgrad, step_dev=step_dev)
+        for p, r in zip(ps, refs):
+            assert rel_err(p, r) < 2e-6
