@@ -101,3 +101,21 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_module_checkpoint_compatibility(tmp_path):
+    """Whole-module th.save / th.load (flat_amazon.py:126-128, eval_perlabel.py:13-19) and the reference's
+    state_dict layout: layers.{i}.weight (in,out), layers.{i}.bias (out)."""
+    from pytextgcn_b200 import GCN
+    m = GCN(40, 5, n_hidden_gcn=16, dropout=0.7)
+    sd = m.state_dict()
+    assert list(sd) == ["layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias"]
+    assert tuple(sd["layers.0.weight"].shape) == (40, 16) and tuple(sd["layers.1.weight"].shape) == (16, 5)
+    p = tmp_path / "gcn.nn"
+    torch.save(m, str(p))
+    m2 = torch.load(str(p), weights_only=False)
+    assert isinstance(m2, GCN) and m2.dropout == 0.7
+    for a, b in zip(m.parameters(), m2.parameters()):
+        assert torch.equal(a, b)
+    m3 = GCN(40, 5, n_hidden_gcn=16)
+    m3.load_state_dict(sd)
