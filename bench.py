@@ -270,7 +270,8 @@ def run_own_arm(args):
 
     torch.manual_seed(args.seed)
     gcn = GCN(n, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=shape.dropout).to(dev).float()
-    tr = TextGCNTrainer(gcn, gd, lr=shape.lr, amsgrad=shape.amsgrad, seed=args.seed, graph=graph)
+    tr = TextGCNTrainer(gcn, gd, lr=shape.lr, amsgrad=shape.amsgrad, seed=args.seed, graph=graph,
+                        fuse_adam=not args.no_fuse_adam, keep_w1_grad=False)
 
     def epoch_device():
         tr.train_step()
@@ -427,6 +428,7 @@ def main():
     ap.add_argument("--no-cuda-graph", dest="no_cuda_graph", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-fused-stores", dest="no_fused_stores", action="store_true")
+    ap.add_argument("--no-fuse-adam", dest="no_fuse_adam", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -125,6 +125,12 @@ typedef struct {
   const int64_t* philox_offset_dev;   /* optional device counter added to philox_offset (CUDA-graph replays) */
   int64_t philox_row_offset;          /* added to the CSR row id in the Philox element index (row shards: global id of local row 0) */
   const float* W_proj; int32_t n_proj; float* P; int64_t ldp;       /* optional projection */
+  /* optional fused Adam/AMSGrad (backward of layer 1 with X = I: output row r IS dW1[r], so the update of
+   * W1[r] runs on the row while it is in registers; replaces optimizer.step() for W1, flat_amazon.py:106).
+   * adam_hyper_dev = float[2] written by tgcn_adam_prepare; C may be NULL (gradient not materialised);
+   * adam_param_mirror_mc: multicast mapping of the parameter (row-partitioned mode) or NULL. */
+  float* adam_param; float* adam_exp_avg; float* adam_exp_avg_sq; float* adam_max_exp_avg_sq; int64_t adam_ld;
+  const float* adam_hyper_dev; float adam_beta1; float adam_beta2; float adam_eps; void* adam_param_mirror_mc;
 } tgcn_spmm_args;
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
 
@@ -198,6 +204,8 @@ int tgcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    int64_t n, float lr, float beta1, float beta2, float eps, int32_t amsgrad,
                    int64_t step, const int64_t* step_dev, void* param_mirror_mc, void* stream);
 int tgcn_increment_step(int64_t* step_dev, void* stream);
+/* step_dev += 1 and hyper_dev[0..1] = {lr/(1-b1^t), sqrt(1-b2^t)} for kernels that fuse the update */
+int tgcn_adam_prepare(int64_t* step_dev, float* hyper_dev, float lr, float beta1, float beta2, void* stream);
 /* the same update for up to 4 SMALL tensors in one launch (b1, W2, b2); the arrays are HOST arrays of device pointers */
 int tgcn_adam_step_small(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                          float* const* exp_avg_sq, float* const* max_exp_avg_sq, const int64_t* sizes, float lr,

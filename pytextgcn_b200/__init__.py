@@ -9,10 +9,10 @@ Public surface (mirrors the reference, BeFranke/PyTextGCN):
 The compute lives in pytextgcn_b200/lib/libtextgcn_b200.so (C ABI: include/textgcn_b200.h).
 """
 from .data import Data
-from .graph import GraphCSR, upload_graph, get_graph, clear_cache
+from .graph import GraphCSR, upload_graph, upload_graph_cached, get_graph, clear_cache, save_csr, load_csr
 from .models import GCN, GCNConv
 from .synthetic import make_graph, SHAPES, GraphShape
 from . import ops
 
-__all__ = ["Data", "GraphCSR", "upload_graph", "get_graph", "clear_cache", "GCN", "GCNConv",
+__all__ = ["Data", "GraphCSR", "upload_graph", "upload_graph_cached", "save_csr", "load_csr", "get_graph", "clear_cache", "GCN", "GCNConv",
            "make_graph", "SHAPES", "GraphShape", "ops"]

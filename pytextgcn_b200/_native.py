@@ -34,6 +34,9 @@ class SpmmArgs(C.Structure):
         ("drop_mode", C.c_int32), ("drop_p", C.c_float), ("keep_mask", c_void), ("ldmask", C.c_int64),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_offset_dev", c_void), ("philox_row_offset", C.c_int64),
         ("W_proj", c_void), ("n_proj", C.c_int32), ("P", c_void), ("ldp", C.c_int64),
+        ("adam_param", c_void), ("adam_exp_avg", c_void), ("adam_exp_avg_sq", c_void), ("adam_max_exp_avg_sq", c_void),
+        ("adam_ld", C.c_int64), ("adam_hyper_dev", c_void), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float),
+        ("adam_eps", C.c_float), ("adam_param_mirror_mc", c_void),
     ]
 
 
@@ -85,6 +88,7 @@ SIGNATURES = {
     "tgcn_adam_step": (C.c_int, [c_void, c_void, c_void, c_void, c_void, C.c_int64, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_int32, C.c_int64, c_void, c_void, c_void]),
     "tgcn_increment_step": (C.c_int, [c_void, c_void]),
+    "tgcn_adam_prepare": (C.c_int, [c_void, c_void, C.c_float, C.c_float, C.c_float, c_void]),
     "tgcn_adam_step_small": (C.c_int, [C.c_int32, c_void, c_void, c_void, c_void, c_void, c_void, C.c_float, C.c_float,
                                        C.c_float, C.c_float, C.c_int32, C.c_int64, c_void, c_void]),
     "tgcn_peer_push": (C.c_int, [c_void, c_void, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_void, c_void]),

@@ -114,6 +114,14 @@ __global__ void __launch_bounds__(256) k_adam_small(AdamSmall t, float lr, float
 
 __global__ void k_increment(int64_t* c) { *c += 1; }
 
+// step += 1 and the two step-dependent Adam scalars for kernels that fuse the update (SpMM epilogue)
+__global__ void k_adam_prepare(int64_t* step, float* hyp, float lr, float b1, float b2) {
+  const int64_t t = *step + 1;
+  *step = t;
+  hyp[0] = (float)((double)lr / (1.0 - pow((double)b1, (double)t)));
+  hyp[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
+}
+
 __global__ void k_cast_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
@@ -253,6 +261,13 @@ extern "C" int tgcn_adam_step_small(int32_t n_tensors, float* const* params, con
   if (nmax == 0) return TGCN_OK;
   dim3 grid((unsigned)std::min<int64_t>(cdiv(nmax, 256), 64), n_tensors);
   k_adam_small<<<grid, 256, 0, (cudaStream_t)stream_>>>(t, lr, beta1, beta2, eps, amsgrad, step, step_dev);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_adam_prepare(int64_t* step_dev, float* hyper_dev, float lr, float beta1, float beta2, void* stream_) {
+  TGCN_CHECK_ARG(step_dev && hyper_dev, "adam_prepare: null pointer");
+  k_adam_prepare<<<1, 1, 0, (cudaStream_t)stream_>>>(step_dev, hyper_dev, lr, beta1, beta2);
   TGCN_LAUNCH_CHECK();
   return TGCN_OK;
 }

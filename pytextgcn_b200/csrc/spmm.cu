@@ -12,6 +12,7 @@
 // entries per warp load, and broadcast by shuffle.  Split rows write fp32 partial rows to a
 // scratch buffer and a fix-up kernel adds them in slot order: deterministic, no atomics.
 #include "common.cuh"
+#include <type_traits>
 
 namespace tgcn {
 
@@ -31,6 +32,9 @@ struct SpmmParams {
   uint64_t philox_seed; uint64_t philox_offset; const int64_t* __restrict__ philox_offset_dev; int64_t philox_row_offset;
   const float* __restrict__ W_proj; int32_t n_proj; float* P; int64_t ldp;
   int32_t wproj_in_smem;
+  // fused Adam/AMSGrad on the finished row (backward of layer 1 with X = I: the row IS dW1[row])
+  float* ad_p; float* ad_m; float* ad_v; float* ad_x; int64_t ad_ld; const float* __restrict__ ad_hyp;
+  float ad_b1, ad_b2, ad_eps; float* ad_mirror;
 };
 
 // ---- loads of 16 bytes of the dense operand -> 4 (fp32) or 8 (bf16) floats ----
@@ -58,7 +62,9 @@ template <> struct Vec<__nv_bfloat16> {
 // Epilogue on one finished row held as: lane l (< LPR) owns elements
 // [ (l + v*LPR)*E , +E ) for v < VPL.  All 32 lanes call this (lanes >= LPR idle in the
 // element part but take part in the projection).
-template <int LPR, int VPL, int E, bool PROJ>
+constexpr int EPI_PLAIN = 0, EPI_PROJ = 1, EPI_ADAM = 2;
+
+template <int LPR, int VPL, int E, int EPI>
 __device__ __forceinline__ void row_epilogue(const SpmmParams& p, int64_t row, int lane, float (&acc)[VPL][E],
                                              const float* smem_w) {
   const int F = p.F;
@@ -108,12 +114,40 @@ __device__ __forceinline__ void row_epilogue(const SpmmParams& p, int64_t row, i
           for (int i = 0; i < E; ++i) z[i] = __bfloat162float(__float2bfloat16_rn(z[i]));
         }
       }
+      if constexpr (EPI == EPI_ADAM) {
+        // z = dW1[row, c0 .. c0+E): Adam/AMSGrad right here, while the gradient row is in registers
+        // (torch.optim.Adam arithmetic, same as k_adam); the gradient itself is stored only if C != NULL.
+        const float step_size = __ldg(p.ad_hyp), bc2s = __ldg(p.ad_hyp + 1);
+        const int64_t off = lrow * p.ad_ld + c0;
+#pragma unroll
+        for (int q = 0; q < E / 4; ++q) {
+          float4 P4 = *reinterpret_cast<const float4*>(p.ad_p + off + 4 * q);
+          float4 M4 = *reinterpret_cast<const float4*>(p.ad_m + off + 4 * q);
+          float4 V4 = *reinterpret_cast<const float4*>(p.ad_v + off + 4 * q);
+          float4 X4 = p.ad_x ? *reinterpret_cast<const float4*>(p.ad_x + off + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float* pp = &P4.x; float* mm = &M4.x; float* vv = &V4.x; float* xx = &X4.x;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float g = z[4 * q + k];
+            mm[k] = mm[k] * p.ad_b1 + (1.0f - p.ad_b1) * g;
+            vv[k] = vv[k] * p.ad_b2 + (1.0f - p.ad_b2) * (g * g);
+            float vh = vv[k];
+            if (p.ad_x) { xx[k] = fmaxf(xx[k], vv[k]); vh = xx[k]; }
+            pp[k] = pp[k] - step_size * (mm[k] / (sqrtf(vh) / bc2s + p.ad_eps));
+          }
+          *reinterpret_cast<float4*>(p.ad_p + off + 4 * q) = P4;
+          *reinterpret_cast<float4*>(p.ad_m + off + 4 * q) = M4;
+          *reinterpret_cast<float4*>(p.ad_v + off + 4 * q) = V4;
+          if (p.ad_x) *reinterpret_cast<float4*>(p.ad_x + off + 4 * q) = X4;
+          if (p.ad_mirror) multimem_st_v4(p.ad_mirror + off + 4 * q, P4.x, P4.y, P4.z, P4.w);
+        }
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < E; ++i) z[i] = 0.0f;     // lanes outside the row contribute nothing to the projection
     }
   }
-  if constexpr (PROJ) {
+  if constexpr (EPI == EPI_PROJ) {
     // P[row, m] = sum_c z[c] * W[c, m].  Every lane multiplies ITS columns (still in registers) into
     // 16 outputs at a time; a transposing butterfly (16 shuffles) then leaves output m0 + lane/2 in
     // every lane pair.
@@ -167,7 +201,7 @@ __device__ __forceinline__ void row_epilogue(const SpmmParams& p, int64_t row, i
   }
 }
 
-template <typename TB, int LPR, int VPL, bool PROJ>
+template <typename TB, int LPR, int VPL, int EPI>
 __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(const SpmmParams p) {
   constexpr int E = Vec<TB>::E;
   constexpr int NZP = 32 / LPR;          // non-zeros processed side by side in a warp
@@ -179,7 +213,7 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   float* smem_w = smem;                                   // [F][pad4(n_proj)] (+32 floats slack) when staged
-  if (PROJ && p.wproj_in_smem) {
+  if (EPI == EPI_PROJ && p.wproj_in_smem) {
     const int Ms = (p.n_proj + 3) & ~3;
     for (int i = threadIdx.x; i < p.F * Ms + 32; i += blockDim.x) {
       const int c = i / Ms, m = i - c * Ms;
@@ -299,19 +333,19 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
       }
     }
   }
-  row_epilogue<LPR, VPL, E, PROJ>(p, ch.x, lane, acc, smem_w);
+  row_epilogue<LPR, VPL, E, EPI>(p, ch.x, lane, acc, smem_w);
   }
 }
 
 // one warp per split row: add its partial rows in slot order, then the same epilogue
-template <int LPR, int VPL, int E, bool PROJ>
+template <int LPR, int VPL, int E, int EPI>
 __global__ void __launch_bounds__(256) k_spmm_fixup(const SpmmParams p) {
   extern __shared__ __align__(16) float smem[];
   const int warps_per_block = blockDim.x >> 5;
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   float* smem_w = smem;                                   // [F][pad4(n_proj)] (+32 floats slack) when staged
-  if (PROJ && p.wproj_in_smem) {
+  if (EPI == EPI_PROJ && p.wproj_in_smem) {
     const int Ms = (p.n_proj + 3) & ~3;
     for (int i = threadIdx.x; i < p.F * Ms + 32; i += blockDim.x) {
       const int c = i / Ms, m = i - c * Ms;
@@ -344,7 +378,7 @@ __global__ void __launch_bounds__(256) k_spmm_fixup(const SpmmParams p) {
       }
     }
   }
-  row_epilogue<LPR, VPL, E, PROJ>(p, row, lane, acc, smem_w);
+  row_epilogue<LPR, VPL, E, EPI>(p, row, lane, acc, smem_w);
 }
 
 // ---- spmm plan: chunk list ------------------------------------------------------------
@@ -416,23 +450,23 @@ __global__ void __launch_bounds__(1024) k_plan(const int32_t* __restrict__ rowpt
   if (tid == 0) { counts[0] = s_base[0]; counts[1] = s_base[1]; counts[2] = s_base[2]; counts[3] = s_maxlen; }
 }
 
-template <typename TB, int LPR, int VPL, bool PROJ>
+template <typename TB, int LPR, int VPL, int EPI>
 static int launch_spmm_t(const SpmmParams& p, cudaStream_t stream) {
   constexpr int E = Vec<TB>::E;
   const int threads = 256, wpb = threads / 32;
   size_t smem = 0;
-  if (PROJ && p.wproj_in_smem) smem = ((size_t)p.F * ((p.n_proj + 3) & ~3) + 32) * sizeof(float);
+  if (EPI == EPI_PROJ && p.wproj_in_smem) smem = ((size_t)p.F * ((p.n_proj + 3) & ~3) + 32) * sizeof(float);
   if (smem > 48 * 1024) {
-    TGCN_CUDA(cudaFuncSetAttribute(k_spmm<TB, LPR, VPL, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TGCN_CUDA(cudaFuncSetAttribute(k_spmm_fixup<LPR, VPL, E, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TGCN_CUDA(cudaFuncSetAttribute(k_spmm<TB, LPR, VPL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TGCN_CUDA(cudaFuncSetAttribute(k_spmm_fixup<LPR, VPL, E, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (p.n_chunks > 0) {
     const int64_t grid = cdiv(p.n_chunks, wpb);
-    k_spmm<TB, LPR, VPL, PROJ><<<(unsigned)grid, threads, smem, stream>>>(p);
+    k_spmm<TB, LPR, VPL, EPI><<<(unsigned)grid, threads, smem, stream>>>(p);
     TGCN_LAUNCH_CHECK();
   }
   if (p.n_split_rows > 0 && p.split_counters == nullptr) {
-    k_spmm_fixup<LPR, VPL, E, PROJ><<<(unsigned)cdiv(p.n_split_rows, wpb), threads, smem, stream>>>(p);
+    k_spmm_fixup<LPR, VPL, E, EPI><<<(unsigned)cdiv(p.n_split_rows, wpb), threads, smem, stream>>>(p);
     TGCN_LAUNCH_CHECK();
   }
   return TGCN_OK;
@@ -440,8 +474,13 @@ static int launch_spmm_t(const SpmmParams& p, cudaStream_t stream) {
 
 template <typename TB, int LPR, int VPL>
 static int launch_spmm(const SpmmParams& p, cudaStream_t stream) {
-  if (p.P) return launch_spmm_t<TB, LPR, VPL, true>(p, stream);
-  return launch_spmm_t<TB, LPR, VPL, false>(p, stream);
+  if (p.ad_p) {
+    if constexpr (std::is_same<TB, float>::value) return launch_spmm_t<TB, LPR, VPL, EPI_ADAM>(p, stream);
+    set_error("spmm: the fused Adam epilogue needs an fp32 operand");
+    return TGCN_EINVAL;
+  }
+  if (p.P) return launch_spmm_t<TB, LPR, VPL, EPI_PROJ>(p, stream);
+  return launch_spmm_t<TB, LPR, VPL, EPI_PLAIN>(p, stream);
 }
 
 template <typename TB>
@@ -488,7 +527,7 @@ extern "C" int tgcn_spmm(const tgcn_spmm_args* a, void* stream_) {
   TGCN_CHECK_ARG(a != nullptr, "spmm: args null");
   TGCN_CHECK_ARG(a->rowptr && a->colidx && a->val && a->chunks, "spmm: CSR/plan pointer null");
   TGCN_CHECK_ARG(a->B != nullptr, "spmm: B null");
-  TGCN_CHECK_ARG(a->C != nullptr || a->P != nullptr, "spmm: no output requested");
+  TGCN_CHECK_ARG(a->C != nullptr || a->P != nullptr || a->adam_param != nullptr, "spmm: no output requested");
   TGCN_CHECK_ARG(a->F > 0, "spmm: F must be > 0");
   TGCN_CHECK_ARG(a->b_dtype == TGCN_F32 || a->b_dtype == TGCN_BF16, "spmm: bad b_dtype");
   TGCN_CHECK_ARG(a->c_dtype == TGCN_F32 || a->c_dtype == TGCN_BF16, "spmm: bad c_dtype");
@@ -522,6 +561,16 @@ extern "C" int tgcn_spmm(const tgcn_spmm_args* a, void* stream_) {
   p.keep_mask = a->keep_mask; p.ldmask = a->ldmask;
   p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset; p.philox_offset_dev = a->philox_offset_dev; p.philox_row_offset = a->philox_row_offset;
   p.W_proj = a->W_proj; p.n_proj = a->n_proj; p.P = a->P; p.ldp = a->ldp;
+  p.ad_p = a->adam_param; p.ad_m = a->adam_exp_avg; p.ad_v = a->adam_exp_avg_sq; p.ad_x = a->adam_max_exp_avg_sq;
+  p.ad_ld = a->adam_ld; p.ad_hyp = a->adam_hyper_dev; p.ad_b1 = a->adam_beta1; p.ad_b2 = a->adam_beta2; p.ad_eps = a->adam_eps;
+  p.ad_mirror = (float*)a->adam_param_mirror_mc;
+  if (p.ad_p) {
+    TGCN_CHECK_ARG(p.ad_m && p.ad_v && p.ad_hyp, "spmm: fused Adam needs exp_avg, exp_avg_sq and the hyper buffer");
+    TGCN_CHECK_ARG(a->P == nullptr && a->b_dtype == TGCN_F32 && p.ad_ld % 4 == 0 && p.ad_ld >= a->F,
+                   "spmm: fused Adam needs fp32 operands, no projection and adam_ld %% 4 == 0");
+    TGCN_CHECK_ARG((((uintptr_t)p.ad_p | (uintptr_t)p.ad_m | (uintptr_t)p.ad_v | (uintptr_t)(p.ad_x ? p.ad_x : p.ad_p)) & 15) == 0,
+                   "spmm: fused Adam buffers must be 16-byte aligned");
+  }
   p.wproj_in_smem = (p.P && (size_t)p.F * ((p.n_proj + 3) & ~3) * sizeof(float) <= 64 * 1024) ? 1 : 0;
   if (a->b_dtype == TGCN_F32) return dispatch_spmm<float>(p, stream);
   return dispatch_spmm<__nv_bfloat16>(p, stream);

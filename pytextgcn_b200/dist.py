@@ -161,7 +161,8 @@ class DistTextGCNTrainer:
     def __init__(self, g, n_classes: int, hidden: int, dropout: float, lr: float, amsgrad: bool,
                  rank: int, world: int, dev: torch.device, seed: int = 0, betas=(0.9, 0.999), eps: float = 1e-8,
                  graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None,
-                 use_cuda_graph: bool = False, exchange: str = "peer", fused_stores: bool = True):
+                 use_cuda_graph: bool = False, exchange: str = "peer", fused_stores: bool = True,
+                 fuse_adam: bool = True, keep_w1_grad: bool = True):
         import torch.distributed as dist
         from . import ops
         from .graph import upload_graph
@@ -232,6 +233,8 @@ class DistTextGCNTrainer:
             return [torch.zeros_like(t), torch.zeros_like(t), torch.zeros_like(t) if amsgrad else None]
         self.st = [state(self.W1_loc), state(self.b1), state(self.W2), state(self.b2)]
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.adam_hyper = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.fuse_adam, self.keep_w1_grad = bool(fuse_adam), bool(keep_w1_grad)
         # activations
         self.H1d = torch.empty((nl, H), **f32)
         self.Pt_full = xbuf("Pt", (npad, Cp))        # projected rows, train forward
@@ -403,15 +406,27 @@ class DistTextGCNTrainer:
         if not (mir is not None and self.px is not None):
             self._exchange(self.dZ1_full, self.dZ1_loc, "dZ1", False)
         self._mark("allgather_dZ1")
-        ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1)
-        self._note_read("dZ1")
-        self._mark("spmm_wide_bwd")
-        ops.increment_step(self.step_dev)
         kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad,
                   step_dev=self.step_dev)
         self._before_write("W1")
         mir = self._mirror("W1", self.W1_loc, self.W1_full)
-        ops.adam_step(self.W1_loc, self.g_W1, *self.st[0], param_mirror=mir, **kw)    # updated rows go to every rank
+        if self.fuse_adam:
+            # dW1 rows of this shard never leave registers: Adam on W1[R_r] runs in the SpMM epilogue and the
+            # updated rows go straight to every rank's copy of W1 (multimem.st) -- compute, optimiser and
+            # exchange in one kernel
+            ops.adam_prepare(self.step_dev, self.adam_hyper, self.lr, self.betas[0], self.betas[1])
+            ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1 if self.keep_w1_grad else None,
+                     want_out=self.keep_w1_grad,
+                     adam=dict(param=self.W1_loc, exp_avg=self.st[0][0], exp_avg_sq=self.st[0][1], max_exp_avg_sq=self.st[0][2],
+                               hyper=self.adam_hyper, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, mirror=mir))
+            self._note_read("dZ1")
+            self._mark("spmm_wide_bwd")
+        else:
+            ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1)
+            self._note_read("dZ1")
+            self._mark("spmm_wide_bwd")
+            ops.increment_step(self.step_dev)
+            ops.adam_step(self.W1_loc, self.g_W1, *self.st[0], param_mirror=mir, **kw)    # updated rows go to every rank
         self._w1_mirrored = mir is not None
         ops.adam_step_small([self.b1, self.W2, self.b2], [self.g_b1, self.g_W2, self.g_b2], [s_[0] for s_ in self.st[1:]],
                             [s_[1] for s_ in self.st[1:]], [s_[2] for s_ in self.st[1:]], **kw)
@@ -545,7 +560,8 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
     n = int(g.x.shape[0])
     tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad,
                             rank, world, dev, seed=args.seed, use_cuda_graph=not getattr(args, "no_cuda_graph", False),
-                            exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False))
+                            exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False),
+                            fuse_adam=not getattr(args, "no_fuse_adam", False), keep_w1_grad=False)
     epoch = tr.epoch
 
     for _ in range(W):

@@ -223,6 +223,45 @@ def upload_graph(edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor], nu
     return GraphCSR(N, rowptr, colidx, val, dis, slot)
 
 
+# ---- CSR sidecar on disk: lets a later run skip the sort of the upload -------------
+def _fingerprint(edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor], n: int):
+    """Cheap content check tying a sidecar to the graph it was built from (exact integer / fp64 sums)."""
+    e = int(edge_index.shape[1])
+    s_idx = int((edge_index[0].to(torch.int64) * 31 + edge_index[1].to(torch.int64)).sum().item()) if e else 0
+    s_w = float(edge_attr.double().sum().item()) if (edge_attr is not None and e) else 0.0
+    return [n, e, s_idx, s_w]
+
+
+def save_csr(graph: GraphCSR, path: str, edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor]) -> None:
+    """Writes the device CSR next to a pickled `Data` (text2graph.py:195-202 writes TGData_<time>.p)."""
+    torch.save({"format": "textgcn_b200.csr.v1", "n_nodes": graph.n_nodes, "fingerprint": _fingerprint(edge_index, edge_attr, graph.n_nodes),
+                "rowptr": graph.rowptr.cpu(), "colidx": graph.colidx.cpu(), "val": graph.val.cpu(), "dis": graph.dis.cpu()}, path)
+
+
+def load_csr(path: str, edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor], num_nodes: int) -> Optional[GraphCSR]:
+    """Returns the CSR stored at `path` if it belongs to this graph (fingerprint match), else None."""
+    import os
+    if not os.path.exists(path):
+        return None
+    try:
+        d = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        return None
+    if d.get("format") != "textgcn_b200.csr.v1" or d.get("fingerprint") != _fingerprint(edge_index, edge_attr, num_nodes):
+        return None
+    dev = edge_index.device
+    return GraphCSR(int(d["n_nodes"]), d["rowptr"].to(dev), d["colidx"].to(dev), d["val"].to(dev), d["dis"].to(dev))
+
+
+def upload_graph_cached(edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor], num_nodes: int, sidecar: str) -> GraphCSR:
+    """upload_graph with a disk sidecar: load when it matches the graph, otherwise build and write it."""
+    g = load_csr(sidecar, edge_index, edge_attr, num_nodes)
+    if g is None:
+        g = upload_graph(edge_index, edge_attr, num_nodes)
+        save_csr(g, sidecar, edge_index, edge_attr)
+    return g
+
+
 # ---- cache: one CSR per live (edge_index, edge_attr) tensor pair ---------------------------
 # Entries hold WEAK references to the tensors they were built from, so a recycled device
 # address can never alias a stale CSR; in-place edits are caught through `_version`.

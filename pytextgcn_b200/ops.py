@@ -59,7 +59,7 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
          drop_mode: int = DROP_NONE, drop_p: float = 0.0, keep_mask: Optional[torch.Tensor] = None,
          philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0,
          W_proj: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
-         want_out: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+         want_out: bool = True, adam: Optional[dict] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """C = epi(A_hat[rows of plan] @ B[:, :F]) (+ P = C @ W_proj).  See tgcn_spmm.
 
     B: [>= n_nodes, >= F] fp32/bf16, row stride a multiple of 4 (fp32) / 8 (bf16) elements.
@@ -80,6 +80,17 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
     a.split_rows, a.n_split_rows = (plan.split_rows.data_ptr() if plan.n_split_rows else None), plan.n_split_rows
     scratch = plan.scratch(F)
     a.scratch = _native.ptr(scratch)
+    if adam is not None:
+        # fused Adam/AMSGrad on the output rows: dict(param, exp_avg, exp_avg_sq, max_exp_avg_sq|None, hyper, beta1, beta2, eps, mirror|None)
+        prm = adam["param"]
+        for t in (prm, adam["exp_avg"], adam["exp_avg_sq"], adam.get("max_exp_avg_sq")):
+            if t is not None and (t.dtype != torch.float32 or t.stride(1) != 1 or t.stride(0) != prm.stride(0)):
+                raise RuntimeError("spmm: fused Adam tensors must be row-major fp32 with the same row pitch")
+        a.adam_param, a.adam_exp_avg, a.adam_exp_avg_sq = prm.data_ptr(), adam["exp_avg"].data_ptr(), adam["exp_avg_sq"].data_ptr()
+        a.adam_max_exp_avg_sq = _native.ptr(adam.get("max_exp_avg_sq"))
+        a.adam_ld, a.adam_hyper_dev = prm.stride(0), adam["hyper"].data_ptr()
+        a.adam_beta1, a.adam_beta2, a.adam_eps = adam.get("beta1", 0.9), adam.get("beta2", 0.999), adam.get("eps", 1e-8)
+        a.adam_param_mirror_mc = adam.get("mirror")
     if plan.n_split_rows and FOLD_FIXUP:
         a.slot_owner, a.split_counters = _native.ptr(plan.slot_owner), _native.ptr(plan.counters)
     a.B, a.ldb, a.b_dtype = B.data_ptr(), B.stride(0), _dt(B)
@@ -286,6 +297,13 @@ def adam_step_small(params, grads, exp_avg, exp_avg_sq, max_exp_avg_sq, *, lr: f
         _native.check(lib.tgcn_adam_step_small(k, arr(params), arr(grads), arr(exp_avg), arr(exp_avg_sq),
                                                arr(max_exp_avg_sq) if amsgrad else None, sizes, lr, beta1, beta2, eps,
                                                1 if amsgrad else 0, int(step), _native.ptr(step_dev), _stream()))
+
+
+def adam_prepare(step_dev: torch.Tensor, hyper: torch.Tensor, lr: float, beta1: float = 0.9, beta2: float = 0.999) -> None:
+    """step_dev += 1; hyper[0:2] = (lr / (1 - beta1^t), sqrt(1 - beta2^t)) for the SpMM's fused Adam epilogue."""
+    lib = _native.load()
+    with torch.cuda.device(step_dev.device):
+        _native.check(lib.tgcn_adam_prepare(step_dev.data_ptr(), hyper.data_ptr(), lr, beta1, beta2, _stream()))
 
 
 def increment_step(step_dev: torch.Tensor) -> None:

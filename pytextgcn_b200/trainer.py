@@ -24,7 +24,8 @@ from .models import GCN, decode_features
 class TextGCNTrainer:
     def __init__(self, gcn: GCN, g, lr: float = 0.05, amsgrad: bool = True, betas=(0.9, 0.999), eps: float = 1e-8,
                  use_cuda_graph: bool = True, seed: int = 0, chunk_nnz: Optional[int] = None,
-                 graph: Optional[GraphCSR] = None, assume_symmetric: bool = False, eval_mode: str = "layered"):
+                 graph: Optional[GraphCSR] = None, assume_symmetric: bool = False, eval_mode: str = "layered",
+                 fuse_adam: bool = True, keep_w1_grad: bool = True):
         if len(gcn.layers) != 2:
             raise NotImplementedError("TextGCNTrainer fuses the 2-layer TextGCN (the configuration of every reference script)")
         l0, l1 = gcn.layers
@@ -65,6 +66,11 @@ class TextGCNTrainer:
         self.exp_avg_sq = [torch.zeros_like(p_.data) for p_ in self.params]
         self.max_exp_avg_sq = [torch.zeros_like(p_.data) for p_ in self.params] if amsgrad else [None] * 4
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.adam_hyper = torch.zeros(2, dtype=torch.float32, device=dev)   # lr/(1-b1^t), sqrt(1-b2^t) of the current step
+        # W1's Adam update can run in the epilogue of the SpMM that produces dW1 (rows of dW1 never leave registers
+        # unless keep_w1_grad asks for the gradient buffer too); not with hierarchy features (W1 has extra rows)
+        self.fuse_adam = bool(fuse_adam) and self.feat.Fdoc is None
+        self.keep_w1_grad = bool(keep_w1_grad)
         self.XW = torch.zeros((n, H), **f32) if self.feat.Fdoc is not None else None
         self.H1d = torch.empty((n, H), **f32)
         self.P = torch.zeros((n, Cp), **f32)
@@ -183,16 +189,21 @@ class TextGCNTrainer:
                           db_out=self.grads[3])
         self._db_ws = r["workspace"]
         k += 1 + 4
-        ops.spmm(self.graph_t, self.dZ1, F=self.H, plan=self.plan_t, out=self.grads[0])
-        k += 2 + 2 * (1 if self.plan_t.n_split_rows else 0)
-        if self.feat.Fdoc is not None:
-            ops.hier_backward(self.grads[0], self.n, self.feat.n_vocab, self.feat.Fdoc, self.H, self.hier_tail)
-            self.grads[0][self.n:].copy_(self.hier_tail)
-            k += 3
-        ops.increment_step(self.step_dev)
-        k += 1
         kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad, step_dev=self.step_dev)
-        ops.adam_step(self.params[0].data, self.grads[0], self.exp_avg[0], self.exp_avg_sq[0], self.max_exp_avg_sq[0], **kw)
+        if self.fuse_adam:
+            ops.adam_prepare(self.step_dev, self.adam_hyper, self.lr, self.betas[0], self.betas[1])     # step += 1
+            ops.spmm(self.graph_t, self.dZ1, F=self.H, plan=self.plan_t, out=self.grads[0] if self.keep_w1_grad else None,
+                     want_out=self.keep_w1_grad,
+                     adam=dict(param=self.params[0].data, exp_avg=self.exp_avg[0], exp_avg_sq=self.exp_avg_sq[0],
+                               max_exp_avg_sq=self.max_exp_avg_sq[0], hyper=self.adam_hyper, beta1=self.betas[0],
+                               beta2=self.betas[1], eps=self.eps))
+        else:
+            ops.spmm(self.graph_t, self.dZ1, F=self.H, plan=self.plan_t, out=self.grads[0])
+            if self.feat.Fdoc is not None:
+                ops.hier_backward(self.grads[0], self.n, self.feat.n_vocab, self.feat.Fdoc, self.H, self.hier_tail)
+                self.grads[0][self.n:].copy_(self.hier_tail)
+            ops.increment_step(self.step_dev)
+            ops.adam_step(self.params[0].data, self.grads[0], self.exp_avg[0], self.exp_avg_sq[0], self.max_exp_avg_sq[0], **kw)
         ops.adam_step_small([p_.data for p_ in self.params[1:]], self.grads[1:], self.exp_avg[1:], self.exp_avg_sq[1:],
                             self.max_exp_avg_sq[1:], **kw)
         return k

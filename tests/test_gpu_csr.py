@@ -102,3 +102,22 @@ def test_symmetry_detection(cuda):
     At = torch.zeros(200, 200, dtype=torch.float64)
     At.index_put_((t.row_ids().cpu(), t.colidx.cpu().long()), t.val.cpu().double(), accumulate=True)
     assert torch.equal(A.T.contiguous(), At)
+
+
+def test_csr_sidecar_roundtrip(cuda, tmp_path):
+    """a cached-CSR sidecar lets a later run skip the sort; it is only accepted for the graph it was
+    built from (fingerprint), otherwise the CSR is rebuilt."""
+    from pytextgcn_b200.graph import upload_graph, upload_graph_cached, load_csr
+    ei, w = random_graph(400, 8000, seed=3, transposed_view=True)
+    ei_d, w_d = ei.T.contiguous().to(cuda).T, w.to(cuda)
+    path = str(tmp_path / "TGData_123.csr")
+    a = upload_graph_cached(ei_d, w_d, 400, path)
+    b = upload_graph_cached(ei_d, w_d, 400, path)                     # second call: loaded from the sidecar
+    ref = upload_graph(ei_d, w_d, 400)
+    for x in (a, b):
+        assert torch.equal(x.rowptr, ref.rowptr) and torch.equal(x.colidx, ref.colidx)
+        assert torch.equal(x.val.view(torch.int32), ref.val.view(torch.int32)) and torch.equal(x.dis, ref.dis)
+    w2 = w_d.clone()
+    w2[5] += 1.0
+    assert load_csr(path, ei_d, w2, 400) is None                       # different weights -> sidecar refused
+    assert load_csr(str(tmp_path / "missing.csr"), ei_d, w_d, 400) is None
