@@ -35,7 +35,7 @@ PyG-1.6.3 semantics restated here (recalled from upstream `gcn_conv.py`, `utils/
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 

@@ -23,7 +23,7 @@ from __future__ import annotations
 import json
 import os
 import time
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional
 
 import torch
 
@@ -549,7 +549,6 @@ def shutdown(trainer: Optional["DistTextGCNTrainer"] = None) -> None:
 # bench entry for N > 1 (called by bench.py under torchrun)
 # --------------------------------------------------------------------------------------
 def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: torch.device):
-    import numpy as np
     import torch.distributed as dist
     from . import _native
     from .synthetic import SHAPES, make_graph

@@ -28,7 +28,6 @@ from typing import Dict, List, Optional, Union
 
 import numpy as np
 import torch as th
-from scipy import sparse as sp
 from sklearn.base import BaseEstimator, TransformerMixin
 from sklearn.feature_extraction.text import CountVectorizer, TfidfTransformer
 

@@ -149,17 +149,15 @@ class TextGCNTrainer:
         ops.spmm(self.graph, self.Q, F=self.Cp, plan=self.plan, out=self.T, bias=self.c_row[0, :self.C])
         ops.spmm(self.graph, self.T, F=self.Cp, plan=self.plan, out=self.Z2, bias=b2)
 
-    def _forward(self, training: bool) -> int:
+    def _forward(self, training: bool) -> None:
         l0, l1 = self.gcn.layers
         W1, b1, W2, b2 = l0.weight.data, l0.bias.data, l1.weight.data, l1.bias.data
-        k = 0
         if not training and self.eval_mode == "collapsed":
             self._forward_collapsed()
-            return 0
+            return
         if self.feat.Fdoc is not None:
             ops.hier_forward(W1, self.n, self.feat.n_vocab, self.feat.Fdoc, out=self.XW)
             B1 = self.XW
-            k += 1
         else:
             B1 = W1[:self.n]
         drop = training and self.p > 0.0
@@ -171,15 +169,13 @@ class TextGCNTrainer:
         if not fuse:
             ops.project(self.H1d, W2, K=self.H, out=self.P)
         ops.spmm(self.graph, self.P, F=self.Cp, plan=self.plan, out=self.Z2, bias=b2)
-        return k + 2 + 2 * (1 if self.plan.n_split_rows else 0)
 
-    def _train_body(self) -> int:
+    def _train_body(self) -> None:
         l0, l1 = self.gcn.layers
         W2 = l1.weight.data
-        k = self._forward(True)
+        self._forward(True)
         ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2,
                        loss_out=self.loss_train, workspace=self._nll_ws)
-        k += 2
         ops.spmm(self.graph_t, self.dZ2, F=self.Cp, plan=self.plan_t, out=self.G2)
         drop = self.p > 0.0
         r = ops.dense_bwd(self.G2, self.H1d, W2, self.dZ2, H=self.H, n_classes=self.C, act=self.act,
@@ -188,7 +184,6 @@ class TextGCNTrainer:
                           dZ1=self.dZ1, workspace=self._db_ws, dW2=self.grads[2], db_hidden=self.grads[1],
                           db_out=self.grads[3])
         self._db_ws = r["workspace"]
-        k += 1 + 4
         kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad, step_dev=self.step_dev)
         if self.fuse_adam:
             ops.adam_prepare(self.step_dev, self.adam_hyper, self.lr, self.betas[0], self.betas[1])     # step += 1
@@ -206,19 +201,16 @@ class TextGCNTrainer:
             ops.adam_step(self.params[0].data, self.grads[0], self.exp_avg[0], self.exp_avg_sq[0], self.max_exp_avg_sq[0], **kw)
         ops.adam_step_small([p_.data for p_ in self.params[1:]], self.grads[1:], self.exp_avg[1:], self.exp_avg_sq[1:],
                             self.max_exp_avg_sq[1:], **kw)
-        return k
 
-    def _eval_body(self) -> int:
+    def _eval_body(self) -> None:
         """eval forward, val loss, argmax of every row, #correct on the val and train rows
         (flat_amazon.py:107-114 without the D2H copies)."""
-        k = self._forward(False)
+        self._forward(False)
         if self.n_val > 0:
             ops.masked_nll(self.Z2, self.C, self.y, self.val_mask, self.n_val, want_grad=False,
                            loss_out=self.loss_val, workspace=self._nll_ws, pred=self.pred, correct=self.correct_val)
-            k += 2
         ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=False,
                        loss_out=self.loss_tr_eval, workspace=self._nll_ws, pred=self.pred, correct=self.correct_train)
-        return k + 2
 
     # ---- graph capture plumbing ----
     def _run(self, name: str, body) -> None:

@@ -3,7 +3,6 @@ padded id space, and -- under a real 2-process gloo group -- the exact collectiv
 DistTextGCNTrainer (all_gather_into_tensor between layers, all_reduce of the small gradients)
 with the local SpMMs emulated by torch CPU index ops, checked against the single-process oracle."""
 import os
-import sys
 
 import pytest
 import torch

@@ -4,12 +4,9 @@ import os
 import pickle
 import sys
 
-import numpy as np
-import pytest
 import torch
 
 from oracle import gcn_oracle as O
-from pytextgcn_b200.data import Data
 from pytextgcn_b200.graph import auto_chunk_nnz
 from pytextgcn_b200.models import decode_features
 from pytextgcn_b200.synthetic import SHAPES, GraphShape, make_graph
