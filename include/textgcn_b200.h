@@ -134,6 +134,38 @@ typedef struct {
 } tgcn_spmm_args;
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
 
+/* (2b) The same operation with the gathered operand rows staged in shared memory (csrc/spmm_staged.cu):
+ * one CTA per PANEL of consecutive chunks of the (length-sorted) chunk list walks the sorted union of
+ * the columns its chunks touch, tile by tile; a producer warp copies the operand rows of a tile from
+ * L2 into a ring of shared-memory stages (cp.async.bulk + mbarrier), consumer warps accumulate from
+ * shared memory.  A row needed by k chunks of a panel crosses L2->SM once instead of k times.
+ * `args` is the tgcn_spmm argument block (rowptr/colidx/val unused; fp32 B, F % 4 == 0, F <= 256, no
+ * fused projection; split rows need slot_owner + split_counters).  The plan is built once per
+ * (chunk list, warps_per_panel, rows_per_warp, tile_cols) by the host (pytextgcn_b200/staged_plan.py):
+ *   panel p = chunks [p*R, (p+1)*R), R = warps_per_panel*rows_per_warp; consumer warp w owns chunks
+ *             (p*warps_per_panel + w)*rows_per_warp + {0..rows_per_warp-1};
+ *   ucols[panel_ucol_ptr[p] .. panel_ucol_ptr[p+1]) = ascending distinct column ids of panel p; tile t
+ *             holds entries [t*tile_cols, (t+1)*tile_cols) of that range;
+ *   stream  = int32 pairs; warp_stream_ptr[p*warps_per_panel + w] = first pair of that warp.  For every
+ *             tile of the panel: a header {n0, n1} (entries of the warp's first / second chunk in the
+ *             tile) followed by n0 + n1 entries {slot within the tile, fp32 value bits}.  The array is
+ *             padded by 64 pairs.
+ * Experimental in round 1 (no B200 time was left to measure it): selected with TGCN_SPMM_STAGED=1. */
+typedef struct {
+  const int32_t* panel_ucol_ptr;   /* [n_panels + 1] */
+  const int32_t* ucols;            /* [panel_ucol_ptr[n_panels]] */
+  const int64_t* warp_stream_ptr;  /* [n_panels * warps_per_panel] */
+  const int32_t* stream;           /* [stream_len + 64][2] */
+  int32_t n_panels;
+  int32_t warps_per_panel;         /* consumer warps per CTA; warps_per_panel + n_producers <= 32 */
+  int32_t rows_per_warp;           /* 1 or 2 */
+  int32_t tile_cols;               /* operand rows per shared-memory stage, 1..128 */
+  /* launch shape (not part of the plan data): producer warps 1..4 and how they copy an operand row */
+  int32_t n_producers;
+  int32_t producer_mode;           /* 0 = one cp.async.bulk per row (TMA unit), 1 = 16-byte cp.async by all lanes */
+} tgcn_staged_plan;
+int tgcn_spmm_staged(const tgcn_spmm_args* args, const tgcn_staged_plan* plan, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (3) Masked log-softmax / NLL and its gradient, one pass over the logits.
  * Replaces: gcn(g)[mask] boolean gather + CrossEntropyLoss(mean) + its backward

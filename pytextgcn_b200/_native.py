@@ -40,6 +40,15 @@ class SpmmArgs(C.Structure):
     ]
 
 
+class StagedPlanArgs(C.Structure):
+    """Mirror of tgcn_staged_plan."""
+    _fields_ = [
+        ("panel_ucol_ptr", c_void), ("ucols", c_void), ("warp_stream_ptr", c_void), ("stream", c_void),
+        ("n_panels", C.c_int32), ("warps_per_panel", C.c_int32), ("rows_per_warp", C.c_int32), ("tile_cols", C.c_int32),
+        ("n_producers", C.c_int32), ("producer_mode", C.c_int32),
+    ]
+
+
 class DenseBwdArgs(C.Structure):
     """Mirror of tgcn_dense_bwd_args."""
     _fields_ = [
@@ -72,6 +81,7 @@ SIGNATURES = {
                                  c_void, C.c_size_t, c_void]),
     "tgcn_spmm_plan_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "tgcn_spmm": (C.c_int, [C.POINTER(SpmmArgs), c_void]),
+    "tgcn_spmm_staged": (C.c_int, [C.POINTER(SpmmArgs), C.POINTER(StagedPlanArgs), c_void]),
     "tgcn_masked_nll": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int32, c_void, c_void, C.c_int64,
                                   c_void, c_void, c_void, C.c_int64, c_void, c_void, c_void,
                                   c_void, C.c_size_t, c_void]),

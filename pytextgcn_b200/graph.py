@@ -75,6 +75,7 @@ class GraphCSR:
         self.nnz = int(colidx.numel())
         self.device = rowptr.device
         self._plans: Dict[Tuple[int, int, int], SpmmPlan] = {}
+        self._staged: Dict[Tuple, Tuple] = {}
         self._symmetric: Optional[bool] = None
         self._transpose: Optional["GraphCSR"] = None
         self.buffers: Dict[str, torch.Tensor] = {}   # static work buffers owned by the host layer
@@ -115,6 +116,18 @@ class GraphCSR:
                      counters=torch.zeros(max(n_split, 1), dtype=torch.int32, device=self.device) if n_split else None)
         self._plans[key] = p
         return p
+
+    def staged_plan(self, plan: SpmmPlan, warps_per_panel: int, rows_per_warp: int, tile_cols: int):
+        """Panel/tile arrays of the shared-memory staged SpMM for `plan` (built once, on the device)."""
+        key = (plan.row_begin, plan.row_end, plan.chunk_nnz, warps_per_panel, rows_per_warp, tile_cols)
+        sp = self._staged.get(key)
+        if sp is None or sp[0] is not plan:
+            from .staged_plan import build_staged_plan
+            built = build_staged_plan(self.colidx, self.val, plan.chunks, self.n_cols, warps_per_panel=warps_per_panel,
+                                      rows_per_warp=rows_per_warp, tile_cols=tile_cols)
+            sp = (plan, built)
+            self._staged[key] = sp
+        return sp[1]
 
     # ---- transpose handling for the backward pass ----
     def row_ids(self) -> torch.Tensor:

@@ -25,6 +25,19 @@ FUSED_PROJ_MAX_CLASSES = int(_os.environ.get("TGCN_FUSED_PROJ_MAX_CLASSES", "0")
 # split rows: 1 = the last-arriving chunk reduces the partial rows inside the SpMM kernel, 0 = separate fix-up kernel
 FOLD_FIXUP = int(_os.environ.get("TGCN_FOLD_FIXUP", "1"))
 
+# Wide fp32 propagations through the shared-memory staged panel kernel (tgcn_spmm_staged) instead of the
+# per-non-zero L2 gathers of tgcn_spmm.  EXPERIMENTAL: written after round 1's B200 budget was spent, so it
+# is parity-tested on the GPU only when selected (TGCN_SPMM_STAGED=1) and is off by default.  Shape knobs:
+# consumer warps per panel, chunks per consumer warp, operand rows per stage, producer warps, producer
+# mode (0 = one cp.async.bulk per row, 1 = 16-byte cp.async by all lanes), smallest F that uses it.
+STAGED = int(_os.environ.get("TGCN_SPMM_STAGED", "0"))
+STAGED_CFG = dict(warps_per_panel=int(_os.environ.get("TGCN_STAGED_WARPS", "28")),
+                  rows_per_warp=int(_os.environ.get("TGCN_STAGED_RPW", "1")),
+                  tile_cols=int(_os.environ.get("TGCN_STAGED_TILE", "64")),
+                  n_producers=int(_os.environ.get("TGCN_STAGED_PRODUCERS", "4")),
+                  producer_mode=int(_os.environ.get("TGCN_STAGED_MODE", "0")),
+                  min_f=int(_os.environ.get("TGCN_STAGED_MIN_F", "96")))
+
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 
@@ -59,8 +72,11 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
          drop_mode: int = DROP_NONE, drop_p: float = 0.0, keep_mask: Optional[torch.Tensor] = None,
          philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0,
          W_proj: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
-         want_out: bool = True, adam: Optional[dict] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+         want_out: bool = True, adam: Optional[dict] = None,
+         staged: Optional[bool] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """C = epi(A_hat[rows of plan] @ B[:, :F]) (+ P = C @ W_proj).  See tgcn_spmm.
+    staged: True/False forces / forbids the shared-memory staged kernel (tgcn_spmm_staged); None follows
+    TGCN_SPMM_STAGED for the shapes that kernel covers (fp32 B, F % 4 == 0, min_f <= F <= 256, no projection).
 
     B: [>= n_nodes, >= F] fp32/bf16, row stride a multiple of 4 (fp32) / 8 (bf16) elements.
     Returns (C or None, P or None).  C has plan.row_end - plan.row_begin rows.
@@ -123,8 +139,22 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
         if P is None:
             P = torch.zeros((n_out, pad4(n_proj)), dtype=torch.float32, device=B.device)
         a.W_proj, a.n_proj, a.P, a.ldp = W_proj.data_ptr(), n_proj, P.data_ptr(), P.stride(0)
+    can_stage = (B.dtype == torch.float32 and F % 4 == 0 and F <= 256 and W_proj is None
+                 and (plan.n_split_rows == 0 or FOLD_FIXUP))
+    if staged is None:
+        staged = bool(STAGED) and can_stage and F >= STAGED_CFG["min_f"]
+    elif staged and not can_stage:
+        raise RuntimeError("spmm: the staged kernel needs an fp32 operand, F % 4 == 0, F <= 256, no fused projection "
+                           "and in-kernel reduction of split rows")
     with torch.cuda.device(B.device):
-        _native.check(lib.tgcn_spmm(C.byref(a), _stream()))
+        if staged:
+            from . import staged_plan as _sp
+            cfg = STAGED_CFG
+            sp = graph.staged_plan(plan, cfg["warps_per_panel"], cfg["rows_per_warp"], cfg["tile_cols"])
+            cp = _sp.c_plan(sp, cfg["n_producers"], cfg["producer_mode"])
+            _native.check(lib.tgcn_spmm_staged(C.byref(a), C.byref(cp), _stream()))
+        else:
+            _native.check(lib.tgcn_spmm(C.byref(a), _stream()))
     return out, P
 
 
