@@ -32,7 +32,7 @@ FOLD_FIXUP = int(_os.environ.get("TGCN_FOLD_FIXUP", "1"))
 # mode (0 = one cp.async.bulk per row, 1 = 16-byte cp.async by all lanes), smallest F that uses it.
 STAGED = int(_os.environ.get("TGCN_SPMM_STAGED", "0"))
 STAGED_CFG = dict(warps_per_panel=int(_os.environ.get("TGCN_STAGED_WARPS", "28")),
-                  rows_per_warp=int(_os.environ.get("TGCN_STAGED_RPW", "1")),
+                  rows_per_warp=int(_os.environ.get("TGCN_STAGED_RPW", "2")),
                   tile_cols=int(_os.environ.get("TGCN_STAGED_TILE", "64")),
                   n_producers=int(_os.environ.get("TGCN_STAGED_PRODUCERS", "4")),
                   producer_mode=int(_os.environ.get("TGCN_STAGED_MODE", "0")),

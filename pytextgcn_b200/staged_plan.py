@@ -52,7 +52,7 @@ class StagedPlan:
 
 
 def build_staged_plan(colidx: torch.Tensor, val: torch.Tensor, chunks: torch.Tensor, n_cols: int, *,
-                      warps_per_panel: int = 28, rows_per_warp: int = 1, tile_cols: int = 64) -> StagedPlan:
+                      warps_per_panel: int = 28, rows_per_warp: int = 2, tile_cols: int = 64) -> StagedPlan:
     """colidx int32 [nnz], val fp32 [nnz]: the CSR arrays the chunk list indexes; chunks int32
     [n_chunks, 4] = {row, begin, end, slot} in the order the kernel will use (tgcn_spmm_plan, sorted)."""
     if rows_per_warp not in (1, 2):
