@@ -77,6 +77,16 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// (c0, c1) += a * (x0, x1) as ONE packed instruction (FFMA2, sm_100): same IEEE fma per element, half the
+// issue slots of two scalar FFMAs -- the consumer loop is issue-sensitive (about 20 instructions per non-zero).
+__device__ __forceinline__ void fma2(float& c0, float& c1, float a, float x0, float x1) {
+  unsigned long long c, x;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("{\n .reg .b64 av;\n mov.b64 av, {%2, %2};\n fma.rn.f32x2 %0, av, %1, %0;\n}" : "+l"(c) : "l"(x), "f"(a));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(c));
+}
+
 constexpr int PROD_BULK = 0;     // one cp.async.bulk (TMA unit) per operand row, issued lane by lane
 constexpr int PROD_LDGSTS = 1;   // the 32 lanes of a producer warp copy a row with 16-byte cp.async
 
@@ -203,7 +213,9 @@ __global__ void __launch_bounds__(1024, 1) k_spmm_staged(const SpmmParams p, con
     asm volatile("prefetch.global.L1 [%0];" ::"l"(st + q + 32));
     asm volatile("prefetch.global.L1 [%0];" ::"l"(st + q + 48));
     mbar_wait(full0 + 8 * stage, parity);                 // the tile's operand rows have landed
-    const unsigned char* tile = stages + (size_t)stage * sp.stage_bytes;
+    const unsigned char* tile[VPL];                       // this lane's pieces of slot 0 of the stage
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) tile[v] = stages + (size_t)stage * sp.stage_bytes + loff[v];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const int cnt = (r == 0) ? hdr.x : hdr.y;
@@ -211,12 +223,12 @@ __global__ void __launch_bounds__(1024, 1) k_spmm_staged(const SpmmParams p, con
       for (int j = 0; j < cnt; ++j) {
         const int2 e = __ldg(st + q + j);                 // {slot within the tile, value bits}
         const float a = __int_as_float(e.y);
-        const unsigned char* row = tile + (uint32_t)e.x * sp.row_bytes;
+        const uint32_t row = (uint32_t)e.x * sp.row_bytes;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
-          const float4 x = *reinterpret_cast<const float4*>(row + loff[v]);
-          acc[r][v][0] = fmaf(a, x.x, acc[r][v][0]); acc[r][v][1] = fmaf(a, x.y, acc[r][v][1]);
-          acc[r][v][2] = fmaf(a, x.z, acc[r][v][2]); acc[r][v][3] = fmaf(a, x.w, acc[r][v][3]);
+          const float4 x = *reinterpret_cast<const float4*>(tile[v] + row);
+          fma2(acc[r][v][0], acc[r][v][1], a, x.x, x.y);
+          fma2(acc[r][v][2], acc[r][v][3], a, x.z, x.w);
         }
       }
       q += cnt;
