@@ -338,8 +338,11 @@ def run_own_arm(args):
     achieved = alg / (k_ms * 1e-3) / 1e9
     prof = load_profile_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": prof.get("dram_bytes_per_launch"),
-                "kernel": "k_spmm<float,32,2,false> (layer-1 propagation of the train step, F=%d, fused bias + Philox dropout epilogue)" % F,
+                "traffic": None if (ops.STAGED and F >= ops.STAGED_CFG["min_f"]) else prof.get("dram_bytes_per_launch"),
+                "kernel": ("k_spmm_staged<2,%d,plain,%s> (shared-memory staged panel kernel, TGCN_SPMM_STAGED=1; "
+                           % (ops.STAGED_CFG["rows_per_warp"], "bulk" if ops.STAGED_CFG["producer_mode"] == 0 else "ldgsts")
+                           if (ops.STAGED and F >= ops.STAGED_CFG["min_f"]) else "k_spmm<float,32,2,false> (")
+                          + "layer-1 propagation of the train step, F=%d, fused bias + Philox dropout epilogue)" % F,
                 "kernel_ms": k_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
                 "note": "algorithmic bytes count each dense row once; the kernel is bound by L2->SM gather bandwidth "
                         "(nnz*F*4 = %.1f GB per launch), see DESIGN.md" % (graph.nnz * F * 4 / 1e9),
