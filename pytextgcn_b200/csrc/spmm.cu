@@ -13,6 +13,12 @@
 // scratch buffer and a fix-up kernel adds them in slot order: deterministic, no atomics.
 #include "spmm_common.cuh"
 
+// Build variant for A/B runs (make variant-addr32 -> lib/libtextgcn_b200_addr32.so, selected with TGCN_B200_LIB):
+// 32-bit row-pitch arithmetic in the gather loop.  The shipped build keeps the 64-bit form its numbers were measured with.
+#ifndef TGCN_SPMM_ADDR32
+#define TGCN_SPMM_ADDR32 0
+#endif
+
 namespace tgcn {
 
 template <typename TB, int LPR, int VPL, int EPI>
@@ -39,6 +45,9 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
   const int l = lane % LPR;
   const TB* __restrict__ B = reinterpret_cast<const TB*>(p.B);
   const int F = p.F;
+#if TGCN_SPMM_ADDR32
+  const uint32_t ldb_bytes = (uint32_t)(p.ldb * (int64_t)sizeof(TB));
+#endif
   bool active[VPL];
 #pragma unroll
   for (int v = 0; v < VPL; ++v) active[v] = ((l + v * LPR) * E) < F;
@@ -74,7 +83,13 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
       float x[U][VPL][E];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
+#if TGCN_SPMM_ADDR32
+        // one IMAD.WIDE.U32 per gather: lane base + column * row pitch in bytes (host checks it fits 32 bits)
+        const TB* brow = reinterpret_cast<const TB*>(reinterpret_cast<const char*>(B) +
+                                                     (uint64_t)(uint32_t)cc[u] * (uint64_t)ldb_bytes);
+#else
         const TB* brow = B + (int64_t)cc[u] * p.ldb;
+#endif
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
           if (active[v] && vv[u] != 0.0f) Vec<TB>::load(brow + (l + v * LPR) * E, x[u][v]);
@@ -364,6 +379,9 @@ extern "C" int tgcn_spmm(const tgcn_spmm_args* a, void* stream_) {
 
   SpmmParams p;
   if (int rc = fill_spmm_params(a, &p)) return rc;
+#if TGCN_SPMM_ADDR32
+  TGCN_CHECK_ARG(a->ldb * (a->b_dtype == TGCN_F32 ? 4 : 2) < (int64_t)1 << 31, "spmm: row pitch too large for the 32-bit address variant");
+#endif
   if (a->b_dtype == TGCN_F32) return dispatch_spmm<float>(p, stream);
   return dispatch_spmm<__nv_bfloat16>(p, stream);
 }

@@ -26,6 +26,11 @@ if [ "$rc_staged" = "0" ]; then
       -o gpurun_out/r02_prof_spmm_staged -f python tools/ab_spmm.py 20ng 1 --only staged:28,2,64,4,0 > gpurun_out/r02_ncu_staged.log 2>&1
   echo "ncu staged rc=$?" | tee -a gpurun_out/r02_status.txt
 fi
+# 5. build variant with 32-bit gather addressing (1.5x fewer instructions in the narrow SpMM loop): same bench
+make -C pytextgcn_b200/csrc variant-addr32 > gpurun_out/r02_build_addr32.log 2>&1 && \
+  TGCN_B200_LIB=$PWD/pytextgcn_b200/lib/libtextgcn_b200_addr32.so timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline \
+    > gpurun_out/r02_bench_addr32.json 2> gpurun_out/r02_bench_addr32.err
+echo "bench addr32 rc=$?" | tee -a gpurun_out/r02_status.txt
 cat gpurun_out/r02_status.txt
 tail -3 gpurun_out/r02_pytest_default.log gpurun_out/r02_pytest_staged.log
 cat gpurun_out/r02_ab_spmm_20ng.jsonl
