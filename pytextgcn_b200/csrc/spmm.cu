@@ -15,8 +15,16 @@
 
 // Build variant for A/B runs (make variant-addr32 -> lib/libtextgcn_b200_addr32.so, selected with TGCN_B200_LIB):
 // 32-bit row-pitch arithmetic in the gather loop.  The shipped build keeps the 64-bit form its numbers were measured with.
+#if defined(TGCN_SPMM_ALL) && TGCN_SPMM_ALL     // variant-all: every variant switch below
+#define TGCN_SPMM_ADDR32 1
+#define TGCN_SPMM_EXACTLPR 1
+#endif
 #ifndef TGCN_SPMM_ADDR32
 #define TGCN_SPMM_ADDR32 0
+#endif
+// variant-exactlpr: lanes per gathered row = its number of 16-byte pieces, also when that is not a power of two
+#ifndef TGCN_SPMM_EXACTLPR
+#define TGCN_SPMM_EXACTLPR 0
 #endif
 
 namespace tgcn {
@@ -79,6 +87,7 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
         cc[u] = __shfl_sync(0xffffffffu, mc, srcl & 31);
         vv[u] = __shfl_sync(0xffffffffu, mv, srcl & 31);
         if (srcl >= cnt) vv[u] = 0.0f;
+        if constexpr (32 % LPR != 0) { if (sub >= NZP) vv[u] = 0.0f; }   // lanes past the last whole group idle
       }
       float x[U][VPL][E];
 #pragma unroll
@@ -108,12 +117,26 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
     }
   }
   // fold the NZP side-by-side partial rows into lanes [0, LPR)
+  if constexpr ((LPR & (LPR - 1)) == 0) {
 #pragma unroll
-  for (int o = 16; o >= LPR; o >>= 1)
+    for (int o = 16; o >= LPR; o >>= 1)
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int i = 0; i < E; ++i) acc[v][i] += __shfl_down_sync(0xffffffffu, acc[v][i], o);
+  } else {
+    // LPR not a power of two (TGCN_SPMM_EXACTLPR): group g of lane l sits at lane l + g*LPR
 #pragma unroll
     for (int v = 0; v < VPL; ++v)
 #pragma unroll
-      for (int i = 0; i < E; ++i) acc[v][i] += __shfl_down_sync(0xffffffffu, acc[v][i], o);
+      for (int i = 0; i < E; ++i) {
+        const float mine = acc[v][i];
+        float sum = mine;
+#pragma unroll
+        for (int g = 1; g < NZP; ++g) sum += __shfl_sync(0xffffffffu, mine, (lane + g * LPR) & 31);
+        acc[v][i] = sum;
+      }
+  }
 
   // (same steps as finish_row() in spmm_common.cuh, kept inline here: routing this kernel through the
   // shared function changes ptxas' schedule of the gather loop above, which is tuned -- DESIGN.md 3)
@@ -318,6 +341,17 @@ template <typename TB>
 static int dispatch_spmm(const SpmmParams& p, cudaStream_t stream) {
   constexpr int E = Vec<TB>::E;
   const int nvec = (p.F + E - 1) / E;   // 16-byte vectors per dense row
+#if TGCN_SPMM_EXACTLPR
+  // class-wide operands: as many lanes per non-zero as the row has 16-byte pieces (20 classes = 5 pieces:
+  // 6 non-zeros side by side instead of 4 with 3 of every 8 lanes idle)
+  if constexpr (std::is_same<TB, float>::value) {
+    if (nvec == 2) return launch_spmm<TB, 2, 1>(p, stream);
+    if (nvec == 3) return launch_spmm<TB, 3, 1>(p, stream);
+    if (nvec == 5) return launch_spmm<TB, 5, 1>(p, stream);
+    if (nvec == 6) return launch_spmm<TB, 6, 1>(p, stream);
+    if (nvec == 7) return launch_spmm<TB, 7, 1>(p, stream);
+  }
+#endif
   if (nvec <= 4) return launch_spmm<TB, 4, 1>(p, stream);
   if (nvec <= 8) return launch_spmm<TB, 8, 1>(p, stream);
   if (nvec <= 16) return launch_spmm<TB, 16, 1>(p, stream);

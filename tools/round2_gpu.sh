@@ -1,5 +1,5 @@
 #!/bin/bash
-# First GPU call of the next round, in one gpurun invocation (about 6-8 minutes of box time):
+# First GPU call of the next round, in one gpurun invocation (about 10-12 minutes of box time):
 #   1. default GPU suite + the staged-kernel parity tests (TGCN_TEST_STAGED=1), each under its own timeout;
 #   2. A/B of the wide propagation: tgcn_spmm vs tgcn_spmm_staged over the plan/launch shapes of tools/ab_spmm.py;
 #   3. bench.py with the default kernel and with TGCN_SPMM_STAGED=1 (no CPU arm: it is timed separately);
@@ -26,11 +26,18 @@ if [ "$rc_staged" = "0" ]; then
       -o gpurun_out/r02_prof_spmm_staged -f python tools/ab_spmm.py 20ng 1 --only staged:28,2,64,4,0 > gpurun_out/r02_ncu_staged.log 2>&1
   echo "ncu staged rc=$?" | tee -a gpurun_out/r02_status.txt
 fi
-# 5. build variant with 32-bit gather addressing (1.5x fewer instructions in the narrow SpMM loop): same bench
-make -C pytextgcn_b200/csrc variant-addr32 > gpurun_out/r02_build_addr32.log 2>&1 && \
-  TGCN_B200_LIB=$PWD/pytextgcn_b200/lib/libtextgcn_b200_addr32.so timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline \
-    > gpurun_out/r02_bench_addr32.json 2> gpurun_out/r02_bench_addr32.err
-echo "bench addr32 rc=$?" | tee -a gpurun_out/r02_status.txt
+# 5. build variants of the gather kernel (same sources, macros flipped): 32-bit gather addressing alone, and with
+#    exact lanes-per-row for class-wide operands (3.2 instead of 6.4 instructions per non-zero in the narrow loop):
+#    parity tests against the oracle with the variant library loaded, then the same bench
+for v in addr32 all; do
+  make -C pytextgcn_b200/csrc variant-$v > gpurun_out/r02_build_$v.log 2>&1 || { echo "build $v failed" | tee -a gpurun_out/r02_status.txt; continue; }
+  export TGCN_B200_LIB=$PWD/pytextgcn_b200/lib/libtextgcn_b200_$v.so
+  timeout 420 python -m pytest tests/test_gpu_spmm.py tests/test_gpu_model.py tests/test_gpu_train.py -x -q -m gpu > gpurun_out/r02_pytest_$v.log 2>&1
+  echo "pytest $v rc=$?" | tee -a gpurun_out/r02_status.txt
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02_bench_$v.json 2> gpurun_out/r02_bench_$v.err
+  echo "bench $v rc=$?" | tee -a gpurun_out/r02_status.txt
+  unset TGCN_B200_LIB
+done
 cat gpurun_out/r02_status.txt
 tail -3 gpurun_out/r02_pytest_default.log gpurun_out/r02_pytest_staged.log
 cat gpurun_out/r02_ab_spmm_20ng.jsonl
