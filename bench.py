@@ -354,7 +354,11 @@ def run_own_arm(args):
     vm_pin = g.val_mask.pin_memory()
     pred_pin = torch.empty(n, dtype=torch.int32).pin_memory()
     scal_pin = torch.empty(4, dtype=torch.float32).pin_memory()
-    y_np, vm_np, tm_np = g.y.numpy(), g.val_mask.numpy(), g.train_mask.numpy()
+    y_np = g.y.numpy()
+    # row ids and labels of the (static) val / train rows, gathered once: the per-epoch host metric is then a
+    # 5.6 k / 11.3 k element gather + compare instead of two boolean-mask passes over all 61.6 k rows
+    vm_idx, tm_idx = np.flatnonzero(g.val_mask.numpy()), np.flatnonzero(g.train_mask.numpy())
+    y_vm, y_tm = y_np[vm_idx], y_np[tm_idx]
     h2d = y_pin.numel() * 8 + tm_pin.numel() + vm_pin.numel()
     d2h = pred_pin.numel() * 4 + 16
 
@@ -369,8 +373,8 @@ def run_own_arm(args):
         scal_pin[2:].copy_(tr.loss_val, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         p = pred_pin.numpy()
-        acc_val = float((p[vm_np] == y_np[vm_np]).mean())    # host metrics as flat_amazon.py:111-114
-        acc_tr = float((p[tm_np] == y_np[tm_np]).mean())
+        acc_val = float((p[vm_idx] == y_vm).mean())          # host metrics as flat_amazon.py:111-114
+        acc_tr = float((p[tm_idx] == y_tm).mean())
         return float(scal_pin[0]), acc_tr, acc_val
     for _ in range(3):
         epoch_e2e()
