@@ -131,6 +131,10 @@ typedef struct {
    * adam_param_mirror_mc: multicast mapping of the parameter (row-partitioned mode) or NULL. */
   float* adam_param; float* adam_exp_avg; float* adam_exp_avg_sq; float* adam_max_exp_avg_sq; int64_t adam_ld;
   const float* adam_hyper_dev; float adam_beta1; float adam_beta2; float adam_eps; void* adam_param_mirror_mc;
+  /* optional: the CSR entries again as interleaved pairs {colidx[k], bits of val[k]} (int32[nnz][2]).  Only read by
+   * library builds made with TGCN_SPMM_CVPACK (one broadcast 8-byte load per non-zero instead of two shuffles);
+   * NULL otherwise. */
+  const int32_t* colval;
 } tgcn_spmm_args;
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
 

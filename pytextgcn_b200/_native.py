@@ -37,6 +37,7 @@ class SpmmArgs(C.Structure):
         ("adam_param", c_void), ("adam_exp_avg", c_void), ("adam_exp_avg_sq", c_void), ("adam_max_exp_avg_sq", c_void),
         ("adam_ld", C.c_int64), ("adam_hyper_dev", c_void), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float),
         ("adam_eps", C.c_float), ("adam_param_mirror_mc", c_void),
+        ("colval", c_void),
     ]
 
 

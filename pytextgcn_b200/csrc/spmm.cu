@@ -13,19 +13,9 @@
 // scratch buffer and a fix-up kernel adds them in slot order: deterministic, no atomics.
 #include "spmm_common.cuh"
 
-// Build variant for A/B runs (make variant-addr32 -> lib/libtextgcn_b200_addr32.so, selected with TGCN_B200_LIB):
-// 32-bit row-pitch arithmetic in the gather loop.  The shipped build keeps the 64-bit form its numbers were measured with.
-#if defined(TGCN_SPMM_ALL) && TGCN_SPMM_ALL     // variant-all: every variant switch below
-#define TGCN_SPMM_ADDR32 1
-#define TGCN_SPMM_EXACTLPR 1
-#endif
-#ifndef TGCN_SPMM_ADDR32
-#define TGCN_SPMM_ADDR32 0
-#endif
-// variant-exactlpr: lanes per gathered row = its number of 16-byte pieces, also when that is not a power of two
-#ifndef TGCN_SPMM_EXACTLPR
-#define TGCN_SPMM_EXACTLPR 0
-#endif
+// Build variants for A/B runs (switches in spmm_common.cuh; `make variant-addr32|exactlpr|cvpack|all` writes
+// lib/libtextgcn_b200_<name>.so, selected with TGCN_B200_LIB).  The shipped build keeps every switch off: its SASS is
+// the one the round-1 numbers were measured with.
 
 namespace tgcn {
 
@@ -73,6 +63,48 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
 #pragma unroll
     for (int i = 0; i < E; ++i) acc[v][i] = 0.0f;
 
+#if TGCN_SPMM_CVPACK
+  if (p.cv != nullptr) {
+    // (col, val) of a non-zero as ONE 8-byte load with the same address in every lane of its group (a broadcast:
+    // one L1 wavefront per warp request) instead of two shuffles (two wavefronts of the same data pipe, which is
+    // the unit this kernel saturates: ncu l1tex__data_pipe_lsu_wavefronts, profiles/dominant_kernel.json)
+    for (int base = ch.y; base < ch.z; base += NZP * U) {
+      if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.cv + base + 2 * NZP * U));
+      int cc[U]; float vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = base + u * NZP + sub;
+        int2 e = make_int2(0, 0);
+        if (k < ch.z && (32 % LPR == 0 || sub < NZP)) e = __ldg(p.cv + k);
+        cc[u] = e.x; vv[u] = __int_as_float(e.y);
+      }
+      float x[U][VPL][E];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#if TGCN_SPMM_ADDR32
+        const TB* brow = reinterpret_cast<const TB*>(reinterpret_cast<const char*>(B) +
+                                                     (uint64_t)(uint32_t)cc[u] * (uint64_t)ldb_bytes);
+#else
+        const TB* brow = B + (int64_t)cc[u] * p.ldb;
+#endif
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          if (active[v] && vv[u] != 0.0f) Vec<TB>::load(brow + (l + v * LPR) * E, x[u][v]);
+          else {
+#pragma unroll
+            for (int i = 0; i < E; ++i) x[u][v][i] = 0.0f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int i = 0; i < E; ++i) acc[v][i] = fmaf(vv[u], x[u][v][i], acc[v][i]);
+    }
+  } else
+#endif
   for (int base = ch.y; base < ch.z; base += 32) {
     const int k = base + lane;
     int mc = 0; float mv = 0.0f;

@@ -5,6 +5,22 @@
 #include "common.cuh"
 #include <type_traits>
 
+// Build-variant switches of the gather kernel (make variant-<name>; the shipped build has all of them off).
+#if defined(TGCN_SPMM_ALL) && TGCN_SPMM_ALL
+#define TGCN_SPMM_ADDR32 1
+#define TGCN_SPMM_EXACTLPR 1
+#define TGCN_SPMM_CVPACK 1
+#endif
+#ifndef TGCN_SPMM_ADDR32
+#define TGCN_SPMM_ADDR32 0      // 32-bit row-pitch arithmetic in the gather loop (one IMAD.WIDE per gather)
+#endif
+#ifndef TGCN_SPMM_EXACTLPR
+#define TGCN_SPMM_EXACTLPR 0    // lanes per gathered row = its number of 16-byte pieces, also when not a power of two
+#endif
+#ifndef TGCN_SPMM_CVPACK
+#define TGCN_SPMM_CVPACK 0      // (col, val) read as one broadcast 8-byte load per non-zero instead of two shuffles
+#endif
+
 namespace tgcn {
 
 struct SpmmParams {
@@ -26,6 +42,9 @@ struct SpmmParams {
   // fused Adam/AMSGrad on the finished row (backward of layer 1 with X = I: the row IS dW1[row])
   float* ad_p; float* ad_m; float* ad_v; float* ad_x; int64_t ad_ld; const float* __restrict__ ad_hyp;
   float ad_b1, ad_b2, ad_eps; float* ad_mirror;
+#if TGCN_SPMM_CVPACK
+  const int2* __restrict__ cv;   // {colidx[k], bits of val[k]} pairs (build variant, see spmm.cu)
+#endif
 };
 
 // ---- loads of 16 bytes of the dense operand -> 4 (fp32) or 8 (bf16) floats ----
@@ -268,6 +287,9 @@ static inline int fill_spmm_params(const tgcn_spmm_args* a, SpmmParams* p) {
   p->ad_p = a->adam_param; p->ad_m = a->adam_exp_avg; p->ad_v = a->adam_exp_avg_sq; p->ad_x = a->adam_max_exp_avg_sq;
   p->ad_ld = a->adam_ld; p->ad_hyp = a->adam_hyper_dev; p->ad_b1 = a->adam_beta1; p->ad_b2 = a->adam_beta2; p->ad_eps = a->adam_eps;
   p->ad_mirror = (float*)a->adam_param_mirror_mc;
+#if TGCN_SPMM_CVPACK
+  p->cv = reinterpret_cast<const int2*>(a->colval);
+#endif
   if (p->ad_p) {
     TGCN_CHECK_ARG(p->ad_m && p->ad_v && p->ad_hyp, "spmm: fused Adam needs exp_avg, exp_avg_sq and the hyper buffer");
     TGCN_CHECK_ARG(a->P == nullptr && a->b_dtype == TGCN_F32 && p->ad_ld % 4 == 0 && p->ad_ld >= a->F,

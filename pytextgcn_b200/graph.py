@@ -76,6 +76,7 @@ class GraphCSR:
         self.device = rowptr.device
         self._plans: Dict[Tuple[int, int, int], SpmmPlan] = {}
         self._staged: Dict[Tuple, Tuple] = {}
+        self._colval: Optional[torch.Tensor] = None
         self._symmetric: Optional[bool] = None
         self._transpose: Optional["GraphCSR"] = None
         self.buffers: Dict[str, torch.Tensor] = {}   # static work buffers owned by the host layer
@@ -116,6 +117,13 @@ class GraphCSR:
                      counters=torch.zeros(max(n_split, 1), dtype=torch.int32, device=self.device) if n_split else None)
         self._plans[key] = p
         return p
+
+    def colval(self) -> torch.Tensor:
+        """The CSR entries once more as interleaved pairs {colidx[k], bits of val[k]} (int32 [nnz, 2]) for library
+        builds that read one 8-byte pair per non-zero (TGCN_SPMM_CVPACK); built on first use."""
+        if self._colval is None:
+            self._colval = torch.stack([self.colidx, self.val.view(torch.int32)], dim=1).contiguous()
+        return self._colval
 
     def staged_plan(self, plan: SpmmPlan, warps_per_panel: int, rows_per_warp: int, tile_cols: int):
         """Panel/tile arrays of the shared-memory staged SpMM for `plan` (built once, on the device)."""

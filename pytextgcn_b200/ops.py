@@ -38,6 +38,10 @@ STAGED_CFG = dict(warps_per_panel=int(_os.environ.get("TGCN_STAGED_WARPS", "28")
                   producer_mode=int(_os.environ.get("TGCN_STAGED_MODE", "0")),
                   min_f=int(_os.environ.get("TGCN_STAGED_MIN_F", "96")))
 
+# 1 = also hand the kernels the CSR entries as interleaved {col, val} pairs (GraphCSR.colval, +8 B per non-zero).
+# Only library builds made with TGCN_SPMM_CVPACK read them (make variant-cvpack / variant-all); the shipped build ignores the field.
+CVPACK = int(_os.environ.get("TGCN_SPMM_CVPACK", "0"))
+
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 
@@ -109,6 +113,8 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
         a.adam_param_mirror_mc = adam.get("mirror")
     if plan.n_split_rows and FOLD_FIXUP:
         a.slot_owner, a.split_counters = _native.ptr(plan.slot_owner), _native.ptr(plan.counters)
+    if CVPACK:
+        a.colval = graph.colval().data_ptr()
     a.B, a.ldb, a.b_dtype = B.data_ptr(), B.stride(0), _dt(B)
     if want_out:
         if out is None:

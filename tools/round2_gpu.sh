@@ -26,17 +26,18 @@ if [ "$rc_staged" = "0" ]; then
       -o gpurun_out/r02_prof_spmm_staged -f python tools/ab_spmm.py 20ng 1 --only staged:28,2,64,4,0 > gpurun_out/r02_ncu_staged.log 2>&1
   echo "ncu staged rc=$?" | tee -a gpurun_out/r02_status.txt
 fi
-# 5. build variants of the gather kernel (same sources, macros flipped): 32-bit gather addressing alone, and with
-#    exact lanes-per-row for class-wide operands (3.2 instead of 6.4 instructions per non-zero in the narrow loop):
+# 5. build variants of the gather kernel (same sources, macros flipped): 32-bit gather addressing; (col,val) as one
+#    broadcast 8-byte load instead of two shuffles (the L1 data pipe is the saturated unit); all switches incl. exact
+#    lanes-per-row for class-wide operands (3.2 instead of 6.4 instructions per non-zero in the narrow loop):
 #    parity tests against the oracle with the variant library loaded, then the same bench
-for v in addr32 all; do
+for v in addr32 cvpack all; do
   make -C pytextgcn_b200/csrc variant-$v > gpurun_out/r02_build_$v.log 2>&1 || { echo "build $v failed" | tee -a gpurun_out/r02_status.txt; continue; }
-  export TGCN_B200_LIB=$PWD/pytextgcn_b200/lib/libtextgcn_b200_$v.so
+  export TGCN_B200_LIB=$PWD/pytextgcn_b200/lib/libtextgcn_b200_$v.so TGCN_SPMM_CVPACK=1
   timeout 420 python -m pytest tests/test_gpu_spmm.py tests/test_gpu_model.py tests/test_gpu_train.py -x -q -m gpu > gpurun_out/r02_pytest_$v.log 2>&1
   echo "pytest $v rc=$?" | tee -a gpurun_out/r02_status.txt
   timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02_bench_$v.json 2> gpurun_out/r02_bench_$v.err
   echo "bench $v rc=$?" | tee -a gpurun_out/r02_status.txt
-  unset TGCN_B200_LIB
+  unset TGCN_B200_LIB TGCN_SPMM_CVPACK
 done
 cat gpurun_out/r02_status.txt
 tail -3 gpurun_out/r02_pytest_default.log gpurun_out/r02_pytest_staged.log
