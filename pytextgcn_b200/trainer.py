@@ -12,6 +12,7 @@ parameters are updated in place, so the wrapped `GCN` stays an ordinary nn.Modul
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -19,6 +20,8 @@ import torch
 from . import ops
 from .graph import GraphCSR, get_graph
 from .models import GCN, decode_features
+
+ROW_ALIGN = int(os.environ.get("TGCN_ROW_ALIGN", "0"))
 
 
 class TextGCNTrainer:
@@ -65,6 +68,24 @@ class TextGCNTrainer:
         self.exp_avg = [torch.zeros_like(p_.data) for p_ in self.params]
         self.exp_avg_sq = [torch.zeros_like(p_.data) for p_ in self.params]
         self.max_exp_avg_sq = [torch.zeros_like(p_.data) for p_ in self.params] if amsgrad else [None] * 4
+        # Row pitch of the gathered hidden-wide operands (W1 and dZ1).  A 200-float row is 800 bytes, so 3 of 4 rows
+        # start off a 128-byte line and a warp's 512-byte load of such a row costs 5 instead of 4 wavefronts of the L1
+        # data pipe -- the unit the wide SpMM saturates.  TGCN_ROW_ALIGN=1 (experimental: not measured yet) re-homes W1,
+        # its gradient and Adam state in buffers whose pitch is a multiple of 32 floats; `layers.0.weight` then is a
+        # strided view of that buffer (same shape and values).  Needs the fused Adam path (its kernels take a pitch).
+        self.row_pitch = H
+        if ROW_ALIGN and H % 32 != 0 and bool(fuse_adam) and self.feat.Fdoc is None:
+            self.row_pitch = (H + 31) // 32 * 32
+
+            def padded(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+                if t is None:
+                    return None
+                buf = torch.zeros((t.shape[0], self.row_pitch), dtype=t.dtype, device=t.device)
+                buf[:, :H].copy_(t)
+                return buf[:, :H]
+            l0.weight.data = padded(l0.weight.data)
+            self.grads[0], self.exp_avg[0], self.exp_avg_sq[0] = padded(self.grads[0]), padded(self.exp_avg[0]), padded(self.exp_avg_sq[0])
+            self.max_exp_avg_sq[0] = padded(self.max_exp_avg_sq[0])
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.adam_hyper = torch.zeros(2, dtype=torch.float32, device=dev)   # lr/(1-b1^t), sqrt(1-b2^t) of the current step
         # W1's Adam update can run in the epilogue of the SpMM that produces dW1 (rows of dW1 never leave registers
@@ -77,7 +98,7 @@ class TextGCNTrainer:
         self.Z2 = torch.zeros((n, Cp), **f32)
         self.dZ2 = torch.zeros((n, Cp), **f32)
         self.G2 = torch.zeros((n, Cp), **f32)
-        self.dZ1 = torch.zeros((n, H), **f32)
+        self.dZ1 = torch.zeros((n, self.row_pitch), **f32)[:, :H]
         self.loss_train = torch.zeros(2, **f32)
         self.loss_val = torch.zeros(2, **f32)
         self.loss_tr_eval = torch.zeros(2, **f32)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# First GPU call of the next round, in one gpurun invocation (about 10-12 minutes of box time):
+# First GPU call of the next round, in one gpurun invocation (about 15 minutes of box time):
 #   1. default GPU suite + the staged-kernel parity tests (TGCN_TEST_STAGED=1), each under its own timeout;
 #   2. A/B of the wide propagation: tgcn_spmm vs tgcn_spmm_staged over the plan/launch shapes of tools/ab_spmm.py;
 #   3. bench.py with the default kernel and with TGCN_SPMM_STAGED=1 (no CPU arm: it is timed separately);
@@ -39,6 +39,14 @@ for v in addr32 cvpack all; do
   echo "bench $v rc=$?" | tee -a gpurun_out/r02_status.txt
   unset TGCN_B200_LIB TGCN_SPMM_CVPACK
 done
+# 6. 128-byte row pitch for the gathered hidden-wide operands (W1, dZ1), default library and the all-switches variant
+TGCN_ROW_ALIGN=1 timeout 300 python -m pytest tests/test_gpu_train.py -x -q -m gpu > gpurun_out/r02_pytest_rowalign.log 2>&1
+echo "pytest rowalign rc=$?" | tee -a gpurun_out/r02_status.txt
+TGCN_ROW_ALIGN=1 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02_bench_rowalign.json 2> gpurun_out/r02_bench_rowalign.err
+echo "bench rowalign rc=$?" | tee -a gpurun_out/r02_status.txt
+TGCN_ROW_ALIGN=1 TGCN_SPMM_CVPACK=1 TGCN_B200_LIB=$PWD/pytextgcn_b200/lib/libtextgcn_b200_all.so timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline \
+  > gpurun_out/r02_bench_all_rowalign.json 2> gpurun_out/r02_bench_all_rowalign.err
+echo "bench all+rowalign rc=$?" | tee -a gpurun_out/r02_status.txt
 cat gpurun_out/r02_status.txt
 tail -3 gpurun_out/r02_pytest_default.log gpurun_out/r02_pytest_staged.log
 cat gpurun_out/r02_ab_spmm_20ng.jsonl
