@@ -94,9 +94,12 @@ class TextGCNTrainer:
         self.keep_w1_grad = bool(keep_w1_grad)
         self.XW = torch.zeros((n, H), **f32) if self.feat.Fdoc is not None else None
         self.H1d = torch.empty((n, H), **f32)
-        self.P = torch.zeros((n, Cp), **f32)
+        # TGCN_ROW_ALIGN=2 also gives the gathered class-wide operands (P, dZ2; Q, T of the collapsed eval) a 128-byte
+        # pitch: an 80-byte row then sits in one line instead of straddling two half of the time
+        cpitch = (Cp + 31) // 32 * 32 if ROW_ALIGN >= 2 else Cp
+        self.P = torch.zeros((n, cpitch), **f32)[:, :Cp]
         self.Z2 = torch.zeros((n, Cp), **f32)
-        self.dZ2 = torch.zeros((n, Cp), **f32)
+        self.dZ2 = torch.zeros((n, cpitch), **f32)[:, :Cp]
         self.G2 = torch.zeros((n, Cp), **f32)
         self.dZ1 = torch.zeros((n, self.row_pitch), **f32)[:, :H]
         self.loss_train = torch.zeros(2, **f32)
@@ -109,8 +112,8 @@ class TextGCNTrainer:
         self._nll_ws = torch.empty(2 * ((n * 4 + 255) // 256 * 256) + 4096, dtype=torch.uint8, device=dev)
         self._db_ws = None
         self.logits = self.Z2[:, :self.C]
-        self.Q = torch.zeros((n, Cp), **f32)          # collapsed eval: X W1 W2
-        self.T = torch.zeros((n, Cp), **f32)          # collapsed eval: A_hat Q + 1 (b1^T W2)
+        self.Q = torch.zeros((n, cpitch), **f32)[:, :Cp]          # collapsed eval: X W1 W2
+        self.T = torch.zeros((n, cpitch), **f32)[:, :Cp]          # collapsed eval: A_hat Q + 1 (b1^T W2)
         self.c_row = torch.zeros((1, Cp), **f32)
         self.eval_mode = "layered"
         self.set_masks(g.y, g.train_mask, getattr(g, "val_mask", None))

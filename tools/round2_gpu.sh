@@ -44,7 +44,7 @@ TGCN_ROW_ALIGN=1 timeout 300 python -m pytest tests/test_gpu_train.py -x -q -m g
 echo "pytest rowalign rc=$?" | tee -a gpurun_out/r02_status.txt
 TGCN_ROW_ALIGN=1 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02_bench_rowalign.json 2> gpurun_out/r02_bench_rowalign.err
 echo "bench rowalign rc=$?" | tee -a gpurun_out/r02_status.txt
-TGCN_ROW_ALIGN=1 TGCN_SPMM_CVPACK=1 TGCN_B200_LIB=$PWD/pytextgcn_b200/lib/libtextgcn_b200_all.so timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline \
+TGCN_ROW_ALIGN=2 TGCN_SPMM_CVPACK=1 TGCN_B200_LIB=$PWD/pytextgcn_b200/lib/libtextgcn_b200_all.so timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline \
   > gpurun_out/r02_bench_all_rowalign.json 2> gpurun_out/r02_bench_all_rowalign.err
 echo "bench all+rowalign rc=$?" | tee -a gpurun_out/r02_status.txt
 cat gpurun_out/r02_status.txt
