@@ -122,7 +122,10 @@ class GraphCSR:
         """The CSR entries once more as interleaved pairs {colidx[k], bits of val[k]} (int32 [nnz, 2]) for library
         builds that read one 8-byte pair per non-zero (TGCN_SPMM_CVPACK); built on first use."""
         if self._colval is None:
-            self._colval = torch.stack([self.colidx, self.val.view(torch.int32)], dim=1).contiguous()
+            cv = torch.zeros((self.nnz + 256, 2), dtype=torch.int32, device=self.device)   # tail: the kernel prefetches ahead
+            cv[:self.nnz, 0] = self.colidx
+            cv[:self.nnz, 1] = self.val.view(torch.int32)
+            self._colval = cv
         return self._colval
 
     def staged_plan(self, plan: SpmmPlan, warps_per_panel: int, rows_per_warp: int, tile_cols: int):
