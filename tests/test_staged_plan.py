@@ -81,3 +81,29 @@ def test_empty_and_degenerate_plans():
         build_staged_plan(colidx, val, chunks, 4, rows_per_warp=3)
     with pytest.raises(ValueError):
         build_staged_plan(colidx, val, chunks, 4, tile_cols=129)
+
+
+def test_plan_property_random_csr():
+    """Random CSRs (empty rows, duplicate columns, hub rows) x random plan shapes: the kernel's walk over the
+    plan always reproduces the row sums."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 60), st.integers(0, 10 ** 6), st.integers(1, 31), st.sampled_from([1, 2]),
+           st.integers(1, 128), st.sampled_from([32, 33, 64, 500]))
+    def check(n_rows, n_cols, seed, W, RPW, KC, chunk_nnz):
+        rng = np.random.default_rng(seed)
+        lens = rng.integers(0, 6, size=n_rows)
+        lens[rng.integers(0, n_rows)] = rng.integers(0, 300)         # one hub row, possibly split
+        rowptr = torch.zeros(n_rows + 1, dtype=torch.int32)
+        rowptr[1:] = torch.from_numpy(np.cumsum(lens)).to(torch.int32)
+        nnz = int(rowptr[-1])
+        colidx = torch.from_numpy(rng.integers(0, n_cols, size=nnz)).to(torch.int32)     # duplicates allowed
+        val = torch.from_numpy(rng.standard_normal(nnz).astype(np.float32))
+        chunks, _ = chunk_list(rowptr, chunk_nnz)
+        plan = build_staged_plan(colidx, val, chunks, n_cols, warps_per_panel=W, rows_per_warp=RPW, tile_cols=KC)
+        B = torch.from_numpy(rng.standard_normal((n_cols, 4)).astype(np.float32))
+        got = rows_from_chunks(emulate(plan, B), chunks, n_rows)
+        ref = _dense_ref(rowptr, colidx, val, B)
+        assert float((got - ref).abs().max()) <= 1e-9 * max(1.0, float(ref.abs().max()))
+    check()
