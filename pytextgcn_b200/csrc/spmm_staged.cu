@@ -244,9 +244,12 @@ __global__ void __launch_bounds__(1024, 1) k_spmm_staged(const SpmmParams p, con
 
 template <int VPL, int RPW, int EPI, int PROD>
 static int launch_staged_t(const SpmmParams& p, StagedParams sp, cudaStream_t stream) {
-  int dev = 0, max_optin = 0;
-  TGCN_CUDA(cudaGetDevice(&dev));
-  TGCN_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  static int max_optin = 0;                               // same for every device of a B200 box
+  if (max_optin == 0) {
+    int dev = 0;
+    TGCN_CUDA(cudaGetDevice(&dev));
+    TGCN_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
   sp.row_bytes = (uint32_t)p.F * 4u;
   sp.stage_bytes = (uint32_t)sp.tile_cols * sp.row_bytes;
   const size_t bar_bytes = 2 * 8 * 8;                      // full[] + empty[], up to 8 stages
