@@ -20,6 +20,9 @@
 #ifndef TGCN_SPMM_CVPACK
 #define TGCN_SPMM_CVPACK 0      // (col, val) read as one broadcast 8-byte load per non-zero instead of two shuffles
 #endif
+#ifndef TGCN_SPMM_NOALLOC
+#define TGCN_SPMM_NOALLOC 0     // fp32 gathers with L1::no_allocate (not part of variant-all: an independent A/B)
+#endif
 
 namespace tgcn {
 
@@ -52,7 +55,12 @@ template <typename TB> struct Vec;
 template <> struct Vec<float> {
   static constexpr int E = 4;
   __device__ __forceinline__ static void load(const float* p, float (&x)[4]) {
+#if TGCN_SPMM_NOALLOC
+    float4 v;   // gathered rows stream through L1 without taking a line (the 11 % L1 hits do not relieve the data pipe)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#else
     float4 v = __ldg(reinterpret_cast<const float4*>(p));
+#endif
     x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
   }
 };

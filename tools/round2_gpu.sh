@@ -30,7 +30,7 @@ fi
 #    broadcast 8-byte load instead of two shuffles (the L1 data pipe is the saturated unit); all switches incl. exact
 #    lanes-per-row for class-wide operands (3.2 instead of 6.4 instructions per non-zero in the narrow loop):
 #    parity tests against the oracle with the variant library loaded, then the same bench
-for v in addr32 cvpack all; do
+for v in addr32 cvpack noalloc all; do
   make -C pytextgcn_b200/csrc variant-$v > gpurun_out/r02_build_$v.log 2>&1 || { echo "build $v failed" | tee -a gpurun_out/r02_status.txt; continue; }
   export TGCN_B200_LIB=$PWD/pytextgcn_b200/lib/libtextgcn_b200_$v.so TGCN_SPMM_CVPACK=1
   timeout 420 python -m pytest tests/test_gpu_spmm.py tests/test_gpu_model.py tests/test_gpu_train.py -x -q -m gpu > gpurun_out/r02_pytest_$v.log 2>&1
