@@ -418,7 +418,10 @@ def run_own_arm(args):
                   "graph_upload_ms": upload_ms, "graph_upload_h2d_bytes": int(ei_host.numel() * 8 + ea_host.numel() * 4),
                   "nnz": graph.nnz, "symmetric": bool(sym), "last_epoch": {"loss": last[0], "acc_train": last[1], "acc_val": last[2]},
                   "kernels_per_epoch": launches_eager_epoch, "lib_launch_counter_delta": int(l1 - l0),
-                  "cuda_graph": True},
+                  "cuda_graph": True,
+                  "switches": {"spmm_staged": int(ops.STAGED), "staged_cfg": dict(ops.STAGED_CFG) if ops.STAGED else None,
+                               "cvpack": int(ops.CVPACK), "row_align": int(os.environ.get("TGCN_ROW_ALIGN", "0")),
+                               "library": os.path.basename(os.environ.get("TGCN_B200_LIB", "") or "libtextgcn_b200.so")}},
     }
     print(json.dumps(line), flush=True)
 
