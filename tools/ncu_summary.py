@@ -26,6 +26,10 @@ WANT = {
     "lts__t_sectors_srcunit_tex_op_read.sum": "l2_to_l1_read_sectors",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": "l1_global_load_sectors",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "shared_wavefronts",
+    "l1tex__data_pipe_lsu_wavefronts.avg": "data_pipe_wavefronts_per_sm",
+    "l1tex__data_pipe_lsu_wavefronts_mem_lgds.avg": "data_pipe_wavefronts_global_per_sm",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg": "data_pipe_wavefronts_shared_per_sm",
+    "l1tex__m_xbar2l1tex_read_bytes.sum": "l2_to_l1_fill_bytes",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "shared_bank_conflicts",
     "sm__inst_executed.sum": "warp_instructions",
     "sm__cycles_elapsed.max": "elapsed_cycles",
