@@ -91,7 +91,7 @@ int tgcn_csr_from_coo_gcn_norm(const int64_t* edge_src, const int64_t* edge_dst,
 int tgcn_spmm_plan(const int32_t* rowptr, int64_t row_begin, int64_t row_end, int32_t chunk_nnz,
                    int32_t* chunks /* [cap][4] */, int64_t chunk_capacity,
                    int32_t* split_rows /* [cap][3] = {row, first_slot, n_slots} */,
-                   int32_t* slot_owner /* optional [n_slots]: split-row index owning each scratch slot */,
+                   int32_t* slot_owner /* [n_slots]: split-row index owning each scratch slot */,
                    int32_t* counts_out, void* workspace, size_t workspace_bytes, void* stream);
 int tgcn_spmm_plan_workspace_bytes(int64_t n_rows, size_t* bytes_out);
 
@@ -111,8 +111,10 @@ typedef struct {
   const int32_t* rowptr; const int32_t* colidx; const float* val;   /* CSR of A_hat */
   const int32_t* chunks; int32_t n_chunks;                           /* plan */
   const int32_t* split_rows; int32_t n_split_rows;
-  const int32_t* slot_owner;    /* from tgcn_spmm_plan; with split_counters: the last-arriving chunk of a split row */
-  int32_t* split_counters;      /* reduces it inside the kernel (int32[n_split_rows], zero once; self-resetting) */
+  const int32_t* slot_owner;    /* from tgcn_spmm_plan: split-row index owning each scratch slot */
+  int32_t* split_counters;      /* int32[n_split_rows], zero once, self-resetting: the last-arriving chunk of a split
+                                   row adds the partial rows in slot order inside the kernel (required when
+                                   n_split_rows > 0) */
   float* scratch;                                                    /* partial rows */
   const void* B; int64_t ldb; int32_t b_dtype;
   void* C; int64_t ldc; int32_t c_dtype;                             /* may be NULL if only P wanted */
@@ -131,44 +133,8 @@ typedef struct {
    * adam_param_mirror_mc: multicast mapping of the parameter (row-partitioned mode) or NULL. */
   float* adam_param; float* adam_exp_avg; float* adam_exp_avg_sq; float* adam_max_exp_avg_sq; int64_t adam_ld;
   const float* adam_hyper_dev; float adam_beta1; float adam_beta2; float adam_eps; void* adam_param_mirror_mc;
-  /* optional: the CSR entries again as interleaved pairs {colidx[k], bits of val[k]} (int32[nnz][2]).  Only read by
-   * library builds made with TGCN_SPMM_CVPACK (one broadcast 8-byte load per non-zero instead of two shuffles);
-   * NULL otherwise. */
-  const int32_t* colval;
 } tgcn_spmm_args;
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
-
-/* (2b) The same operation with the gathered operand rows staged in shared memory (csrc/spmm_staged.cu):
- * one CTA per PANEL of consecutive chunks of the (length-sorted) chunk list walks the sorted union of
- * the columns its chunks touch, tile by tile; a producer warp copies the operand rows of a tile from
- * L2 into a ring of shared-memory stages (cp.async.bulk + mbarrier), consumer warps accumulate from
- * shared memory.  A row needed by k chunks of a panel crosses L2->SM once instead of k times.
- * `args` is the tgcn_spmm argument block (rowptr/colidx/val unused; fp32 B, F % 4 == 0, F <= 256, no
- * fused projection; split rows need slot_owner + split_counters).  The plan is built once per
- * (chunk list, warps_per_panel, rows_per_warp, tile_cols) by the host (pytextgcn_b200/staged_plan.py):
- *   panel p = chunks [p*R, (p+1)*R), R = warps_per_panel*rows_per_warp; consumer warp w owns chunks
- *             (p*warps_per_panel + w)*rows_per_warp + {0..rows_per_warp-1};
- *   ucols[panel_ucol_ptr[p] .. panel_ucol_ptr[p+1]) = ascending distinct column ids of panel p; tile t
- *             holds entries [t*tile_cols, (t+1)*tile_cols) of that range;
- *   stream  = int32 pairs; warp_stream_ptr[p*warps_per_panel + w] = first pair of that warp.  For every
- *             tile of the panel: a header {n0, n1} (entries of the warp's first / second chunk in the
- *             tile) followed by n0 + n1 entries {slot within the tile, fp32 value bits}.  The array is
- *             padded by 64 pairs.
- * Experimental in round 1 (no B200 time was left to measure it): selected with TGCN_SPMM_STAGED=1. */
-typedef struct {
-  const int32_t* panel_ucol_ptr;   /* [n_panels + 1] */
-  const int32_t* ucols;            /* [panel_ucol_ptr[n_panels]] */
-  const int64_t* warp_stream_ptr;  /* [n_panels * warps_per_panel] */
-  const int32_t* stream;           /* [stream_len + 64][2] */
-  int32_t n_panels;
-  int32_t warps_per_panel;         /* consumer warps per CTA; warps_per_panel + n_producers <= 32 */
-  int32_t rows_per_warp;           /* 1 or 2 */
-  int32_t tile_cols;               /* operand rows per shared-memory stage, 1..128 */
-  /* launch shape (not part of the plan data): producer warps 1..4 and how they copy an operand row */
-  int32_t n_producers;
-  int32_t producer_mode;           /* 0 = one cp.async.bulk per row (TMA unit), 1 = 16-byte cp.async by all lanes */
-} tgcn_staged_plan;
-int tgcn_spmm_staged(const tgcn_spmm_args* args, const tgcn_staged_plan* plan, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (3) Masked log-softmax / NLL and its gradient, one pass over the logits.
@@ -215,6 +181,15 @@ int tgcn_dense_bwd_workspace_bytes(int32_t H, int32_t C, size_t* bytes_out);
  * hidden->classes layer when it is not fused into the producing SpMM. */
 int tgcn_project(const void* X, int64_t ldx, int32_t x_dtype, int64_t n_rows, int32_t K,
                  const float* W, int32_t M, float* P, int64_t ldp, void* P_mirror_mc, void* stream);
+
+/* Y = dropout(X) with exactly the keep decision of the tgcn_spmm epilogue (same mode / seed / offset / element index
+ * (row + philox_row_offset) * F + col).  Used to reuse the pre-dropout hidden activation A_hat (X W1) + b1 of an eval
+ * forward as the training forward of the next epoch: W1/b1 do not change in between (flat_amazon.py:100-110) and
+ * F.dropout follows the product (models.py:20-23), so the result is bit-identical to recomputing the propagation. */
+int tgcn_dropout_apply(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n_rows, int32_t F,
+                       int32_t drop_mode, float drop_p, const uint8_t* keep_mask, int64_t ldmask,
+                       uint64_t philox_seed, uint64_t philox_offset, const int64_t* philox_offset_dev,
+                       int64_t philox_row_offset, void* stream);
 
 /* Hierarchy-feature prologue/epilogue for X = [I | F] (text2graph.py:237-241;
  * perlevel_dbpedia.py:140-141):  XW[r,:] = W1[r,:] (+ F[r-n_vocab,:] @ W1[N:, :] on doc rows);

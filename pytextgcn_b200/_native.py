@@ -37,16 +37,6 @@ class SpmmArgs(C.Structure):
         ("adam_param", c_void), ("adam_exp_avg", c_void), ("adam_exp_avg_sq", c_void), ("adam_max_exp_avg_sq", c_void),
         ("adam_ld", C.c_int64), ("adam_hyper_dev", c_void), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float),
         ("adam_eps", C.c_float), ("adam_param_mirror_mc", c_void),
-        ("colval", c_void),
-    ]
-
-
-class StagedPlanArgs(C.Structure):
-    """Mirror of tgcn_staged_plan."""
-    _fields_ = [
-        ("panel_ucol_ptr", c_void), ("ucols", c_void), ("warp_stream_ptr", c_void), ("stream", c_void),
-        ("n_panels", C.c_int32), ("warps_per_panel", C.c_int32), ("rows_per_warp", C.c_int32), ("tile_cols", C.c_int32),
-        ("n_producers", C.c_int32), ("producer_mode", C.c_int32),
     ]
 
 
@@ -82,7 +72,6 @@ SIGNATURES = {
                                  c_void, C.c_size_t, c_void]),
     "tgcn_spmm_plan_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "tgcn_spmm": (C.c_int, [C.POINTER(SpmmArgs), c_void]),
-    "tgcn_spmm_staged": (C.c_int, [C.POINTER(SpmmArgs), C.POINTER(StagedPlanArgs), c_void]),
     "tgcn_masked_nll": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int32, c_void, c_void, C.c_int64,
                                   c_void, c_void, c_void, C.c_int64, c_void, c_void, c_void,
                                   c_void, C.c_size_t, c_void]),
@@ -91,6 +80,8 @@ SIGNATURES = {
     "tgcn_dense_bwd_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "tgcn_project": (C.c_int, [c_void, C.c_int64, C.c_int32, C.c_int64, C.c_int32, c_void, C.c_int32,
                                c_void, C.c_int64, c_void, c_void]),
+    "tgcn_dropout_apply": (C.c_int, [c_void, C.c_int64, c_void, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float,
+                                     c_void, C.c_int64, C.c_uint64, C.c_uint64, c_void, C.c_int64, c_void]),
     "tgcn_hier_forward": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int64, c_void, C.c_int64, C.c_int32,
                                     C.c_int32, c_void, C.c_int64, c_void]),
     "tgcn_hier_backward": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int64, c_void, C.c_int64, C.c_int32,

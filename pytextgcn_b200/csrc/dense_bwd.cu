@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
   float dbh[KQ][4];
 #pragma unroll
   for (int k = 0; k < KQ; ++k) dbh[k][0] = dbh[k][1] = dbh[k][2] = dbh[k][3] = 0.0f;
-  float dbo = 0.0f;   // thread c < C accumulates db_out[c]
+  constexpr int DBO_MAX = 2;   // thread t accumulates db_out[t + k*DB_THREADS], k < DBO_MAX (host checks C <= 512)
+  float dbo[DBO_MAX] = {0.0f, 0.0f};
   const uint64_t ph_off = p.philox_offset + (p.philox_offset_dev ? (uint64_t)__ldg(p.philox_offset_dev) : 0ull);
   __syncthreads();
 
@@ -109,9 +110,15 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
     }
     __syncthreads();
 
-    if (do_rows && p.dZ2 && tid < C) {
+    if (do_rows && p.dZ2) {
+#pragma unroll
+      for (int k = 0; k < DBO_MAX; ++k) {
+        const int c = tid + k * DB_THREADS;
+        if (c < C) {
 #pragma unroll 8
-      for (int r = 0; r < DB_ROWS; ++r) dbo += dZs[r * Cp + tid];
+          for (int r = 0; r < DB_ROWS; ++r) dbo[k] += dZs[r * Cp + c];
+        }
+      }
     }
 
     // ---- dW2 += Hs^T G2s  (4x4 register blocks) ----
@@ -296,7 +303,9 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
       for (int w = 0; w < DB_THREADS / 32; ++w) s += red[w * H + h];
       p.part_dbh[(int64_t)blockIdx.x * H + h] = s;
     }
-    if (tid < C) p.part_dbo[(int64_t)blockIdx.x * C + tid] = dbo;
+#pragma unroll
+    for (int k = 0; k < DBO_MAX; ++k)
+      if (tid + k * DB_THREADS < C) p.part_dbo[(int64_t)blockIdx.x * C + tid + k * DB_THREADS] = dbo[k];
   }
 }
 
@@ -390,6 +399,7 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
   TGCN_CHECK_ARG(a->dW2 != nullptr, "dense_bwd: dW2 null");
   TGCN_CHECK_ARG(a->n_rows > 0 && a->H > 0 && a->C > 0, "dense_bwd: bad shape");
   TGCN_CHECK_ARG(a->H <= 512, "dense_bwd: hidden width %d > 512 not supported", a->H);
+  TGCN_CHECK_ARG(a->C <= 512, "dense_bwd: %d classes > 512 not supported", a->C);
   TGCN_CHECK_ARG(a->ldg2 >= a->C && a->ldh >= a->H, "dense_bwd: leading dimension too small");
   TGCN_CHECK_ARG(a->dZ1 == nullptr || a->lddz1 >= a->H, "dense_bwd: lddz1 < H");
   TGCN_CHECK_ARG(a->drop_mode != TGCN_DROP_MASK || a->act == TGCN_ACT_RELU || a->keep_mask || a->drop_p == 0.0f,

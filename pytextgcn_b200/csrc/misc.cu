@@ -196,6 +196,35 @@ __global__ void __launch_bounds__(256) k_hier_backward(const float* __restrict__
   }
 }
 
+// Y = dropout(X): the SpMM epilogue's dropout step as a stand-alone pass (same keep decision per element: keep-mask
+// byte, or Philox keyed by (seed, offset, global row * F + col)).  Lets a pre-dropout activation computed once
+// (eval forward of epoch k) serve the training forward of epoch k+1, whose A_hat (X W1) + b1 is identical because
+// W1/b1 do not change in between (flat_amazon.py:100-110; dropout comes after the product, models.py:20-23).
+__global__ void __launch_bounds__(256) k_dropout_apply(const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
+                                                       int64_t n_rows, int F, int drop_mode, float drop_p, float scale,
+                                                       const uint8_t* __restrict__ keep, int64_t ldmask, uint64_t seed,
+                                                       uint64_t offset, const int64_t* __restrict__ offset_dev, int64_t row_offset) {
+  const int FQ = F >> 2;
+  const int64_t total = n_rows * FQ;
+  const uint64_t ph_off = offset + (offset_dev ? (uint64_t)__ldg(offset_dev) : 0ull);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / FQ;
+    const int c0 = (int)(i - row * FQ) << 2;
+    float4 v = __ldg(reinterpret_cast<const float4*>(X + row * ldx + c0));
+    if (drop_mode == TGCN_DROP_MASK) {
+      const uint8_t* m = keep + row * ldmask + c0;
+      v.x = m[0] ? v.x * scale : 0.0f; v.y = m[1] ? v.y * scale : 0.0f;
+      v.z = m[2] ? v.z * scale : 0.0f; v.w = m[3] ? v.w * scale : 0.0f;
+    } else if (drop_mode == TGCN_DROP_PHILOX) {
+      const uint64_t e4 = ((uint64_t)(row + row_offset) * (uint64_t)F + (uint64_t)c0) >> 2;
+      const uint4 r = philox_quad(e4, seed, ph_off);
+      v.x = (u01(r.x) >= drop_p) ? v.x * scale : 0.0f; v.y = (u01(r.y) >= drop_p) ? v.y * scale : 0.0f;
+      v.z = (u01(r.z) >= drop_p) ? v.z * scale : 0.0f; v.w = (u01(r.w) >= drop_p) ? v.w * scale : 0.0f;
+    }
+    *reinterpret_cast<float4*>(Y + row * ldy + c0) = v;
+  }
+}
+
 __global__ void k_reduce_parts(const float* __restrict__ part, int n_parts, int64_t n, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -285,6 +314,27 @@ extern "C" int tgcn_cast_f32_to_bf16(const float* src, void* dst, int64_t n, voi
   const int T = 256;
   const int64_t blocks = std::min<int64_t>(cdiv(n, T), (int64_t)sm_count() * 16);
   k_cast_bf16<<<(unsigned)blocks, T, 0, (cudaStream_t)stream_>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_dropout_apply(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n_rows, int32_t F,
+                                  int32_t drop_mode, float drop_p, const uint8_t* keep_mask, int64_t ldmask,
+                                  uint64_t philox_seed, uint64_t philox_offset, const int64_t* philox_offset_dev,
+                                  int64_t philox_row_offset, void* stream_) {
+  TGCN_CHECK_ARG(X && Y && n_rows >= 0 && F > 0, "dropout_apply: bad arguments");
+  TGCN_CHECK_ARG(F % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= F && ldy >= F && (((uintptr_t)X | (uintptr_t)Y) & 15) == 0,
+                 "dropout_apply: F and the row pitches must be multiples of 4 floats, the buffers 16-byte aligned");
+  TGCN_CHECK_ARG(drop_mode >= TGCN_DROP_NONE && drop_mode <= TGCN_DROP_PHILOX, "dropout_apply: bad drop_mode");
+  TGCN_CHECK_ARG(drop_mode == TGCN_DROP_NONE || (drop_p >= 0.0f && drop_p < 1.0f), "dropout_apply: p must be in [0,1)");
+  TGCN_CHECK_ARG(drop_mode != TGCN_DROP_MASK || keep_mask, "dropout_apply: TGCN_DROP_MASK needs keep_mask");
+  if (n_rows == 0) return TGCN_OK;
+  const int mode = (drop_mode != TGCN_DROP_NONE && drop_p > 0.0f) ? drop_mode : TGCN_DROP_NONE;
+  const int T = 256;
+  const int64_t blocks = std::min<int64_t>(cdiv(n_rows * (F / 4), T), (int64_t)sm_count() * 16);
+  k_dropout_apply<<<(unsigned)blocks, T, 0, (cudaStream_t)stream_>>>(X, ldx, Y, ldy, n_rows, F, mode, drop_p, 1.0f / (1.0f - drop_p),
+                                                                     keep_mask, ldmask, philox_seed, philox_offset, philox_offset_dev,
+                                                                     philox_row_offset);
   TGCN_LAUNCH_CHECK();
   return TGCN_OK;
 }

@@ -10,12 +10,14 @@
 // LPR lanes cover one gathered B row with 16-byte vector loads (VPL vectors per lane) and
 // 32/LPR non-zeros are processed side by side; the (col,val) stream is loaded coalesced, 32
 // entries per warp load, and broadcast by shuffle.  Split rows write fp32 partial rows to a
-// scratch buffer and a fix-up kernel adds them in slot order: deterministic, no atomics.
+// scratch buffer and the chunk that arrives last adds them in slot order: deterministic, no
+// floating-point atomics.
 #include "spmm_common.cuh"
 
-// Build variants for A/B runs (switches in spmm_common.cuh; `make variant-addr32|exactlpr|cvpack|all` writes
-// lib/libtextgcn_b200_<name>.so, selected with TGCN_B200_LIB).  The shipped build keeps every switch off: its SASS is
-// the one the round-1 numbers were measured with.
+// Measured alternatives that were removed (profiles/r02_ab_variants.json, 20NG-shape, B200): (col,val) as one 8-byte
+// broadcast load instead of two shuffles (+6 %), L1::no_allocate gathers (+36 %), exact lanes-per-row for class-wide
+// rows (+1 %), 128-byte row pitch (-2.6 %), shared-memory staged panels fed by per-row cp.async.bulk (2.5-4x slower:
+// ~46 clk per 800-byte bulk copy per SM).  Kept: 32-bit row-pitch arithmetic in the gather loop (-4.4 %).
 
 namespace tgcn {
 
@@ -43,9 +45,7 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
   const int l = lane % LPR;
   const TB* __restrict__ B = reinterpret_cast<const TB*>(p.B);
   const int F = p.F;
-#if TGCN_SPMM_ADDR32
-  const uint32_t ldb_bytes = (uint32_t)(p.ldb * (int64_t)sizeof(TB));
-#endif
+  const uint32_t ldb_bytes = (uint32_t)(p.ldb * (int64_t)sizeof(TB));   // host checks the pitch fits 32 bits
   bool active[VPL];
 #pragma unroll
   for (int v = 0; v < VPL; ++v) active[v] = ((l + v * LPR) * E) < F;
@@ -63,48 +63,6 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
 #pragma unroll
     for (int i = 0; i < E; ++i) acc[v][i] = 0.0f;
 
-#if TGCN_SPMM_CVPACK
-  if (p.cv != nullptr) {
-    // (col, val) of a non-zero as ONE 8-byte load with the same address in every lane of its group (a broadcast:
-    // one L1 wavefront per warp request) instead of two shuffles (two wavefronts of the same data pipe, which is
-    // the unit this kernel saturates: ncu l1tex__data_pipe_lsu_wavefronts, profiles/dominant_kernel.json)
-    for (int base = ch.y; base < ch.z; base += NZP * U) {
-      if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.cv + base + 2 * NZP * U));
-      int cc[U]; float vv[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int k = base + u * NZP + sub;
-        int2 e = make_int2(0, 0);
-        if (k < ch.z && (32 % LPR == 0 || sub < NZP)) e = __ldg(p.cv + k);
-        cc[u] = e.x; vv[u] = __int_as_float(e.y);
-      }
-      float x[U][VPL][E];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-#if TGCN_SPMM_ADDR32
-        const TB* brow = reinterpret_cast<const TB*>(reinterpret_cast<const char*>(B) +
-                                                     (uint64_t)(uint32_t)cc[u] * (uint64_t)ldb_bytes);
-#else
-        const TB* brow = B + (int64_t)cc[u] * p.ldb;
-#endif
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          if (active[v] && vv[u] != 0.0f) Vec<TB>::load(brow + (l + v * LPR) * E, x[u][v]);
-          else {
-#pragma unroll
-            for (int i = 0; i < E; ++i) x[u][v][i] = 0.0f;
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int v = 0; v < VPL; ++v)
-#pragma unroll
-          for (int i = 0; i < E; ++i) acc[v][i] = fmaf(vv[u], x[u][v][i], acc[v][i]);
-    }
-  } else
-#endif
   for (int base = ch.y; base < ch.z; base += 32) {
     const int k = base + lane;
     int mc = 0; float mv = 0.0f;
@@ -119,18 +77,13 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
         cc[u] = __shfl_sync(0xffffffffu, mc, srcl & 31);
         vv[u] = __shfl_sync(0xffffffffu, mv, srcl & 31);
         if (srcl >= cnt) vv[u] = 0.0f;
-        if constexpr (32 % LPR != 0) { if (sub >= NZP) vv[u] = 0.0f; }   // lanes past the last whole group idle
       }
       float x[U][VPL][E];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-#if TGCN_SPMM_ADDR32
-        // one IMAD.WIDE.U32 per gather: lane base + column * row pitch in bytes (host checks it fits 32 bits)
+        // one IMAD.WIDE.U32 per gather: lane base + column * row pitch in bytes
         const TB* brow = reinterpret_cast<const TB*>(reinterpret_cast<const char*>(B) +
                                                      (uint64_t)(uint32_t)cc[u] * (uint64_t)ldb_bytes);
-#else
-        const TB* brow = B + (int64_t)cc[u] * p.ldb;
-#endif
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
           if (active[v] && vv[u] != 0.0f) Vec<TB>::load(brow + (l + v * LPR) * E, x[u][v]);
@@ -149,29 +102,13 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
     }
   }
   // fold the NZP side-by-side partial rows into lanes [0, LPR)
-  if constexpr ((LPR & (LPR - 1)) == 0) {
 #pragma unroll
-    for (int o = 16; o >= LPR; o >>= 1)
-#pragma unroll
-      for (int v = 0; v < VPL; ++v)
-#pragma unroll
-        for (int i = 0; i < E; ++i) acc[v][i] += __shfl_down_sync(0xffffffffu, acc[v][i], o);
-  } else {
-    // LPR not a power of two (TGCN_SPMM_EXACTLPR): group g of lane l sits at lane l + g*LPR
+  for (int o = 16; o >= LPR; o >>= 1)
 #pragma unroll
     for (int v = 0; v < VPL; ++v)
 #pragma unroll
-      for (int i = 0; i < E; ++i) {
-        const float mine = acc[v][i];
-        float sum = mine;
-#pragma unroll
-        for (int g = 1; g < NZP; ++g) sum += __shfl_sync(0xffffffffu, mine, (lane + g * LPR) & 31);
-        acc[v][i] = sum;
-      }
-  }
+      for (int i = 0; i < E; ++i) acc[v][i] += __shfl_down_sync(0xffffffffu, acc[v][i], o);
 
-  // (same steps as finish_row() in spmm_common.cuh, kept inline here: routing this kernel through the
-  // shared function changes ptxas' schedule of the gather loop above, which is tuned -- DESIGN.md 3)
   if (ch.w >= 0) {
     // split row: raw fp32 partial into the scratch slot of this chunk
     if (lane < LPR) {
@@ -186,12 +123,12 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
         }
       }
     }
-    if (p.split_counters == nullptr) return;          // reduced by k_spmm_fixup afterwards
     // The chunk that arrives LAST adds the partial rows in slot order (the order is fixed, so the
     // result does not depend on which chunk that is) and runs the epilogue: no second kernel.
     const int sr = __ldg(p.slot_owner + ch.w);
     const int first = __ldg(p.split_rows + 3 * sr + 1), n = __ldg(p.split_rows + 3 * sr + 2);
     __threadfence();
+    __syncwarp();                                     // every lane's partial is fenced before lane 0 publishes the arrival
     int arrived = 0;
     if (lane == 0) arrived = atomicAdd(p.split_counters + sr, 1);
     arrived = __shfl_sync(0xffffffffu, arrived, 0);
@@ -221,50 +158,6 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
   }
   row_epilogue<LPR, VPL, E, EPI>(p, ch.x, lane, acc, smem_w);
   }
-}
-
-// one warp per split row: add its partial rows in slot order, then the same epilogue
-template <int LPR, int VPL, int E, int EPI>
-__global__ void __launch_bounds__(256) k_spmm_fixup(const SpmmParams p) {
-  extern __shared__ __align__(16) float smem[];
-  const int warps_per_block = blockDim.x >> 5;
-  const int wib = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  float* smem_w = smem;                                   // [F][pad4(n_proj)] (+32 floats slack) when staged
-  if (EPI == EPI_PROJ && p.wproj_in_smem) {
-    const int Ms = (p.n_proj + 3) & ~3;
-    for (int i = threadIdx.x; i < p.F * Ms + 32; i += blockDim.x) {
-      const int c = i / Ms, m = i - c * Ms;
-      smem_w[i] = (c < p.F && m < p.n_proj) ? p.W_proj[c * p.n_proj + m] : 0.0f;
-    }
-    __syncthreads();
-  }
-  const int sr = blockIdx.x * warps_per_block + wib;
-  if (sr >= p.n_split_rows) return;
-  const int row = p.split_rows[3 * sr], first = p.split_rows[3 * sr + 1], n = p.split_rows[3 * sr + 2];
-  const int F = p.F;
-  float acc[VPL][E];
-#pragma unroll
-  for (int v = 0; v < VPL; ++v)
-#pragma unroll
-    for (int i = 0; i < E; ++i) acc[v][i] = 0.0f;
-  if (lane < LPR) {
-    for (int s = 0; s < n; ++s) {
-      const float* src = p.scratch + (int64_t)(first + s) * F;
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const int c0 = (lane + v * LPR) * E;
-        if (c0 < F) {
-#pragma unroll
-          for (int q = 0; q < E / 4; ++q) {
-            float4 t = *reinterpret_cast<const float4*>(src + c0 + 4 * q);
-            acc[v][4 * q] += t.x; acc[v][4 * q + 1] += t.y; acc[v][4 * q + 2] += t.z; acc[v][4 * q + 3] += t.w;
-          }
-        }
-      }
-    }
-  }
-  row_epilogue<LPR, VPL, E, EPI>(p, row, lane, acc, smem_w);
 }
 
 // ---- spmm plan: chunk list ------------------------------------------------------------
@@ -338,21 +231,15 @@ __global__ void __launch_bounds__(1024) k_plan(const int32_t* __restrict__ rowpt
 
 template <typename TB, int LPR, int VPL, int EPI>
 static int launch_spmm_t(const SpmmParams& p, cudaStream_t stream) {
-  constexpr int E = Vec<TB>::E;
   const int threads = 256, wpb = threads / 32;
   size_t smem = 0;
   if (EPI == EPI_PROJ && p.wproj_in_smem) smem = ((size_t)p.F * ((p.n_proj + 3) & ~3) + 32) * sizeof(float);
   if (smem > 48 * 1024) {
     TGCN_CUDA(cudaFuncSetAttribute(k_spmm<TB, LPR, VPL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TGCN_CUDA(cudaFuncSetAttribute(k_spmm_fixup<LPR, VPL, E, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (p.n_chunks > 0) {
     const int64_t grid = cdiv(p.n_chunks, wpb);
     k_spmm<TB, LPR, VPL, EPI><<<(unsigned)grid, threads, smem, stream>>>(p);
-    TGCN_LAUNCH_CHECK();
-  }
-  if (p.n_split_rows > 0 && p.split_counters == nullptr) {
-    k_spmm_fixup<LPR, VPL, E, EPI><<<(unsigned)cdiv(p.n_split_rows, wpb), threads, smem, stream>>>(p);
     TGCN_LAUNCH_CHECK();
   }
   return TGCN_OK;
@@ -373,17 +260,6 @@ template <typename TB>
 static int dispatch_spmm(const SpmmParams& p, cudaStream_t stream) {
   constexpr int E = Vec<TB>::E;
   const int nvec = (p.F + E - 1) / E;   // 16-byte vectors per dense row
-#if TGCN_SPMM_EXACTLPR
-  // class-wide operands: as many lanes per non-zero as the row has 16-byte pieces (20 classes = 5 pieces:
-  // 6 non-zeros side by side instead of 4 with 3 of every 8 lanes idle)
-  if constexpr (std::is_same<TB, float>::value) {
-    if (nvec == 2) return launch_spmm<TB, 2, 1>(p, stream);
-    if (nvec == 3) return launch_spmm<TB, 3, 1>(p, stream);
-    if (nvec == 5) return launch_spmm<TB, 5, 1>(p, stream);
-    if (nvec == 6) return launch_spmm<TB, 6, 1>(p, stream);
-    if (nvec == 7) return launch_spmm<TB, 7, 1>(p, stream);
-  }
-#endif
   if (nvec <= 4) return launch_spmm<TB, 4, 1>(p, stream);
   if (nvec <= 8) return launch_spmm<TB, 8, 1>(p, stream);
   if (nvec <= 16) return launch_spmm<TB, 16, 1>(p, stream);
@@ -436,7 +312,8 @@ extern "C" int tgcn_spmm(const tgcn_spmm_args* a, void* stream_) {
     TGCN_CHECK_ARG(a->ldc % ec == 0 && ((uintptr_t)a->C % 16) == 0, "spmm: C must be 16-byte aligned with ldc %% %d == 0", ec);
     TGCN_CHECK_ARG(a->ldc >= a->F, "spmm: ldc < F");
   }
-  TGCN_CHECK_ARG(a->n_split_rows == 0 || (a->split_rows && a->scratch), "spmm: split rows need split_rows and scratch");
+  TGCN_CHECK_ARG(a->n_split_rows == 0 || (a->split_rows && a->scratch && a->slot_owner && a->split_counters),
+                 "spmm: split rows need split_rows, scratch, slot_owner and split_counters");
   TGCN_CHECK_ARG(a->drop_mode >= TGCN_DROP_NONE && a->drop_mode <= TGCN_DROP_PHILOX, "spmm: bad drop_mode");
   TGCN_CHECK_ARG(a->drop_mode == TGCN_DROP_NONE || (a->drop_p >= 0.0f && a->drop_p < 1.0f), "spmm: dropout p must be in [0,1)");
   TGCN_CHECK_ARG(a->drop_mode != TGCN_DROP_MASK || a->keep_mask, "spmm: TGCN_DROP_MASK needs keep_mask");
@@ -445,9 +322,7 @@ extern "C" int tgcn_spmm(const tgcn_spmm_args* a, void* stream_) {
 
   SpmmParams p;
   if (int rc = fill_spmm_params(a, &p)) return rc;
-#if TGCN_SPMM_ADDR32
-  TGCN_CHECK_ARG(a->ldb * (a->b_dtype == TGCN_F32 ? 4 : 2) < (int64_t)1 << 31, "spmm: row pitch too large for the 32-bit address variant");
-#endif
+  TGCN_CHECK_ARG(a->ldb * (a->b_dtype == TGCN_F32 ? 4 : 2) < (int64_t)1 << 31, "spmm: row pitch must fit 32 bits");
   if (a->b_dtype == TGCN_F32) return dispatch_spmm<float>(p, stream);
   return dispatch_spmm<__nv_bfloat16>(p, stream);
 }

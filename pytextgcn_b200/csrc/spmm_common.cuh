@@ -1,28 +1,7 @@
-// Shared pieces of the SpMM kernels (spmm.cu: warp-per-chunk gather kernel; spmm_staged.cu: the
-// panel kernel that stages gathered rows in shared memory): launch parameters, 16-byte operand
-// loads, the fused row epilogue and the split-row finish.
+// Pieces of the SpMM kernel (spmm.cu): launch parameters, 16-byte operand loads and the fused row epilogue.
 #pragma once
 #include "common.cuh"
 #include <type_traits>
-
-// Build-variant switches of the gather kernel (make variant-<name>; the shipped build has all of them off).
-#if defined(TGCN_SPMM_ALL) && TGCN_SPMM_ALL
-#define TGCN_SPMM_ADDR32 1
-#define TGCN_SPMM_EXACTLPR 1
-#define TGCN_SPMM_CVPACK 1
-#endif
-#ifndef TGCN_SPMM_ADDR32
-#define TGCN_SPMM_ADDR32 0      // 32-bit row-pitch arithmetic in the gather loop (one IMAD.WIDE per gather)
-#endif
-#ifndef TGCN_SPMM_EXACTLPR
-#define TGCN_SPMM_EXACTLPR 0    // lanes per gathered row = its number of 16-byte pieces, also when not a power of two
-#endif
-#ifndef TGCN_SPMM_CVPACK
-#define TGCN_SPMM_CVPACK 0      // (col, val) read as one broadcast 8-byte load per non-zero instead of two shuffles
-#endif
-#ifndef TGCN_SPMM_NOALLOC
-#define TGCN_SPMM_NOALLOC 0     // fp32 gathers with L1::no_allocate (not part of variant-all: an independent A/B)
-#endif
 
 namespace tgcn {
 
@@ -30,7 +9,7 @@ struct SpmmParams {
   const int32_t* __restrict__ rowptr; const int32_t* __restrict__ colidx; const float* __restrict__ val;
   const int4* __restrict__ chunks; int32_t n_chunks;
   const int32_t* __restrict__ split_rows; int32_t n_split_rows;
-  const int32_t* __restrict__ slot_owner; int32_t* split_counters;   // both set: the last chunk of a split row reduces it in-kernel
+  const int32_t* __restrict__ slot_owner; int32_t* split_counters;   // the last chunk of a split row reduces it in-kernel
   float* scratch;
   const void* __restrict__ B; int64_t ldb;
   void* C; int64_t ldc; int32_t c_dtype;
@@ -45,9 +24,6 @@ struct SpmmParams {
   // fused Adam/AMSGrad on the finished row (backward of layer 1 with X = I: the row IS dW1[row])
   float* ad_p; float* ad_m; float* ad_v; float* ad_x; int64_t ad_ld; const float* __restrict__ ad_hyp;
   float ad_b1, ad_b2, ad_eps; float* ad_mirror;
-#if TGCN_SPMM_CVPACK
-  const int2* __restrict__ cv;   // {colidx[k], bits of val[k]} pairs (build variant, see spmm.cu)
-#endif
 };
 
 // ---- loads of 16 bytes of the dense operand -> 4 (fp32) or 8 (bf16) floats ----
@@ -55,12 +31,7 @@ template <typename TB> struct Vec;
 template <> struct Vec<float> {
   static constexpr int E = 4;
   __device__ __forceinline__ static void load(const float* p, float (&x)[4]) {
-#if TGCN_SPMM_NOALLOC
-    float4 v;   // gathered rows stream through L1 without taking a line (the 11 % L1 hits do not relieve the data pipe)
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-#else
     float4 v = __ldg(reinterpret_cast<const float4*>(p));
-#endif
     x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
   }
 };
@@ -219,69 +190,12 @@ __device__ __forceinline__ void row_epilogue(const SpmmParams& p, int64_t row, i
   }
 }
 
-// Ends one chunk {row, begin, end, slot} whose partial sum sits in acc (lanes [0, LPR) own the row):
-// a whole row goes straight to the epilogue; a chunk of a split row stores its fp32 partial into its
-// scratch slot, and the chunk that arrives LAST adds the partial rows in slot order and runs the epilogue.
-template <int LPR, int VPL, int E, int EPI>
-__device__ __forceinline__ void finish_row(const SpmmParams& p, const int4 ch, int lane, float (&acc)[VPL][E],
-                                           const float* smem_w) {
-  const int F = p.F;
-  if (ch.w >= 0) {
-    // split row: raw fp32 partial into the scratch slot of this chunk
-    if (lane < LPR) {
-      float* s = p.scratch + (int64_t)ch.w * F;
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const int c0 = (lane + v * LPR) * E;
-        if (c0 < F) {
-#pragma unroll
-          for (int q = 0; q < E / 4; ++q)
-            *reinterpret_cast<float4*>(s + c0 + 4 * q) = make_float4(acc[v][4 * q], acc[v][4 * q + 1], acc[v][4 * q + 2], acc[v][4 * q + 3]);
-        }
-      }
-    }
-    if (p.split_counters == nullptr) return;          // reduced by k_spmm_fixup afterwards
-    // The chunk that arrives LAST adds the partial rows in slot order (the order is fixed, so the
-    // result does not depend on which chunk that is) and runs the epilogue: no second kernel.
-    const int sr = __ldg(p.slot_owner + ch.w);
-    const int first = __ldg(p.split_rows + 3 * sr + 1), n = __ldg(p.split_rows + 3 * sr + 2);
-    __threadfence();
-    int arrived = 0;
-    if (lane == 0) arrived = atomicAdd(p.split_counters + sr, 1);
-    arrived = __shfl_sync(0xffffffffu, arrived, 0);
-    if (arrived != n - 1) return;
-    __threadfence();
-    if (lane == 0) p.split_counters[sr] = 0;          // self-resetting: ready for the next launch
-#pragma unroll
-    for (int v = 0; v < VPL; ++v)
-#pragma unroll
-      for (int i = 0; i < E; ++i) acc[v][i] = 0.0f;
-    if (lane < LPR) {
-      for (int sl = 0; sl < n; ++sl) {
-        const float* src = p.scratch + (int64_t)(first + sl) * F;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          const int c0 = (lane + v * LPR) * E;
-          if (c0 < F) {
-#pragma unroll
-            for (int q = 0; q < E / 4; ++q) {
-              const float4 t = __ldcg(reinterpret_cast<const float4*>(src + c0 + 4 * q));   // L2: written by other SMs
-              acc[v][4 * q] += t.x; acc[v][4 * q + 1] += t.y; acc[v][4 * q + 2] += t.z; acc[v][4 * q + 3] += t.w;
-            }
-          }
-        }
-      }
-    }
-  }
-  row_epilogue<LPR, VPL, E, EPI>(p, ch.x, lane, acc, smem_w);
-}
-
-// tgcn_spmm_args -> kernel parameters (shared by tgcn_spmm and tgcn_spmm_staged); checks the fused-Adam arguments
+// tgcn_spmm_args -> kernel parameters; checks the fused-Adam arguments
 static inline int fill_spmm_params(const tgcn_spmm_args* a, SpmmParams* p) {
   p->rowptr = a->rowptr; p->colidx = a->colidx; p->val = a->val;
   p->chunks = reinterpret_cast<const int4*>(a->chunks); p->n_chunks = a->n_chunks;
   p->split_rows = a->split_rows; p->n_split_rows = a->n_split_rows;
-  p->slot_owner = a->slot_owner; p->split_counters = (a->slot_owner && a->split_counters) ? a->split_counters : nullptr;
+  p->slot_owner = a->slot_owner; p->split_counters = a->split_counters;
   p->scratch = a->scratch;
   p->B = a->B; p->ldb = a->ldb;
   p->C = a->C; p->ldc = a->ldc; p->c_dtype = a->c_dtype;
@@ -295,9 +209,6 @@ static inline int fill_spmm_params(const tgcn_spmm_args* a, SpmmParams* p) {
   p->ad_p = a->adam_param; p->ad_m = a->adam_exp_avg; p->ad_v = a->adam_exp_avg_sq; p->ad_x = a->adam_max_exp_avg_sq;
   p->ad_ld = a->adam_ld; p->ad_hyp = a->adam_hyper_dev; p->ad_b1 = a->adam_beta1; p->ad_b2 = a->adam_beta2; p->ad_eps = a->adam_eps;
   p->ad_mirror = (float*)a->adam_param_mirror_mc;
-#if TGCN_SPMM_CVPACK
-  p->cv = reinterpret_cast<const int2*>(a->colval);
-#endif
   if (p->ad_p) {
     TGCN_CHECK_ARG(p->ad_m && p->ad_v && p->ad_hyp, "spmm: fused Adam needs exp_avg, exp_avg_sq and the hyper buffer");
     TGCN_CHECK_ARG(a->P == nullptr && a->b_dtype == TGCN_F32 && p->ad_ld % 4 == 0 && p->ad_ld >= a->F,

@@ -75,8 +75,6 @@ class GraphCSR:
         self.nnz = int(colidx.numel())
         self.device = rowptr.device
         self._plans: Dict[Tuple[int, int, int], SpmmPlan] = {}
-        self._staged: Dict[Tuple, Tuple] = {}
-        self._colval: Optional[torch.Tensor] = None
         self._symmetric: Optional[bool] = None
         self._transpose: Optional["GraphCSR"] = None
         self.buffers: Dict[str, torch.Tensor] = {}   # static work buffers owned by the host layer
@@ -117,28 +115,6 @@ class GraphCSR:
                      counters=torch.zeros(max(n_split, 1), dtype=torch.int32, device=self.device) if n_split else None)
         self._plans[key] = p
         return p
-
-    def colval(self) -> torch.Tensor:
-        """The CSR entries once more as interleaved pairs {colidx[k], bits of val[k]} (int32 [nnz, 2]) for library
-        builds that read one 8-byte pair per non-zero (TGCN_SPMM_CVPACK); built on first use."""
-        if self._colval is None:
-            cv = torch.zeros((self.nnz + 256, 2), dtype=torch.int32, device=self.device)   # tail: the kernel prefetches ahead
-            cv[:self.nnz, 0] = self.colidx
-            cv[:self.nnz, 1] = self.val.view(torch.int32)
-            self._colval = cv
-        return self._colval
-
-    def staged_plan(self, plan: SpmmPlan, warps_per_panel: int, rows_per_warp: int, tile_cols: int):
-        """Panel/tile arrays of the shared-memory staged SpMM for `plan` (built once, on the device)."""
-        key = (plan.row_begin, plan.row_end, plan.chunk_nnz, warps_per_panel, rows_per_warp, tile_cols)
-        sp = self._staged.get(key)
-        if sp is None or sp[0] is not plan:
-            from .staged_plan import build_staged_plan
-            built = build_staged_plan(self.colidx, self.val, plan.chunks, self.n_cols, warps_per_panel=warps_per_panel,
-                                      rows_per_warp=rows_per_warp, tile_cols=tile_cols)
-            sp = (plan, built)
-            self._staged[key] = sp
-        return sp[1]
 
     # ---- transpose handling for the backward pass ----
     def row_ids(self) -> torch.Tensor:

@@ -22,26 +22,6 @@ DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
 # shipped default is stand-alone; classes <= this threshold use the fused epilogue (0 = never).
 import os as _os
 FUSED_PROJ_MAX_CLASSES = int(_os.environ.get("TGCN_FUSED_PROJ_MAX_CLASSES", "0"))
-# split rows: 1 = the last-arriving chunk reduces the partial rows inside the SpMM kernel, 0 = separate fix-up kernel
-FOLD_FIXUP = int(_os.environ.get("TGCN_FOLD_FIXUP", "1"))
-
-# Wide fp32 propagations through the shared-memory staged panel kernel (tgcn_spmm_staged) instead of the
-# per-non-zero L2 gathers of tgcn_spmm.  EXPERIMENTAL: written after round 1's B200 budget was spent, so it
-# is parity-tested on the GPU only when selected (TGCN_SPMM_STAGED=1) and is off by default.  Shape knobs:
-# consumer warps per panel, chunks per consumer warp, operand rows per stage, producer warps, producer
-# mode (0 = one cp.async.bulk per row, 1 = 16-byte cp.async by all lanes), smallest F that uses it.
-STAGED = int(_os.environ.get("TGCN_SPMM_STAGED", "0"))
-STAGED_CFG = dict(warps_per_panel=int(_os.environ.get("TGCN_STAGED_WARPS", "28")),
-                  rows_per_warp=int(_os.environ.get("TGCN_STAGED_RPW", "2")),
-                  tile_cols=int(_os.environ.get("TGCN_STAGED_TILE", "64")),
-                  n_producers=int(_os.environ.get("TGCN_STAGED_PRODUCERS", "4")),
-                  producer_mode=int(_os.environ.get("TGCN_STAGED_MODE", "0")),
-                  min_f=int(_os.environ.get("TGCN_STAGED_MIN_F", "96")))
-
-# 1 = also hand the kernels the CSR entries as interleaved {col, val} pairs (GraphCSR.colval, +8 B per non-zero).
-# Only library builds made with TGCN_SPMM_CVPACK read them (make variant-cvpack / variant-all); the shipped build ignores the field.
-CVPACK = int(_os.environ.get("TGCN_SPMM_CVPACK", "0"))
-
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 
@@ -76,11 +56,8 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
          drop_mode: int = DROP_NONE, drop_p: float = 0.0, keep_mask: Optional[torch.Tensor] = None,
          philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0,
          W_proj: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
-         want_out: bool = True, adam: Optional[dict] = None,
-         staged: Optional[bool] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+         want_out: bool = True, adam: Optional[dict] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """C = epi(A_hat[rows of plan] @ B[:, :F]) (+ P = C @ W_proj).  See tgcn_spmm.
-    staged: True/False forces / forbids the shared-memory staged kernel (tgcn_spmm_staged); None follows
-    TGCN_SPMM_STAGED for the shapes that kernel covers (fp32 B, F % 4 == 0, min_f <= F <= 256, no projection).
 
     B: [>= n_nodes, >= F] fp32/bf16, row stride a multiple of 4 (fp32) / 8 (bf16) elements.
     Returns (C or None, P or None).  C has plan.row_end - plan.row_begin rows.
@@ -111,10 +88,8 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
         a.adam_ld, a.adam_hyper_dev = prm.stride(0), adam["hyper"].data_ptr()
         a.adam_beta1, a.adam_beta2, a.adam_eps = adam.get("beta1", 0.9), adam.get("beta2", 0.999), adam.get("eps", 1e-8)
         a.adam_param_mirror_mc = adam.get("mirror")
-    if plan.n_split_rows and FOLD_FIXUP:
+    if plan.n_split_rows:
         a.slot_owner, a.split_counters = _native.ptr(plan.slot_owner), _native.ptr(plan.counters)
-    if CVPACK:
-        a.colval = graph.colval().data_ptr()
     a.B, a.ldb, a.b_dtype = B.data_ptr(), B.stride(0), _dt(B)
     if want_out:
         if out is None:
@@ -145,22 +120,8 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
         if P is None:
             P = torch.zeros((n_out, pad4(n_proj)), dtype=torch.float32, device=B.device)
         a.W_proj, a.n_proj, a.P, a.ldp = W_proj.data_ptr(), n_proj, P.data_ptr(), P.stride(0)
-    can_stage = (B.dtype == torch.float32 and F % 4 == 0 and F <= 256 and W_proj is None
-                 and (plan.n_split_rows == 0 or FOLD_FIXUP))
-    if staged is None:
-        staged = bool(STAGED) and can_stage and F >= STAGED_CFG["min_f"]
-    elif staged and not can_stage:
-        raise RuntimeError("spmm: the staged kernel needs an fp32 operand, F % 4 == 0, F <= 256, no fused projection "
-                           "and in-kernel reduction of split rows")
     with torch.cuda.device(B.device):
-        if staged:
-            from . import staged_plan as _sp
-            cfg = STAGED_CFG
-            sp = graph.staged_plan(plan, cfg["warps_per_panel"], cfg["rows_per_warp"], cfg["tile_cols"])
-            cp = _sp.c_plan(sp, cfg["n_producers"], cfg["producer_mode"])
-            _native.check(lib.tgcn_spmm_staged(C.byref(a), C.byref(cp), _stream()))
-        else:
-            _native.check(lib.tgcn_spmm(C.byref(a), _stream()))
+        _native.check(lib.tgcn_spmm(C.byref(a), _stream()))
     return out, P
 
 
@@ -267,6 +228,32 @@ def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Opti
     with torch.cuda.device(X.device):
         _native.check(lib.tgcn_project(X.data_ptr(), X.stride(0), _dt(X), n, K, W.data_ptr(), M,
                                        out.data_ptr(), out.stride(0), mirror, _stream()))
+    return out
+
+
+def dropout_apply(X: torch.Tensor, *, F: Optional[int] = None, out: Optional[torch.Tensor] = None, drop_mode: int = DROP_NONE,
+                  drop_p: float = 0.0, keep_mask: Optional[torch.Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,
+                  philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0) -> torch.Tensor:
+    """out = dropout(X[:, :F]) with the keep decision of the SpMM epilogue (see tgcn_dropout_apply)."""
+    _need_cuda(X, out, keep_mask, philox_offset_dev)
+    lib = _native.load()
+    F = int(X.shape[1]) if F is None else int(F)
+    if X.dtype != torch.float32 or X.dim() != 2 or X.stride(1) != 1:
+        raise RuntimeError("dropout_apply: X must be a row-major fp32 matrix")
+    if out is None:
+        out = torch.empty((X.shape[0], F), dtype=torch.float32, device=X.device)
+    if out.dtype != torch.float32 or out.stride(1) != 1 or out.shape[0] < X.shape[0] or out.shape[1] < F:
+        raise RuntimeError("dropout_apply: bad `out` tensor")
+    km, ldm = None, 0
+    if keep_mask is not None:
+        if keep_mask.dtype not in (torch.uint8, torch.bool) or keep_mask.stride(1) != 1:
+            raise RuntimeError("dropout_apply: keep_mask must be a row-major uint8/bool tensor")
+        km, ldm = keep_mask.data_ptr(), keep_mask.stride(0)
+    with torch.cuda.device(X.device):
+        _native.check(lib.tgcn_dropout_apply(X.data_ptr(), X.stride(0), out.data_ptr(), out.stride(0), int(X.shape[0]), F,
+                                             drop_mode, float(drop_p), km, ldm, philox_seed & (2**64 - 1),
+                                             philox_offset & (2**64 - 1), _native.ptr(philox_offset_dev), int(row_id_offset),
+                                             _stream()))
     return out
 
 

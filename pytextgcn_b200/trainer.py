@@ -12,7 +12,6 @@ parameters are updated in place, so the wrapped `GCN` stays an ordinary nn.Modul
 """
 from __future__ import annotations
 
-import os
 from typing import Dict, Optional
 
 import torch
@@ -21,14 +20,12 @@ from . import ops
 from .graph import GraphCSR, get_graph
 from .models import GCN, decode_features
 
-ROW_ALIGN = int(os.environ.get("TGCN_ROW_ALIGN", "0"))
-
 
 class TextGCNTrainer:
     def __init__(self, gcn: GCN, g, lr: float = 0.05, amsgrad: bool = True, betas=(0.9, 0.999), eps: float = 1e-8,
                  use_cuda_graph: bool = True, seed: int = 0, chunk_nnz: Optional[int] = None,
                  graph: Optional[GraphCSR] = None, assume_symmetric: bool = False, eval_mode: str = "layered",
-                 fuse_adam: bool = True, keep_w1_grad: bool = True):
+                 fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True):
         if len(gcn.layers) != 2:
             raise NotImplementedError("TextGCNTrainer fuses the 2-layer TextGCN (the configuration of every reference script)")
         l0, l1 = gcn.layers
@@ -68,24 +65,6 @@ class TextGCNTrainer:
         self.exp_avg = [torch.zeros_like(p_.data) for p_ in self.params]
         self.exp_avg_sq = [torch.zeros_like(p_.data) for p_ in self.params]
         self.max_exp_avg_sq = [torch.zeros_like(p_.data) for p_ in self.params] if amsgrad else [None] * 4
-        # Row pitch of the gathered hidden-wide operands (W1 and dZ1).  A 200-float row is 800 bytes, so 3 of 4 rows
-        # start off a 128-byte line and a warp's 512-byte load of such a row costs 5 instead of 4 wavefronts of the L1
-        # data pipe -- the unit the wide SpMM saturates.  TGCN_ROW_ALIGN=1 (experimental: not measured yet) re-homes W1,
-        # its gradient and Adam state in buffers whose pitch is a multiple of 32 floats; `layers.0.weight` then is a
-        # strided view of that buffer (same shape and values).  Needs the fused Adam path (its kernels take a pitch).
-        self.row_pitch = H
-        if ROW_ALIGN and H % 32 != 0 and bool(fuse_adam) and self.feat.Fdoc is None:
-            self.row_pitch = (H + 31) // 32 * 32
-
-            def padded(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-                if t is None:
-                    return None
-                buf = torch.zeros((t.shape[0], self.row_pitch), dtype=t.dtype, device=t.device)
-                buf[:, :H].copy_(t)
-                return buf[:, :H]
-            l0.weight.data = padded(l0.weight.data)
-            self.grads[0], self.exp_avg[0], self.exp_avg_sq[0] = padded(self.grads[0]), padded(self.exp_avg[0]), padded(self.exp_avg_sq[0])
-            self.max_exp_avg_sq[0] = padded(self.max_exp_avg_sq[0])
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.adam_hyper = torch.zeros(2, dtype=torch.float32, device=dev)   # lr/(1-b1^t), sqrt(1-b2^t) of the current step
         # W1's Adam update can run in the epilogue of the SpMM that produces dW1 (rows of dW1 never leave registers
@@ -94,14 +73,19 @@ class TextGCNTrainer:
         self.keep_w1_grad = bool(keep_w1_grad)
         self.XW = torch.zeros((n, H), **f32) if self.feat.Fdoc is not None else None
         self.H1d = torch.empty((n, H), **f32)
-        # TGCN_ROW_ALIGN=2 also gives the gathered class-wide operands (P, dZ2; Q, T of the collapsed eval) a 128-byte
-        # pitch: an 80-byte row then sits in one line instead of straddling two half of the time
-        cpitch = (Cp + 31) // 32 * 32 if ROW_ALIGN >= 2 else Cp
-        self.P = torch.zeros((n, cpitch), **f32)[:, :Cp]
+        # A_hat (X W1) + b1 of the eval forward of epoch k IS the pre-dropout hidden activation of the training forward
+        # of epoch k+1: W1/b1 do not change between them (flat_amazon.py:100-110: step -> eval -> next step) and
+        # F.dropout follows the product (models.py:20-23).  With share_h1 the eval pass keeps it in `H1` and the next
+        # train step only applies its dropout mask (tgcn_dropout_apply) instead of repeating the hidden-wide SpMM:
+        # bit-identical activations, one wide propagation less per epoch.  `_h1_key` names the parameter state H1 holds.
+        self.share_h1 = bool(share_h1)
+        self.H1 = torch.empty((n, H), **f32) if (self.share_h1 and self.p > 0.0) else self.H1d
+        self._h1_key = None
+        self.P = torch.zeros((n, Cp), **f32)
         self.Z2 = torch.zeros((n, Cp), **f32)
-        self.dZ2 = torch.zeros((n, cpitch), **f32)[:, :Cp]
+        self.dZ2 = torch.zeros((n, Cp), **f32)
         self.G2 = torch.zeros((n, Cp), **f32)
-        self.dZ1 = torch.zeros((n, self.row_pitch), **f32)[:, :H]
+        self.dZ1 = torch.zeros((n, H), **f32)
         self.loss_train = torch.zeros(2, **f32)
         self.loss_val = torch.zeros(2, **f32)
         self.loss_tr_eval = torch.zeros(2, **f32)
@@ -112,14 +96,15 @@ class TextGCNTrainer:
         self._nll_ws = torch.empty(2 * ((n * 4 + 255) // 256 * 256) + 4096, dtype=torch.uint8, device=dev)
         self._db_ws = None
         self.logits = self.Z2[:, :self.C]
-        self.Q = torch.zeros((n, cpitch), **f32)[:, :Cp]          # collapsed eval: X W1 W2
-        self.T = torch.zeros((n, cpitch), **f32)[:, :Cp]          # collapsed eval: A_hat Q + 1 (b1^T W2)
+        self.Q = torch.zeros((n, Cp), **f32)          # collapsed eval: X W1 W2
+        self.T = torch.zeros((n, Cp), **f32)          # collapsed eval: A_hat Q + 1 (b1^T W2)
         self.c_row = torch.zeros((1, Cp), **f32)
         self.eval_mode = "layered"
         self.set_masks(g.y, g.train_mask, getattr(g, "val_mask", None))
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._warm: Dict[str, int] = {}
         self.launches_per_train_step = 0
+        self.launches_per_train_step_reuse = 0
         self.launches_per_eval = 0
         self.set_eval_mode(eval_mode)
 
@@ -173,31 +158,47 @@ class TextGCNTrainer:
         ops.spmm(self.graph, self.Q, F=self.Cp, plan=self.plan, out=self.T, bias=self.c_row[0, :self.C])
         ops.spmm(self.graph, self.T, F=self.Cp, plan=self.plan, out=self.Z2, bias=b2)
 
-    def _forward(self, training: bool) -> None:
+    def _param_key(self):
+        l0 = self.gcn.layers[0]
+        return (l0.weight._version, l0.bias._version, l0.weight.data_ptr(), l0.bias.data_ptr())
+
+    def invalidate_cache(self) -> None:
+        """Forget the shared hidden activation (call after changing W1/b1 through raw pointers or `.data`;
+        in-place torch ops on the Parameters such as load_state_dict are detected through their version counters)."""
+        self._h1_key = None
+
+    def _forward(self, training: bool, reuse_h1: bool = False) -> None:
         l0, l1 = self.gcn.layers
         W1, b1, W2, b2 = l0.weight.data, l0.bias.data, l1.weight.data, l1.bias.data
         if not training and self.eval_mode == "collapsed":
             self._forward_collapsed()
             return
-        if self.feat.Fdoc is not None:
-            ops.hier_forward(W1, self.n, self.feat.n_vocab, self.feat.Fdoc, out=self.XW)
-            B1 = self.XW
-        else:
-            B1 = W1[:self.n]
         drop = training and self.p > 0.0
-        fuse = self.C <= ops.FUSED_PROJ_MAX_CLASSES
-        ops.spmm(self.graph, B1, F=self.H, plan=self.plan, out=self.H1d, bias=b1, act=self.act,
-                 drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p,
-                 philox_seed=self.seed, philox_offset=0, philox_offset_dev=self.step_dev if drop else None,
-                 W_proj=W2 if fuse else None, P=self.P if fuse else None)
+        dkw = dict(drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
+                   philox_offset=0, philox_offset_dev=self.step_dev if drop else None)
+        fuse = self.C <= ops.FUSED_PROJ_MAX_CLASSES and not reuse_h1
+        if reuse_h1:
+            # H1 = act(A_hat (X W1) + b1) of the preceding eval pass, same W1/b1: only the dropout mask is applied
+            if drop:
+                ops.dropout_apply(self.H1, F=self.H, out=self.H1d, **dkw)
+            h_out = self.H1d
+        else:
+            if self.feat.Fdoc is not None:
+                ops.hier_forward(W1, self.n, self.feat.n_vocab, self.feat.Fdoc, out=self.XW)
+                B1 = self.XW
+            else:
+                B1 = W1[:self.n]
+            h_out = self.H1d if training else self.H1
+            ops.spmm(self.graph, B1, F=self.H, plan=self.plan, out=h_out, bias=b1, act=self.act,
+                     W_proj=W2 if fuse else None, P=self.P if fuse else None, **dkw)
         if not fuse:
-            ops.project(self.H1d, W2, K=self.H, out=self.P)
+            ops.project(h_out, W2, K=self.H, out=self.P)
         ops.spmm(self.graph, self.P, F=self.Cp, plan=self.plan, out=self.Z2, bias=b2)
 
-    def _train_body(self) -> None:
+    def _train_body(self, reuse_h1: bool = False) -> None:
         l0, l1 = self.gcn.layers
         W2 = l1.weight.data
-        self._forward(True)
+        self._forward(True, reuse_h1)
         ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2,
                        loss_out=self.loss_train, workspace=self._nll_ws)
         ops.spmm(self.graph_t, self.dZ2, F=self.Cp, plan=self.plan_t, out=self.G2)
@@ -266,6 +267,8 @@ class TextGCNTrainer:
     def _set_launches(self, name: str, k: int) -> None:
         if name == "train":
             self.launches_per_train_step = k
+        elif name == "train_reuse":
+            self.launches_per_train_step_reuse = k
         else:
             self.launches_per_eval = k
 
@@ -273,13 +276,19 @@ class TextGCNTrainer:
     def train_step(self) -> torch.Tensor:
         """One full-batch training step.  Returns the device tensor [mean train loss, #rows]."""
         self.gcn.train()
-        self._run("train", self._train_body)
+        if self.share_h1 and self._h1_key is not None and self._h1_key == self._param_key():
+            self._run("train_reuse", lambda: self._train_body(True))
+        else:
+            self._run("train", self._train_body)
+        self._h1_key = None          # W1/b1 have just been updated
         return self.loss_train
 
     def eval_step(self) -> Dict[str, torch.Tensor]:
         """Eval forward + val loss + on-device argmax/accuracy counts (device tensors, no sync)."""
         self.gcn.eval()
         self._run("eval", self._eval_body)
+        if self.share_h1 and self.eval_mode == "layered":
+            self._h1_key = self._param_key()      # H1 now holds act(A_hat (X W1) + b1) for the current W1/b1
         return dict(logits=self.logits, val_loss=self.loss_val, pred=self.pred, correct_val=self.correct_val,
                     correct_train=self.correct_train)
 

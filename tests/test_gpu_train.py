@@ -57,7 +57,7 @@ def test_adam_matches_torch(cuda, amsgrad):
     assert int(step_dev.item()) == 5
 
 
-@pytest.mark.parametrize("H,C,act", [(200, 20, 0), (100, 64, 0), (32, 219, 0), (256, 20, 1), (64, 6, 0), (256, 220, 0)])
+@pytest.mark.parametrize("H,C,act", [(200, 20, 0), (100, 64, 0), (32, 219, 0), (256, 20, 1), (64, 6, 0), (256, 220, 0), (32, 300, 0)])
 def test_dense_backward(cuda, H, C, act):
     from pytextgcn_b200 import ops
     torch.manual_seed(H + C)
@@ -239,3 +239,64 @@ def test_adam_small_multi_tensor_matches_torch(cuda, amsgrad):
         ops.adam_step_small(ps, [g.to(cuda) for g in gs], ms, vs, xs, lr=0.05, amsgrad=amsgrad, step_dev=step_dev)
         for p, r in zip(ps, refs):
             assert rel_err(p, r) < 2e-6
+
+
+@pytest.mark.parametrize("mode", ["philox", "mask"])
+def test_dropout_apply_equals_the_spmm_epilogue(cuda, mode):
+    """tgcn_dropout_apply(A B + bias) must be bit-identical to the SpMM with the dropout epilogue."""
+    from pytextgcn_b200 import ops
+    from pytextgcn_b200.graph import upload_graph
+    from pytextgcn_b200.synthetic import make_graph
+    g = make_graph("small", seed=3)
+    n, F = int(g.x.shape[0]), 200
+    gr = upload_graph(g.edge_index.to(cuda), g.edge_attr.to(cuda), n)
+    torch.manual_seed(1)
+    B, bias = torch.randn(n, F, device=cuda), torch.randn(F, device=cuda)
+    step = torch.full((1,), 5, dtype=torch.int64, device=cuda)
+    if mode == "philox":
+        kw = dict(drop_mode=ops.DROP_PHILOX, drop_p=0.5, philox_seed=11, philox_offset=3, philox_offset_dev=step)
+    else:
+        kw = dict(drop_mode=ops.DROP_MASK, drop_p=0.3, keep_mask=(torch.rand(n, F, device=cuda) > 0.3).to(torch.uint8))
+    fused, _ = ops.spmm(gr, B, bias=bias, **kw)
+    pre, _ = ops.spmm(gr, B, bias=bias)
+    two_step = ops.dropout_apply(pre, **kw)
+    assert torch.equal(fused, two_step)
+    assert 0.2 < (fused == 0).float().mean().item() < 0.6
+
+
+@pytest.mark.parametrize("graph_mode", [False, True])
+@pytest.mark.parametrize("relu", [False, True])
+def test_shared_hidden_activation_is_bit_identical_and_saves_a_wide_spmm(cuda, graph_mode, relu, monkeypatch):
+    """share_h1: the eval forward's A_hat (X W1) + b1 serves the next training forward (same W1/b1,
+    flat_amazon.py:100-110).  Losses, parameters and logits must be bit-identical to recomputing it."""
+    from pytextgcn_b200 import ops
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    hist, wide_calls = {}, {}
+    real_spmm = ops.spmm
+    for share in (False, True):
+        g, gd, ref, mod, shape = _make_pair(cuda, p=0.5, relu=relu)
+        tr = TextGCNTrainer(mod, gd, lr=0.05, amsgrad=True, seed=7, share_h1=share, use_cuda_graph=graph_mode)
+        count = [0]
+
+        def counting(graph, B, *a, F=None, **k):
+            if F == shape.hidden:
+                count[0] += 1
+            return real_spmm(graph, B, *a, F=F, **k)
+        monkeypatch.setattr(ops, "spmm", counting)
+        out = []
+        for ep in range(6):
+            if ep == 3:
+                with torch.no_grad():                       # an in-place edit of W1 must invalidate the shared activation
+                    mod.layers[0].weight.mul_(1.0)
+            r = tr.epoch()
+            out.append((r["loss"], r["val_loss"], r["acc_val"]))
+        monkeypatch.setattr(ops, "spmm", real_spmm)
+        hist[share] = (out, [p_.detach().clone() for p_ in mod.parameters()], tr.logits.clone())
+        wide_calls[share] = count[0]
+    assert hist[True][0] == hist[False][0]
+    for a, b in zip(hist[True][1], hist[False][1]):
+        assert torch.equal(a, b)
+    assert torch.equal(hist[True][2], hist[False][2])
+    if not graph_mode:
+        # 3 wide propagations per epoch without sharing; with it 2, plus one for the very first step and one after the edit
+        assert wide_calls[False] == 18 and wide_calls[True] == 14

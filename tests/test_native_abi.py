@@ -70,49 +70,17 @@ int main(void) {{
          offsetof(tgcn_spmm_args, ldp), offsetof(tgcn_spmm_args, bias_len));
   printf("%zu %zu %zu %zu\\n", sizeof(tgcn_dense_bwd_args), offsetof(tgcn_dense_bwd_args, H), offsetof(tgcn_dense_bwd_args, dZ1),
          offsetof(tgcn_dense_bwd_args, db_out));
-  printf("%zu %zu %zu %zu %zu\\n", offsetof(tgcn_spmm_args, colval), offsetof(tgcn_spmm_args, adam_param_mirror_mc),
-         sizeof(tgcn_staged_plan), offsetof(tgcn_staged_plan, n_panels), offsetof(tgcn_staged_plan, producer_mode));
+  printf("%zu %zu\\n", offsetof(tgcn_spmm_args, split_counters), offsetof(tgcn_spmm_args, adam_param_mirror_mc));
   return 0;
 }}''')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    S, D, P = _native.SpmmArgs, _native.DenseBwdArgs, _native.StagedPlanArgs
+    S, D = _native.SpmmArgs, _native.DenseBwdArgs
     mine = [ctypes.sizeof(S), S.F.offset, S.philox_offset_dev.offset, S.ldp.offset, S.bias_len.offset,
             ctypes.sizeof(D), D.H.offset, D.dZ1.offset, D.db_out.offset,
-            S.colval.offset, S.adam_param_mirror_mc.offset, ctypes.sizeof(P), P.n_panels.offset, P.producer_mode.offset]
+            S.split_counters.offset, S.adam_param_mirror_mc.offset]
     assert [int(v) for v in out] == mine
-
-
-def test_staged_spmm_argument_validation(lib):
-    """tgcn_spmm_staged rejects inconsistent plans / operands before any CUDA call (fake non-null pointers)."""
-    from pytextgcn_b200 import _native
-    a = _native.SpmmArgs()
-    a.chunks, a.n_chunks = 0x1000, 100
-    a.B, a.ldb, a.b_dtype, a.C, a.ldc, a.c_dtype, a.F = 0x2000, 200, 0, 0x3000, 200, 0, 200
-    p = _native.StagedPlanArgs()
-
-    def call():
-        rc = lib.tgcn_spmm_staged(ctypes.byref(a), ctypes.byref(p), None)
-        return rc, lib.tgcn_last_error().decode()
-    assert call() == (1, "spmm_staged: plan pointer null")
-    p.panel_ucol_ptr = p.ucols = p.warp_stream_ptr = p.stream = 0x100
-    p.rows_per_warp, p.n_producers, p.warps_per_panel, p.tile_cols, p.n_panels = 3, 4, 28, 64, 2
-    assert "rows_per_warp" in call()[1]
-    p.rows_per_warp = 2
-    p.warps_per_panel = 30
-    assert "at most 32" in call()[1]
-    p.warps_per_panel, p.tile_cols = 28, 200
-    assert "tile_cols" in call()[1]
-    p.tile_cols, p.n_panels = 64, 1                      # 56 chunk slots for 100 chunks
-    assert "does not match the chunk list" in call()[1]
-    p.n_panels = 2
-    a.b_dtype = 1
-    assert "fp32 operand" in call()[1]
-    a.b_dtype, a.F = 0, 260
-    assert "at most 256" in call()[1]
-    a.F, a.n_split_rows = 200, 3
-    assert "split rows need" in call()[1]
 
 
 def test_no_cpu_fallback():
