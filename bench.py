@@ -293,7 +293,7 @@ def run_own_arm(args):
     ev1.record()
     torch.cuda.synchronize()
     ms_total = ev0.elapsed_time(ev1)
-    launches_eager_epoch = tr.launches_per_train_step + tr.launches_per_eval
+    launches_eager_epoch = (tr.launches_per_train_step_reuse or tr.launches_per_train_step) + tr.launches_per_eval
     ms_per_step = ms_total / K
     value = 1e3 / ms_per_step
 
@@ -338,11 +338,8 @@ def run_own_arm(args):
     achieved = alg / (k_ms * 1e-3) / 1e9
     prof = load_profile_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None if (ops.STAGED and F >= ops.STAGED_CFG["min_f"]) else prof.get("dram_bytes_per_launch"),
-                "kernel": ("k_spmm_staged<2,%d,plain,%s> (shared-memory staged panel kernel, TGCN_SPMM_STAGED=1; "
-                           % (ops.STAGED_CFG["rows_per_warp"], "bulk" if ops.STAGED_CFG["producer_mode"] == 0 else "ldgsts")
-                           if (ops.STAGED and F >= ops.STAGED_CFG["min_f"]) else "k_spmm<float,32,2,false> (")
-                          + "layer-1 propagation of the train step, F=%d, fused bias + Philox dropout epilogue)" % F,
+                "traffic": prof.get("dram_bytes_per_launch"),
+                "kernel": "k_spmm<float,32,2,false> (layer-1 propagation of the train step, F=%d, fused bias + Philox dropout epilogue)" % F,
                 "kernel_ms": k_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
                 "note": "algorithmic bytes count each dense row once; the kernel is bound by L2->SM gather bandwidth "
                         "(nnz*F*4 = %.1f GB per launch), see DESIGN.md" % (graph.nnz * F * 4 / 1e9),
@@ -419,9 +416,7 @@ def run_own_arm(args):
                   "nnz": graph.nnz, "symmetric": bool(sym), "last_epoch": {"loss": last[0], "acc_train": last[1], "acc_val": last[2]},
                   "kernels_per_epoch": launches_eager_epoch, "lib_launch_counter_delta": int(l1 - l0),
                   "cuda_graph": True,
-                  "switches": {"spmm_staged": int(ops.STAGED), "staged_cfg": dict(ops.STAGED_CFG) if ops.STAGED else None,
-                               "cvpack": int(ops.CVPACK), "row_align": int(os.environ.get("TGCN_ROW_ALIGN", "0")),
-                               "library": os.path.basename(os.environ.get("TGCN_B200_LIB", "") or "libtextgcn_b200.so")}},
+                  "share_h1": bool(tr.share_h1)},
     }
     print(json.dumps(line), flush=True)
 

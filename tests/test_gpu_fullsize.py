@@ -1,8 +1,8 @@
 """Parity at BASELINE.json's full size (20NG-shape: 61,603 nodes, 2.15e7 non-zeros, hidden 200, 20
-classes).  The CPU oracle can still build gcn_norm's CSR at this size (bit-exact check), but not the
-E x hidden message tensors of a whole training step in reasonable time, so the numerical checks use
-size-independent properties: sampled rows recomputed in fp64 on the host, the adjoint identity of
-the symmetric operator, determinism, and the epoch statistics of a few fused training steps."""
+classes): gcn_norm's CSR bit for bit, one whole training step + eval forward element for element against
+the oracle (logits, loss, all gradients <= 1e-5), and size-independent properties on top: sampled rows
+recomputed in fp64 on the host, the adjoint identity of the symmetric operator, determinism, and the
+epoch statistics of a few fused training steps."""
 import numpy as np
 import pytest
 import torch
@@ -91,3 +91,57 @@ def test_fused_training_epochs_at_full_size(big, cuda):
     tr.set_eval_mode("collapsed")
     z2 = tr.eval_step()["logits"].clone()
     assert rel_err(z2, z1) < 1e-5
+
+
+def test_full_train_step_and_eval_against_the_oracle_at_full_size(big, cuda):
+    """One whole training step (forward with an explicit dropout keep-mask, masked cross-entropy, backward)
+    and the eval forward on the BASELINE 20NG-shape graph, compared element for element with
+    oracle.gcn_oracle (the restated GCNConv path, flat_amazon.py:99-110): logits, loss and all four
+    gradients within 1e-5 relative (max-norm).  The oracle materialises the (E+N) x 200 message tensors
+    (~17 GB each), so this needs ~50 GB of host memory and ~1 min of CPU time."""
+    from pytextgcn_b200 import GCN
+    g, n, csr, ei, ea = big
+    H, C, p = 200, 20, 0.5
+    torch.manual_seed(0)
+    ref = O.OracleGCN(n, C, n_hidden_gcn=H, dropout=p)
+    with torch.no_grad():
+        for l in ref.layers:
+            l.bias.uniform_(-0.1, 0.1)                      # non-zero biases: the epilogue's bias add is exercised
+    keep = torch.rand(n, H) > p
+    mod = GCN(n, C, n_hidden_gcn=H, dropout=p)
+    with torch.no_grad():
+        for pd, ps in zip(mod.parameters(), ref.parameters()):
+            pd.copy_(ps)
+    mod = mod.to(cuda)
+    gd = g.clone()
+    gd.edge_index, gd.edge_attr = ei, ea
+    gd = gd.to(cuda)
+
+    # ---- CUDA path: the drop-in module, autograd through the C ABI ----
+    mod.train()
+    mod.drop_mask_override = [keep.to(cuda)]
+    z = mod(gd)
+    loss = torch.nn.functional.cross_entropy(z[gd.train_mask], gd.y[gd.train_mask])
+    loss.backward()
+    z_train, loss_train = z.detach().cpu(), float(loss.item())
+    grads = [p_.grad.detach().cpu() for p_ in mod.parameters()]
+    mod.eval()
+    with torch.no_grad():
+        z_eval = mod(gd).cpu()
+    del z, loss
+    torch.cuda.empty_cache()
+
+    # ---- oracle ----
+    ref.train()
+    zr = ref(g, drop_masks=[keep])
+    lr = O.masked_cross_entropy(zr, g.y, g.train_mask)
+    lr.backward()
+    assert rel_err(z_train, zr.detach()) < 1e-5
+    assert abs(loss_train - lr.item()) < 1e-5 * abs(lr.item())
+    for name, gm, pr in zip(("W1", "b1", "W2", "b2"), grads, ref.parameters()):
+        assert rel_err(gm, pr.grad) < 1e-5, name
+    del zr, lr
+    ref.eval()
+    with torch.no_grad():
+        zr = ref(g)
+    assert rel_err(z_eval, zr) < 1e-5
