@@ -7,14 +7,17 @@ epochs/sec + SpMM HBM GB/s as % of roofline).
 
 A "step" is one REFERENCE EPOCH (flat_amazon.py:99-117): full-batch train step (forward,
 masked cross-entropy, backward, Adam/AMSGrad) + eval forward + val loss + argmax/accuracy.
-Workload: synthetic 20NG-shape doc-word graph (61,603 nodes, ~2.15e7 nnz, hidden 200, 20
-classes), seed 0, random-init weights.  N > 1: the same graph, 1D row-partitioned
-over the ranks with NCCL all-gathers between layers (strong scaling).
+Default workload: synthetic 20NG-shape doc-word graph (61,603 nodes, ~2.15e7 nnz, hidden 200, 20
+classes), seed 0, random-init weights.  Other workloads (--workload): r8, amazon,
+dbpedia (one level: 219 classes, x = [I | onehot(70)]), dbpedia-perlevel (the three GCNs of
+perlevel_dbpedia.py, one after the other; a step = one epoch of each), scale (1.2 M nodes).
+N > 1: the same graph, 1D row-partitioned over the ranks (strong scaling).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
 import subprocess
@@ -31,6 +34,7 @@ import torch
 
 METRIC = "train_epochs_per_sec"
 UNIT = "epochs/s"
+MIN_TIMED_S = 1.0          # the timed region is stretched to at least this long (whole multiples of --steps)
 
 
 # --------------------------------------------------------------------------------------
@@ -103,12 +107,36 @@ def spmm_alg_bytes(nnz: int, n: int, F: int, s_in: int = 4, s_out: int = 4) -> i
 
 
 def load_profile_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)."""
+    """dram bytes per launch of the dominant kernel from the committed ncu capture of the CURRENT build
+    (profiles/r02_ncu_summary_spmm.json, written by tools/ncu_summary.py); {} when there is none."""
     try:
-        with open(os.path.join(ROOT, "profiles", "dominant_kernel.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_summary_spmm.json")) as f:
             return json.load(f)
     except Exception:
         return {}
+
+
+def device_timed(fn, k: int) -> float:
+    """ms per call of fn over k back-to-back calls (CUDA events on the current stream)."""
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(k):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / k
+
+
+def resolve_workload(name: str):
+    """-> list of (label, GraphShape, hierarchy_classes) trained one after the other in one 'step'."""
+    from pytextgcn_b200.synthetic import SHAPES
+    if name == "dbpedia-perlevel":
+        base = SHAPES["dbpedia"]              # perlevel_dbpedia.py:95,141,186: l1 (9 classes), l2 (70), l3 (219)
+        return [("dbpedia-l1", dataclasses.replace(base, name="dbpedia-l1", n_classes=9), None),
+                ("dbpedia-l2", dataclasses.replace(base, name="dbpedia-l2", n_classes=70), 9),
+                ("dbpedia-l3", dataclasses.replace(base, name="dbpedia-l3", n_classes=219), 70)]
+    if name in ("dbpedia", "dbpedia-l3"):
+        return [("dbpedia-l3", dataclasses.replace(SHAPES["dbpedia"], name="dbpedia-l3"), 70)]
+    return [(name, SHAPES[name], None)]
 
 
 # --------------------------------------------------------------------------------------
@@ -125,7 +153,6 @@ def edge_subsample(g, frac: float, seed: int = 0):
     lo, hi = torch.minimum(ei[0], ei[1]), torch.maximum(ei[0], ei[1])
     key = lo * n + hi
     gen = torch.Generator().manual_seed(seed)
-    # hash-free selection: draw one uniform per undirected pair via its sorted rank
     uniq, inv = torch.unique(key, return_inverse=True)
     keep_u = torch.rand(uniq.numel(), generator=gen) < frac
     keep = keep_u[inv]
@@ -134,19 +161,23 @@ def edge_subsample(g, frac: float, seed: int = 0):
     return out
 
 
-def cpu_reference_epochs(g, shape, steps: int, warmup: int, budget_s: float, seed: int = 0):
-    """Times the reference epoch (oracle.reference_epoch: flat_amazon.py:99-117 restated on plain
-    torch CPU ops, gcn_norm recomputed per layer as cached=False does) on all host cores, on an
-    edge-subsample sized to the time budget.  Returns (epochs/s extrapolated, info dict)."""
+def cpu_reference_epochs(g, shape, steps: int = 3, warmup: int = 1, seed: int = 0, cpu_budget_s: float = 0.0):
+    """Times the reference epoch (oracle.reference_epoch: flat_amazon.py:99-117 restated on plain torch CPU
+    ops, gcn_norm recomputed per layer as cached=False does) on all host cores.
+
+    Default: the FULL graph, `warmup` untimed + `steps` timed epochs, median -- a measurement, no model.
+    cpu_budget_s > 0 (explicit fallback, labelled "extrapolated": true): if the full graph is predicted not
+    to fit that budget, an edge-subsample is timed and scaled with a two-point linear model in E."""
     from oracle import gcn_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n = int(g.x.shape[0])
+    in_ch = int(g.x.shape[1])
     E = int(g.edge_index.shape[1])
 
     def run(gs, k_warm, k_steps):
         torch.manual_seed(seed)
-        gcn = O.OracleGCN(n, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=shape.dropout)
+        gcn = O.OracleGCN(in_ch, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=shape.dropout)
         opt = torch.optim.Adam(gcn.parameters(), lr=shape.lr, amsgrad=shape.amsgrad)
         for _ in range(k_warm):
             O.reference_epoch(gcn, gs, opt)
@@ -157,75 +188,231 @@ def cpu_reference_epochs(g, shape, steps: int, warmup: int, budget_s: float, see
             ts.append(time.perf_counter() - t0)
         return ts
 
-    # calibration on a 2% edge sample -> seconds per edge (+ a per-node floor)
-    f_cal = min(1.0, max(0.02, 400_000 / max(E, 1)))
-    g_cal = edge_subsample(g, f_cal, seed)
-    t_cal = float(np.median(run(g_cal, 1, 2)))
-    pred_full = t_cal / f_cal
-    per_step_budget = budget_s / max(steps + warmup, 1)
-    frac = float(min(1.0, max(f_cal, per_step_budget / max(pred_full, 1e-9))))
+    what = (f"oracle/gcn_oracle.py reference_epoch (plain-torch port of the torch_geometric CPU path: edge-wise gather / scale / "
+            f"scatter-add, gcn_norm recomputed per layer, Adam amsgrad={shape.amsgrad}) on the {shape.name}-shape graph")
+    frac = 1.0
+    t_cal = e_cal = None
+    if cpu_budget_s > 0:
+        f_cal = min(1.0, max(0.02, 400_000 / max(E, 1)))
+        g_cal = edge_subsample(g, f_cal, seed)
+        t_cal = float(np.median(run(g_cal, 1, 2)))
+        e_cal = int(g_cal.edge_index.shape[1])
+        pred_full = t_cal / f_cal
+        per_step = cpu_budget_s / max(steps + warmup, 1)
+        frac = float(min(1.0, max(f_cal, per_step / max(pred_full, 1e-9))))
     gs = edge_subsample(g, frac, seed) if frac < 1.0 else g
     ts = run(gs, warmup, steps)
     t_step = float(np.median(ts))
     e_s = int(gs.edge_index.shape[1])
-    e_cal = int(g_cal.edge_index.shape[1])
     if e_s >= E:
-        t_full, how = t_step, "full graph, no extrapolation"
-    elif e_s > 2 * e_cal:
-        # two-point linear cost model t(E) = a + b*E (a: per-node work such as Adam on W1; b: per-edge work)
-        b = (t_step - t_cal) / (e_s - e_cal)
-        a = max(t_step - b * e_s, 0.0)
-        t_full = a + b * E
-        how = f"two-point linear model t(E)=a+b*E from E={e_cal} ({t_cal:.3f} s) and E={e_s} ({t_step:.3f} s)"
+        t_full, extrapolated = t_step, False
+        sample = (f"{what}: FULL graph ({E} directed edges, {n} nodes), {steps} timed epochs after {warmup} warm-up, "
+                  f"median {t_step:.3f} s/epoch (min {min(ts):.3f}, max {max(ts):.3f}); no extrapolation")
     else:
-        t_full, how = t_step * E / max(e_s, 1), "cost taken as linear in E"
+        b = (t_step - t_cal) / max(e_s - e_cal, 1)
+        a = max(t_step - b * e_s, 0.0)
+        t_full, extrapolated = a + b * E, True
+        sample = (f"{what}: edge-subsample {e_s} of {E} directed edges (--cpu-budget {cpu_budget_s:.0f} s), median "
+                  f"{t_step:.3f} s/epoch on the sample, EXTRAPOLATED to {t_full:.2f} s/epoch with t(E)=a+b*E")
     value = 1.0 / t_full
-    info = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": (f"oracle/gcn_oracle.py reference_epoch (plain-torch port of the torch_geometric CPU path, "
-                       f"gcn_norm per layer, AMSGrad={shape.amsgrad}) on an edge-subsample of the {shape.name}-shape "
-                       f"graph: {e_s} of {E} directed edges (all {n} nodes kept), {steps} timed epochs after {warmup} "
-                       f"warm-up, median {t_step:.3f} s/epoch on the sample; extrapolated to the full graph: {t_full:.2f} s/epoch "
-                       f"({how})"),
-            "t_step_sample_s": t_step, "edge_fraction": e_s / max(E, 1)}
+    info = {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "extrapolated": extrapolated,
+            "s_per_epoch": t_full, "timed_epochs": steps, "epoch_times_s": [round(t, 4) for t in ts],
+            "edge_fraction": e_s / max(E, 1)}
     return value, info
 
 
+def cpu_reference_workload(specs, seed: int, cpu_budget_s: float, graphs=None):
+    """CPU arm over every level of a workload (one level for the flat shapes); a step = one epoch of each."""
+    from pytextgcn_b200.synthetic import make_graph
+    infos, total = [], 0.0
+    for i, (label, shape, hier) in enumerate(specs):
+        g = graphs[i] if graphs is not None else make_graph(shape, seed=seed, hierarchy_classes=hier)
+        _, info = cpu_reference_epochs(g, shape, steps=3, warmup=1, seed=seed, cpu_budget_s=cpu_budget_s)
+        infos.append(info)
+        total += info["s_per_epoch"]
+    if len(infos) == 1:
+        return infos[0]
+    return {"value": 1.0 / total, "unit": UNIT, "cores": infos[0]["cores"], "kind": "port",
+            "extrapolated": any(i["extrapolated"] for i in infos), "s_per_epoch": total,
+            "sample": " | ".join(i["sample"] for i in infos)}
+
+
 def run_reference_arm(args):
+    """--impl reference: rank 0 times the reference's CPU path on the full graph(s) of the workload.  The epoch costs
+    seconds, so 1 warm-up + 3 timed epochs (median) are run whatever --steps/--warmup ask for; the line says so."""
     rank, local_rank, world = env_rank()
     if rank != 0:
         return
-    from pytextgcn_b200.synthetic import SHAPES, make_graph
-    shape = SHAPES[args.workload]
-    g = make_graph(shape, seed=args.seed)
-    value, info = cpu_reference_epochs(g, shape, args.steps, args.warmup, budget_s=150.0, seed=args.seed)
-    n = int(g.x.shape[0])
+    from pytextgcn_b200.synthetic import make_graph
+    specs = resolve_workload(args.workload)
+    t_wall = time.perf_counter()
+    graphs = [make_graph(shape, seed=args.seed, hierarchy_classes=hier) for _, shape, hier in specs]
+    info = cpu_reference_workload(specs, args.seed, args.cpu_budget, graphs)
+    value = info["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "steps": 3, "warmup": 1, "requested_steps": args.steps, "requested_warmup": args.warmup,
+        "ms_per_step": 1e3 / value, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(shape, g),
+        "config": workload_config(args.workload, specs, graphs[-1]),
         "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t_wall,
+        "note": ("extrapolated from an edge-subsample (--cpu-budget)" if info.get("extrapolated") else
+                 "a CPU epoch costs seconds: 1 warm-up + 3 timed epochs (median) on the FULL graph whatever --steps/--warmup "
+                 "ask for; measured, not extrapolated"),
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(shape, g):
+def workload_config(name, specs, g):
+    label, shape, hier = specs[-1]
     n = int(g.x.shape[0])
-    return {"workload": f"{shape.name}-shape synthetic doc-word graph: {shape.n_words} words + {shape.n_docs} docs = {n} nodes, "
-                        f"{int(g.edge_index.shape[1])} directed edges (+{n} self loops), 2-layer GCN hidden {shape.hidden}, "
-                        f"{shape.n_classes} classes, dropout {shape.dropout}, Adam amsgrad={shape.amsgrad} lr={shape.lr}; "
-                        f"step = reference epoch (train step + eval forward + val loss + argmax/accuracy)",
-            "shape": shape.name, "n_nodes": n, "n_edges": int(g.edge_index.shape[1]), "hidden": shape.hidden,
+    E = int(g.edge_index.shape[1])
+    if len(specs) > 1:
+        what = (f"dbpedia-perlevel: three independent 2-layer GCNs (perlevel_dbpedia.py:95,141,186) on one {shape.n_words} words + "
+                f"{shape.n_docs} docs = {n} node graph ({E} directed edges): 9 classes x = I; 70 classes x = [I | onehot(9)]; "
+                f"219 classes x = [I | onehot(70)]; hidden {shape.hidden}, dropout {shape.dropout}, plain Adam lr={shape.lr}; "
+                f"step = one reference epoch of EACH of the three")
+    else:
+        what = (f"{shape.name}-shape synthetic doc-word graph: {shape.n_words} words + {shape.n_docs} docs = {n} nodes, "
+                f"{E} directed edges (+{n} self loops), 2-layer GCN hidden {shape.hidden}, "
+                f"{shape.n_classes} classes{'' if not hier else f', x = [I | onehot({hier})]'}, dropout {shape.dropout}, "
+                f"Adam amsgrad={shape.amsgrad} lr={shape.lr}; "
+                f"step = reference epoch (train step + eval forward + val loss + argmax/accuracy)")
+    return {"workload": what, "shape": name, "n_nodes": n, "n_edges": E, "hidden": shape.hidden,
             "n_classes": shape.n_classes, "seed": 0,
-            "l2_policy": "inputs larger than L2 (CSR 172 MB + dense operands > 126 MB L2; every kernel of a step "
-                         "streams more than L2 between two uses of the same buffer)"}
+            "l2_policy": "inputs larger than L2 (CSR + dense operands of a step exceed the 126 MB L2; every kernel of a "
+                         "step streams more than L2 between two uses of the same buffer)"}
 
 
 # --------------------------------------------------------------------------------------
-# own arm
+# own arm, one GPU
 # --------------------------------------------------------------------------------------
+class Level:
+    """One GCN + its graph + its fused trainer on the device."""
+
+    def __init__(self, label, shape, hier, seed, dev, fuse_adam=True):
+        from pytextgcn_b200 import GCN
+        from pytextgcn_b200.graph import upload_graph
+        from pytextgcn_b200.synthetic import make_graph
+        from pytextgcn_b200.trainer import TextGCNTrainer
+        self.label, self.shape, self.hier = label, shape, hier
+        g = make_graph(shape, seed=seed, hierarchy_classes=hier)
+        self.g = g
+        self.n, self.in_ch = int(g.x.shape[0]), int(g.x.shape[1])
+        # graph upload (one-off, like g.to(device) in flat_amazon.py:86)
+        self.ei_host = g.edge_index.T.contiguous().pin_memory()      # the (E,2) storage the reference's coo.T views
+        self.ea_host = g.edge_attr.pin_memory()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ei_dev = self.ei_host.to(dev, non_blocking=True).T
+        ea_dev = self.ea_host.to(dev, non_blocking=True)
+        self.graph = upload_graph(ei_dev, ea_dev, self.n)
+        self.graph._symmetric = None
+        self.sym = self.graph.is_symmetric()
+        torch.cuda.synchronize()
+        self.upload_ms = (time.perf_counter() - t0) * 1e3
+        gd = g.clone()
+        gd.edge_index, gd.edge_attr = ei_dev, ea_dev
+        self.gd = gd.to(dev)
+        torch.manual_seed(seed)
+        self.gcn = GCN(self.in_ch, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=shape.dropout).to(dev).float()
+        self.tr = TextGCNTrainer(self.gcn, self.gd, lr=shape.lr, amsgrad=shape.amsgrad, seed=seed, graph=self.graph,
+                                 fuse_adam=fuse_adam, keep_w1_grad=False)
+
+    def epoch(self):
+        self.tr.train_step()
+        self.tr.eval_step()
+
+    def kernels_per_epoch(self):
+        tr = self.tr
+        return (tr.launches_per_train_step_reuse or tr.launches_per_train_step) + tr.launches_per_eval
+
+    def time_spmm(self, F: int, k: int, warm: int = 3) -> float:
+        """Mean device time of the propagation kernel at width F (CUDA events around the launch, on the launch stream).
+        A whole eval pass runs between two timed launches, so the CSR (>L2 together with the operands) is cold."""
+        from pytextgcn_b200 import ops
+        tr = self.tr
+        if F == tr.H:
+            B = self.gcn.layers[0].weight.data[:self.n] if tr.XW is None else tr.XW
+            kw = dict(out=tr.H1, bias=self.gcn.layers[0].bias.data)
+        else:
+            B, kw = tr.P, dict(out=tr.Z2, bias=self.gcn.layers[1].bias.data)
+        evs = []
+        for _ in range(warm + k):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.spmm(self.graph, B, F=F, plan=tr.plan, **kw)
+            b.record()
+            tr.eval_step()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        tr.invalidate_cache()
+        return float(np.mean([a.elapsed_time(b) for a, b in evs[warm:]]))
+
+
+def dropin_loop(level: Level, k: int, dev):
+    """The reference's own training loop (flat_amazon.py:99-117) on the drop-in module: gcn(g)[mask] ->
+    CrossEntropyLoss -> loss.backward() -> torch.optim.Adam.step() -> eval forward -> val loss -> .cpu() argmax ->
+    host accuracy -> loss.item().  Wall-clock per epoch, host syncs included."""
+    from pytextgcn_b200 import GCN
+    shape, g = level.shape, level.gd
+    torch.manual_seed(1)
+    gcn = GCN(level.in_ch, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=shape.dropout).to(dev).float()
+    criterion = torch.nn.CrossEntropyLoss(reduction="mean")
+    optimizer = torch.optim.Adam(gcn.parameters(), lr=shape.lr, amsgrad=shape.amsgrad)
+    y_val, y_train = g.y[g.val_mask].cpu().numpy(), g.y[g.train_mask].cpu().numpy()
+
+    def epoch():
+        gcn.train()
+        outputs = gcn(g)[g.train_mask]
+        loss = criterion(outputs, g.y[g.train_mask])
+        optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        optimizer.step()
+        gcn.eval()
+        with torch.no_grad():
+            logits = gcn(g)
+            val_loss = criterion(logits[g.val_mask], g.y[g.val_mask])
+            pred_val = np.argmax(logits[g.val_mask].cpu().numpy(), axis=1)
+            pred_train = np.argmax(logits[g.train_mask].cpu().numpy(), axis=1)
+            acc_val = float((pred_val == y_val).mean())
+            acc_train = float((pred_train == y_train).mean())
+        return loss.item(), val_loss.item(), acc_train, acc_val
+    for _ in range(3):
+        epoch()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        last = epoch()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / k
+    return {"epochs_per_s": 1e3 / ms, "ms_per_epoch": ms, "epochs": k, "last": {"loss": last[0], "acc_val": last[3]},
+            "what": "flat_amazon.py:99-117 verbatim on pytextgcn_b200.GCN + torch.optim.Adam + CrossEntropyLoss, host metrics and "
+                    "loss.item() included (no TextGCNTrainer, no CUDA graph)"}
+
+
+def other_shape_record(label, shape, hier, seed, dev, k: int = 15):
+    """ms/epoch and propagation-kernel roofline fraction of another BASELINE config on this GPU."""
+    lv = Level(label, shape, hier, seed, dev)
+    for _ in range(6):
+        lv.epoch()
+    ms = device_timed(lv.epoch, k)
+    peak, _ = measured_peak()
+    F = shape.hidden
+    k_ms = lv.time_spmm(F, 6)
+    alg = spmm_alg_bytes(lv.graph.nnz, lv.n, F)
+    rec = {"n_nodes": lv.n, "nnz": lv.graph.nnz, "hidden": F, "n_classes": shape.n_classes, "hierarchy_feats": hier,
+           "ms_per_epoch": ms, "epochs_per_s": 1e3 / ms, "kernels_per_epoch": lv.kernels_per_epoch(),
+           "hidden_spmm_ms": k_ms, "hidden_spmm_frac_of_hbm_peak": alg / (k_ms * 1e-3) / 1e9 / peak,
+           "graph_upload_ms": lv.upload_ms}
+    del lv
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_own_arm(args):
     rank, local_rank, world = env_rank()
     if not torch.cuda.is_available():
@@ -239,158 +426,156 @@ def run_own_arm(args):
         from pytextgcn_b200.dist import run_distributed_bench
         return run_distributed_bench(args, rank, local_rank, world, dev)
 
-    from pytextgcn_b200 import GCN, _native
-    from pytextgcn_b200.graph import upload_graph
-    from pytextgcn_b200.synthetic import SHAPES, make_graph
-    from pytextgcn_b200.trainer import TextGCNTrainer
-    from pytextgcn_b200 import ops
-
+    from pytextgcn_b200 import _native
     lib = _native.load()
-    shape = SHAPES[args.workload]
-    K, W = args.steps, max(args.warmup, 3)
-    g = make_graph(shape, seed=args.seed)
-    n = int(g.x.shape[0])
-    cfg = workload_config(shape, g)
-
-    # ---- graph upload (one-off, like g.to(device) in flat_amazon.py:86) ----
-    ei_host = g.edge_index.T.contiguous().pin_memory()       # the (E,2) storage the reference's coo.T views
-    ea_host = g.edge_attr.pin_memory()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    ei_dev = ei_host.to(dev, non_blocking=True).T
-    ea_dev = ea_host.to(dev, non_blocking=True)
-    graph = upload_graph(ei_dev, ea_dev, n)
-    graph._symmetric = None
-    sym = graph.is_symmetric()
-    torch.cuda.synchronize()
-    upload_ms = (time.perf_counter() - t0) * 1e3
-    gd = g.clone() if hasattr(g, "clone") else g
-    gd.edge_index, gd.edge_attr = ei_dev, ea_dev
-    gd = gd.to(dev)
-
-    torch.manual_seed(args.seed)
-    gcn = GCN(n, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=shape.dropout).to(dev).float()
-    tr = TextGCNTrainer(gcn, gd, lr=shape.lr, amsgrad=shape.amsgrad, seed=args.seed, graph=graph,
-                        fuse_adam=not args.no_fuse_adam, keep_w1_grad=False)
+    K, W = args.steps, max(args.warmup, 5)     # >= 5: two eager passes + the CUDA-graph capture of each step variant
+    specs = resolve_workload(args.workload)
+    levels = [Level(label, shape, hier, args.seed, dev, fuse_adam=not args.no_fuse_adam) for label, shape, hier in specs]
+    lv0 = levels[-1]
+    shape, g, n, graph, tr = lv0.shape, lv0.g, lv0.n, lv0.graph, lv0.tr
+    cfg = workload_config(args.workload, specs, g)
 
     def epoch_device():
-        tr.train_step()
-        tr.eval_step()
+        for lv in levels:
+            lv.epoch()
 
     for _ in range(W):
         epoch_device()
     torch.cuda.synchronize()
+    est_ms = device_timed(epoch_device, 3)
+    rounds = max(1, int(np.ceil(MIN_TIMED_S * 1e3 / max(K * est_ms, 1e-6))))
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- timed region: K reference epochs, inputs resident in HBM ----
+    # ---- timed region: rounds x K reference epochs, inputs resident in HBM ----
     l0 = lib.tgcn_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
-    for _ in range(K):
+    for _ in range(rounds * K):
         epoch_device()
     ev1.record()
     torch.cuda.synchronize()
     ms_total = ev0.elapsed_time(ev1)
-    launches_eager_epoch = (tr.launches_per_train_step_reuse or tr.launches_per_train_step) + tr.launches_per_eval
-    ms_per_step = ms_total / K
+    kernels_per_epoch = sum(lv.kernels_per_epoch() for lv in levels)
+    ms_per_step = ms_total / (rounds * K)
     value = 1e3 / ms_per_step
 
-    # train-step only / eval only split (same graphs, device-timed)
-    def timed(fn, k):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); a.record()
-        for _ in range(k):
-            fn()
-        b.record(); torch.cuda.synchronize()
-        return a.elapsed_time(b) / k
-    ms_train = timed(tr.train_step, K)
-    ms_eval = timed(tr.eval_step, K)
-    # same epoch with the eval forward re-associated (A(A(XW1W2)+1 b1^T W2)+b2): reported beside the headline
-    tr.set_eval_mode("collapsed")
-    for _ in range(4):
-        tr.eval_step()
-    ms_eval_collapsed = timed(tr.eval_step, K)
-    ms_epoch_collapsed = timed(epoch_device, K)
-    tr.set_eval_mode("layered")
-    for _ in range(4):
-        tr.eval_step()
-
-    # ---- per-kernel timing of the dominant kernel (wide SpMM), CUDA events on the launch stream ----
-    F = shape.hidden
-    Bop = gcn.layers[0].weight.data[:n]
-    out = tr.H1d
-    evs = []
-    for i in range(W + K):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        ops.spmm(graph, Bop, F=F, plan=tr.plan, out=out, bias=gcn.layers[0].bias.data, drop_mode=ops.DROP_PHILOX,
-                 drop_p=shape.dropout, philox_seed=args.seed, philox_offset_dev=tr.step_dev)
-        b.record()
-        # the rest of a step runs between two launches of this kernel (evicts L2: > 1 GB streamed)
-        tr.eval_step()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in evs[W:]]))
-    alg = spmm_alg_bytes(graph.nnz, n, F)
-    peak, peak_src = measured_peak()
-    achieved = alg / (k_ms * 1e-3) / 1e9
-    prof = load_profile_traffic()
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": prof.get("dram_bytes_per_launch"),
-                "kernel": "k_spmm<float,32,2,false> (layer-1 propagation of the train step, F=%d, fused bias + Philox dropout epilogue)" % F,
-                "kernel_ms": k_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
-                "note": "algorithmic bytes count each dense row once; the kernel is bound by L2->SM gather bandwidth "
-                        "(nnz*F*4 = %.1f GB per launch), see DESIGN.md" % (graph.nnz * F * 4 / 1e9),
-                "l2_gather_gbs": graph.nnz * F * 4 / (k_ms * 1e-3) / 1e9}
-
-    # ---- e2e: same epoch through the public API with HOST buffers ----
-    y_pin = g.y.pin_memory()
-    tm_pin = g.train_mask.pin_memory()
-    vm_pin = g.val_mask.pin_memory()
-    pred_pin = torch.empty(n, dtype=torch.int32).pin_memory()
-    scal_pin = torch.empty(4, dtype=torch.float32).pin_memory()
-    y_np = g.y.numpy()
-    # row ids and labels of the (static) val / train rows, gathered once: the per-epoch host metric is then a
-    # 5.6 k / 11.3 k element gather + compare instead of two boolean-mask passes over all 61.6 k rows
-    vm_idx, tm_idx = np.flatnonzero(g.val_mask.numpy()), np.flatnonzero(g.train_mask.numpy())
-    y_vm, y_tm = y_np[vm_idx], y_np[tm_idx]
-    h2d = y_pin.numel() * 8 + tm_pin.numel() + vm_pin.numel()
-    d2h = pred_pin.numel() * 4 + 16
+    # ---- e2e: same epoch through the public API with HOST buffers (also inside the clock-sampled window) ----
+    e2e_state = []
+    for lv in levels:
+        gg = lv.g
+        st = dict(lv=lv, y_pin=gg.y.pin_memory(), tm_pin=gg.train_mask.pin_memory(), vm_pin=gg.val_mask.pin_memory(),
+                  pred_pin=torch.empty(lv.n, dtype=torch.int32).pin_memory(), scal_pin=torch.empty(4, dtype=torch.float32).pin_memory())
+        y_np = gg.y.numpy()
+        st["vm_idx"], st["tm_idx"] = np.flatnonzero(gg.val_mask.numpy()), np.flatnonzero(gg.train_mask.numpy())
+        st["y_vm"], st["y_tm"] = y_np[st["vm_idx"]], y_np[st["tm_idx"]]
+        e2e_state.append(st)
+    h2d = sum(st["y_pin"].numel() * 8 + st["tm_pin"].numel() + st["vm_pin"].numel() for st in e2e_state)
+    d2h = sum(st["pred_pin"].numel() * 4 + 16 for st in e2e_state)
 
     def epoch_e2e():
-        tr.y.copy_(y_pin, non_blocking=True)                # labels + masks: the per-call inputs of the loss
-        tr.train_mask.copy_(tm_pin, non_blocking=True)
-        tr.val_mask.copy_(vm_pin, non_blocking=True)
-        tr.train_step()
-        tr.eval_step()
-        pred_pin.copy_(tr.pred, non_blocking=True)
-        scal_pin[:2].copy_(tr.loss_train, non_blocking=True)
-        scal_pin[2:].copy_(tr.loss_val, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        p = pred_pin.numpy()
-        acc_val = float((p[vm_idx] == y_vm).mean())          # host metrics as flat_amazon.py:111-114
-        acc_tr = float((p[tm_idx] == y_tm).mean())
-        return float(scal_pin[0]), acc_tr, acc_val
+        out = None
+        for st in e2e_state:
+            t = st["lv"].tr
+            t.y.copy_(st["y_pin"], non_blocking=True)                # labels + masks: the per-call inputs of the loss
+            t.train_mask.copy_(st["tm_pin"], non_blocking=True)
+            t.val_mask.copy_(st["vm_pin"], non_blocking=True)
+            t.train_step()
+            t.eval_step()
+            st["pred_pin"].copy_(t.pred, non_blocking=True)
+            st["scal_pin"][:2].copy_(t.loss_train, non_blocking=True)
+            st["scal_pin"][2:].copy_(t.loss_val, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            p = st["pred_pin"].numpy()
+            acc_val = float((p[st["vm_idx"]] == st["y_vm"]).mean())          # host metrics as flat_amazon.py:111-114
+            acc_tr = float((p[st["tm_idx"]] == st["y_tm"]).mean())
+            out = (float(st["scal_pin"][0]), acc_tr, acc_val)
+        return out
     for _ in range(3):
         epoch_e2e()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(K):
+    for _ in range(rounds * K):
         last = epoch_e2e()
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / (rounds * K)
     clocks = sampler.stop()
     l1 = lib.tgcn_launch_count()
 
-    # kernels per epoch = kernel nodes of the two captured graphs (counted while capturing/eager)
-    gpu_launches = int(launches_eager_epoch * K)
+    # train-step only / eval only split (same graphs, device-timed; repeated train steps cannot reuse the eval's
+    # hidden activation, so train_step_ms is the stand-alone step with its own hidden-wide forward SpMM)
+    ms_train = device_timed(tr.train_step, K)
+    ms_eval = device_timed(tr.eval_step, K)
+    extra = {"train_step_ms": ms_train, "eval_ms": ms_eval, "train_steps_per_sec": 1e3 / ms_train,
+             "timed_steps": rounds * K, "timed_region_s": ms_total / 1e3,
+             "graph_upload_ms": sum(lv.upload_ms for lv in levels),
+             "graph_upload_h2d_bytes": int(sum(lv.ei_host.numel() * 8 + lv.ea_host.numel() * 4 for lv in levels)),
+             "nnz": graph.nnz, "symmetric": bool(lv0.sym),
+             "last_epoch": {"loss": last[0], "acc_train": last[1], "acc_val": last[2]},
+             "kernels_per_epoch": kernels_per_epoch, "lib_launch_counter_delta": int(l1 - l0), "cuda_graph": True,
+             "share_h1": bool(tr.share_h1)}
+    if len(levels) > 1:
+        extra["levels"] = {lv.label: {"ms_per_epoch": device_timed(lv.epoch, K), "n_classes": lv.shape.n_classes,
+                                      "hierarchy_feats": lv.hier} for lv in levels}
+    if tr.act == 0 and len(levels) == 1:
+        # same epoch with the eval forward re-associated (A(A(XW1W2)+1 b1^T W2)+b2): reported beside the headline
+        tr.set_eval_mode("collapsed")
+        for _ in range(4):
+            tr.eval_step()
+        extra["collapsed_eval"] = {"eval_ms": device_timed(tr.eval_step, K), "epoch_ms": device_timed(epoch_device, K),
+                                   "note": "eval forward re-associated as A(A(X W1 W2) + 1 b1^T W2) + b2 (no activation in the "
+                                           "reference model); NOT the headline, which keeps the reference's layer order"}
+        tr.set_eval_mode("layered")
+        for _ in range(4):
+            tr.eval_step()
+
+    # ---- dominant kernel (hidden-wide propagation) and the class-wide one, CUDA events on the launch stream ----
+    F = shape.hidden
+    k_ms = lv0.time_spmm(F, max(K, 10))
+    n_ms = lv0.time_spmm(tr.Cp, max(K, 10))
+    alg = spmm_alg_bytes(graph.nnz, n, F)
+    alg_n = spmm_alg_bytes(graph.nnz, n, tr.Cp)
+    peak, peak_src = measured_peak()
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    prof = load_profile_traffic()
+    wide_per_epoch = 2 if tr.share_h1 else 3
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": prof.get("dram_bytes_per_launch"),
+                "traffic_source": prof.get("source", None),
+                "kernel": "k_spmm<float,32,2,*> hidden-wide propagation A_hat (X W1) + b1, F=%d (%d launches per epoch: eval "
+                          "forward -- shared with the next train forward -- and the backward that carries W1's Adam update)" % (F, wide_per_epoch),
+                "kernel_ms": k_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
+                "share_of_epoch": wide_per_epoch * k_ms / ms_per_step,
+                "note": "algorithmic bytes count each dense row once; the kernel is bound by L2->SM gather bandwidth "
+                        "(nnz*F*4 = %.1f GB per launch), see DESIGN.md" % (graph.nnz * F * 4 / 1e9),
+                "l2_gather_gbs": graph.nnz * F * 4 / (k_ms * 1e-3) / 1e9}
+    extra["narrow_spmm"] = {"kernel_ms": n_ms, "F": tr.Cp, "algorithmic_bytes": alg_n, "frac": alg_n / (n_ms * 1e-3) / 1e9 / peak,
+                            "launches_per_epoch": 3}
+
+    graphs_host = [lv.g for lv in levels]
+    if not args.no_extras:
+        try:
+            extra["dropin"] = dropin_loop(lv0, 10, dev)
+        except Exception as e:
+            extra["dropin"] = {"error": repr(e)}
+        others = {}
+        del levels, e2e_state, lv0, tr, graph
+        torch.cuda.empty_cache()
+        for name in [s for s in args.other_shapes.split(",") if s]:
+            try:
+                if name == args.workload:
+                    continue
+                for label, sh, hier in resolve_workload(name):
+                    others[label] = other_shape_record(label, sh, hier, args.seed, dev)
+            except Exception as e:
+                others[name] = {"error": repr(e)}
+        extra["other_shapes"] = others
 
     cpu_info = None
     if not args.no_cpu_baseline:
         try:
-            _, cpu_info = cpu_reference_epochs(g, shape, steps=2, warmup=1, budget_s=45.0, seed=args.seed)
+            cpu_info = cpu_reference_workload(specs, args.seed, args.cpu_budget, graphs_host)
         except Exception as e:  # the baseline must never take the GPU number down with it
             cpu_info = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
@@ -404,19 +589,11 @@ def run_own_arm(args):
                 "note": "TextGCNTrainer.train_step()+eval_step() per epoch; labels/masks copied from pinned host memory "
                         "every epoch, argmax + losses read back and accuracy computed on the host; the graph itself is "
                         "uploaded once (g.to(device), flat_amazon.py:86): see graph_upload_ms"},
-        "gpu_launches": gpu_launches,
+        "gpu_launches": int(kernels_per_epoch * rounds * K),
+        "timed_steps": rounds * K,
         "roofline": roofline,
         "cpu_baseline": cpu_info,
-        "extra": {"train_step_ms": ms_train, "eval_ms": ms_eval, "train_steps_per_sec": 1e3 / ms_train,
-                  "collapsed_eval": {"eval_ms": ms_eval_collapsed, "epoch_ms": ms_epoch_collapsed,
-                                     "epochs_per_sec": 1e3 / ms_epoch_collapsed,
-                                     "note": "eval forward re-associated as A(A(X W1 W2) + 1 b1^T W2) + b2 (no activation in the "
-                                             "reference model); NOT the headline, which keeps the reference's layer order"},
-                  "graph_upload_ms": upload_ms, "graph_upload_h2d_bytes": int(ei_host.numel() * 8 + ea_host.numel() * 4),
-                  "nnz": graph.nnz, "symmetric": bool(sym), "last_epoch": {"loss": last[0], "acc_train": last[1], "acc_val": last[2]},
-                  "kernels_per_epoch": launches_eager_epoch, "lib_launch_counter_delta": int(l1 - l0),
-                  "cuda_graph": True,
-                  "share_h1": bool(tr.share_h1)},
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
 
@@ -430,6 +607,10 @@ def main():
     ap.add_argument("--workload", default="20ng")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=0.0,
+                    help="> 0: time the CPU arm on an edge-subsample sized to this many seconds and extrapolate (labelled)")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra.dropin / extra.other_shapes / extra.scale_config")
+    ap.add_argument("--other-shapes", default="r8,amazon,dbpedia-l3,scale")
     ap.add_argument("--no-cuda-graph", dest="no_cuda_graph", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-fused-stores", dest="no_fused_stores", action="store_true")

@@ -162,7 +162,7 @@ class DistTextGCNTrainer:
                  rank: int, world: int, dev: torch.device, seed: int = 0, betas=(0.9, 0.999), eps: float = 1e-8,
                  graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None,
                  use_cuda_graph: bool = False, exchange: str = "peer", fused_stores: bool = True,
-                 fuse_adam: bool = True, keep_w1_grad: bool = True):
+                 fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True):
         import torch.distributed as dist
         from . import ops
         from .graph import upload_graph
@@ -186,23 +186,38 @@ class DistTextGCNTrainer:
         self.plan = self.shard.plan()
         nl, npad, H, Cp = self.part.n_loc, self.part.n_pad, hidden, self.Cp
         f32 = dict(dtype=torch.float32, device=dev)
-        # exchange buffers: symmetric (peer-mapped) allocations when the NVLink path is available
+        # exchange buffers: symmetric (peer-mapped) allocations when the NVLink path is available.  The decision is
+        # COLLECTIVE: every rank tries to allocate all of them, the outcomes are all-reduced (MIN), and either every
+        # rank takes the peer path or every rank takes the NCCL path -- a rank falling back alone would deadlock the
+        # others in the device barrier.
         self.exchange, self.exchange_error, self.px = "nccl", None, None
+        n_small = H + H * n_classes + n_classes                              # packed grads of b1, W2, b2 (one exchange)
+        self.n_small = n_small
+        self.n_small_pad = (n_small + 3) // 4 * 4
+        xshapes = {"W1": (npad, H), "small": (world, self.n_small_pad), "Pt": (npad, Cp), "Pe": (npad, Cp),
+                   "dZ2": (npad, Cp), "dZ1": (npad, H)}
+        xbufs: Dict[str, torch.Tensor] = {}
         if world > 1 and exchange == "peer":
+            ok = 1
             try:
                 self.px = PeerExchange(dist.group.WORLD, rank, world, dev)
-                self.exchange = "peer"
+                for name, shp in xshapes.items():
+                    xbufs[name] = self.px.alloc(name, shp)
             except Exception as e:          # symmetric memory not available in this stack: NCCL collectives
                 self.exchange_error = repr(e)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                self.exchange = "peer"
+            else:
+                self.px, xbufs = None, {}
+                if self.exchange_error is None:
+                    self.exchange_error = "symmetric allocation failed on another rank"
 
         def xbuf(name, shape):
-            if self.px is not None:
-                try:
-                    return self.px.alloc(name, shape)
-                except Exception as e:
-                    self.exchange_error = repr(e)
-                    self.px, self.exchange = None, "nccl"
-            return torch.zeros(tuple(shape), **f32)
+            assert tuple(shape) == tuple(xshapes[name])
+            return xbufs[name] if name in xbufs else torch.zeros(tuple(shape), **f32)
         # parameters: same init on every rank (same seed), W1 kept in the NEW row order
         gen = torch.Generator().manual_seed(seed)
         if init_weights is None:
@@ -218,9 +233,6 @@ class DistTextGCNTrainer:
         lo = rank * nl
         self.W1_loc = self.W1_full[lo:lo + nl]                               # view: this rank's shard (authoritative)
         self.b1, self.W2, self.b2 = b1.to(dev), W2.to(dev).contiguous(), b2.to(dev)
-        n_small = H + H * n_classes + n_classes                              # packed grads of b1, W2, b2 (one exchange)
-        self.n_small = n_small
-        self.n_small_pad = (n_small + 3) // 4 * 4
         self.small_slots = xbuf("small", (world, self.n_small_pad))          # slot r = rank r's partial sums
         self.small_local = self.small_slots[rank]                             # dense_bwd writes my slot in place
         self.small = torch.zeros(self.n_small_pad, **f32)                     # summed over ranks
@@ -237,6 +249,11 @@ class DistTextGCNTrainer:
         self.fuse_adam, self.keep_w1_grad = bool(fuse_adam), bool(keep_w1_grad)
         # activations
         self.H1d = torch.empty((nl, H), **f32)
+        # pre-dropout hidden rows of the last eval forward, reused by the next train step (same W1/b1,
+        # flat_amazon.py:100-110): one hidden-wide SpMM less per epoch and per rank, bit-identical (trainer.py)
+        self.share_h1 = bool(share_h1)
+        self.H1 = torch.empty((nl, H), **f32) if (self.share_h1 and dropout > 0) else self.H1d
+        self._h1_valid = False
         self.Pt_full = xbuf("Pt", (npad, Cp))        # projected rows, train forward
         self.Pt_loc = self.Pt_full[lo:lo + nl]
         self.Pe_full = xbuf("Pe", (npad, Cp))        # projected rows, eval forward (double buffer)
@@ -247,7 +264,8 @@ class DistTextGCNTrainer:
         self.G2 = torch.zeros((nl, Cp), **f32)
         self.dZ1_full = xbuf("dZ1", (npad, H))
         self.dZ1_loc = self.dZ1_full[lo:lo + nl]
-        self.loss_part = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.loss_part = torch.zeros(2, dtype=torch.float64, device=dev)        # train step: sum nll, count (local rows)
+        self.loss_part_val = torch.zeros(2, dtype=torch.float64, device=dev)    # eval step
         self.loss_buf = torch.zeros(2, **f32)
         self.stats = torch.zeros(6, dtype=torch.float64, device=dev)         # packed scalars for one all-reduce
         self.pred = torch.zeros(nl, dtype=torch.int32, device=dev)
@@ -262,6 +280,9 @@ class DistTextGCNTrainer:
         self.train_mask = tm_new[lo:lo + nl].to(dev).contiguous()
         self.val_mask = vm_new[lo:lo + nl].to(dev).contiguous()
         self.n_train, self.n_val = int(g.train_mask.sum()), int(g.val_mask.sum())
+        used = g.train_mask.cpu() | g.val_mask.cpu()
+        if bool((used & ((g.y.cpu() < 0) | (g.y.cpu() >= n_classes))).any()):
+            raise RuntimeError(f"labels of masked rows must lie in [0, {n_classes})")
         self.w1_stale = False         # every rank initialised the full W1 identically
         self._w1_mirrored = False
         self._pending_reads = set()
@@ -273,6 +294,10 @@ class DistTextGCNTrainer:
         self.graph_error = None
         self.profile = None           # list of (name, event) when per-phase timing is on
         self.launches_per_epoch = 0
+        # every rank has finished zeroing / filling its symmetric buffers before any peer may store into them
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
 
     # ---- optional per-phase timing (eager mode only; used by the scaling analysis in DESIGN.md) ----
     def _mark(self, name: str) -> None:
@@ -358,19 +383,27 @@ class DistTextGCNTrainer:
     def _forward(self, training: bool) -> None:
         ops = self.ops
         self._mark("begin")
-        self._gather_w1()
-        self._mark("allgather_W1")
         drop = training and self.p > 0
-        ops.spmm(self.shard, self.W1_full, F=self.H, plan=self.plan, out=self.H1d, bias=self.b1,
-                 drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
-                 philox_offset_dev=self.step_dev if drop else None, row_id_offset=self.rank * self.part.n_loc)
-        self._note_read("W1")
-        self._mark("spmm_wide_fwd")
+        dkw = dict(drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
+                   philox_offset_dev=self.step_dev if drop else None, row_id_offset=self.rank * self.part.n_loc)
+        if training and self.share_h1 and self._h1_valid:
+            # the eval forward that preceded this step saw the same W1/b1: its rows only need this step's dropout mask
+            if drop:
+                ops.dropout_apply(self.H1, F=self.H, out=self.H1d, **dkw)
+            h = self.H1d
+            self._mark("dropout_apply")
+        else:
+            self._gather_w1()
+            self._mark("allgather_W1")
+            h = self.H1d if training else self.H1
+            ops.spmm(self.shard, self.W1_full, F=self.H, plan=self.plan, out=h, bias=self.b1, **dkw)
+            self._note_read("W1")
+            self._mark("spmm_wide_fwd")
         pname = "Pt" if training else "Pe"                       # double-buffered, see _pending_reads
         P_full, P_loc = (self.Pt_full, self.Pt_loc) if training else (self.Pe_full, self.Pe_loc)
         self._before_write(pname)
         mir = self._mirror(pname, P_loc, P_full)
-        ops.project(self.H1d, self.W2, K=self.H, out=P_loc, mirror=mir)     # layer 2's thin X W, stored to all ranks
+        ops.project(h, self.W2, K=self.H, out=P_loc, mirror=mir)     # layer 2's thin X W, stored to all ranks
         self._exchange(P_full, P_loc, pname, mir is not None)
         self._mark("allgather_P")
         ops.spmm(self.shard, P_full, F=self.Cp, plan=self.plan, out=self.Z2, bias=self.b2)
@@ -432,14 +465,16 @@ class DistTextGCNTrainer:
                             [s_[1] for s_ in self.st[1:]], [s_[2] for s_ in self.st[1:]], **kw)
         self._mark("adam")
         self.w1_stale = True
+        self._h1_valid = False
 
     def eval_step(self) -> None:
         ops = self.ops
         self._forward(False)
         ops.masked_nll(self.Z2, self.C, self.y, self.val_mask, max(self.n_val, 1), want_grad=False,
                        loss_out=self.loss_buf, workspace=self._nll_ws, pred=self.pred, correct=self.correct,
-                       partial=self.loss_part)
+                       partial=self.loss_part_val)
         self._mark("masked_nll")
+        self._h1_valid = self.share_h1
 
     def epoch(self) -> None:
         """train_step + eval_step; after two eager epochs the pair is captured (kernels AND the NCCL
@@ -482,7 +517,7 @@ class DistTextGCNTrainer:
     def epoch_stats(self) -> Dict[str, float]:
         """Global (all-reduced) train loss of the last train step is not kept here; this returns the
         val loss / accuracy of the last eval_step."""
-        s = torch.stack([self.loss_part[0], self.correct[0].double()])
+        s = torch.stack([self.loss_part_val[0], self.correct[0].double()])
         if self.world > 1:
             self.dist.all_reduce(s)
         v = s.cpu().tolist()
@@ -546,38 +581,114 @@ def shutdown(trainer: Optional["DistTextGCNTrainer"] = None) -> None:
 
 
 # --------------------------------------------------------------------------------------
+# the same graph in the partition's node numbering (parity reference for the N-rank path)
+# --------------------------------------------------------------------------------------
+def renumbered_data(g, part: RowPartition):
+    """`g` with its nodes renumbered into the partition's padded id space (padding ids = isolated nodes outside every
+    mask), so a single-GPU TextGCNTrainer on it sees exactly the rows, the within-row entry order and the global
+    Philox element indices the N ranks see: the single-GPU run is then the parity reference of the partitioned run."""
+    from .data import Data
+    new_id = part.new_id.cpu()
+    npad = part.n_pad
+    idx = torch.arange(npad, dtype=torch.int64)
+    x = torch.sparse_coo_tensor(torch.stack([idx, idx]), torch.ones(npad), size=(npad, npad), check_invariants=False).coalesce()
+    ei = new_id[g.edge_index.cpu().contiguous()]
+    return Data(x=x, edge_index=ei, edge_attr=g.edge_attr.cpu(), y=part.to_new(g.y.cpu(), 0),
+                train_mask=part.to_new(g.train_mask.cpu(), False), val_mask=part.to_new(g.val_mask.cpu(), False),
+                test_mask=part.to_new(g.test_mask.cpu(), False), n_vocab=getattr(g, "n_vocab", 0))
+
+
+def parity_against_single_gpu(g, shape, rank: int, world: int, dev: torch.device, seed: int, epochs: int = 5, **trainer_kw):
+    """Runs `epochs` epochs of a FRESH N-rank trainer in its shipped configuration (CUDA graph from the third epoch on,
+    multicast stores fused into the producers, dropout on) and, on rank 0, the same epochs of the single-GPU
+    TextGCNTrainer on the renumbered graph with the same seed and initial weights.  Returns on rank 0
+    {max_rel_err_loss, max_rel_err_W2, max_rel_err_W1, ...}.  Collective: every rank must call it."""
+    import torch.distributed as dist
+    from .models import GCN
+    from .trainer import TextGCNTrainer
+    n = int(g.x.shape[0])
+    tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad, rank, world, dev,
+                            seed=seed, **trainer_kw)
+    losses = []
+    for _ in range(epochs):
+        tr.epoch()
+        losses.append(tr.train_loss())                   # all-reduce of the per-rank partial sums
+    val = tr.epoch_stats()
+    params = tr.gathered_parameters()
+    graphed = tr._graph is not None
+    out = None
+    if rank == 0:
+        gen = torch.Generator().manual_seed(seed)        # the draw order of DistTextGCNTrainer.__init__
+        a1, a2 = (6.0 / (n + shape.hidden)) ** 0.5, (6.0 / (shape.hidden + shape.n_classes)) ** 0.5
+        W1 = (torch.rand(n, shape.hidden, generator=gen) * 2 - 1) * a1
+        W2 = (torch.rand(shape.hidden, shape.n_classes, generator=gen) * 2 - 1) * a2
+        gp = renumbered_data(g, tr.part).to(dev)
+        gcn = GCN(tr.part.n_pad, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=shape.dropout).to(dev)
+        with torch.no_grad():
+            gcn.layers[0].weight.copy_(tr.part.to_new(W1).to(dev))
+            gcn.layers[1].weight.copy_(W2.to(dev))
+            gcn.layers[0].bias.zero_(); gcn.layers[1].bias.zero_()
+        one = TextGCNTrainer(gcn, gp, lr=shape.lr, amsgrad=shape.amsgrad, seed=seed, use_cuda_graph=False, assume_symmetric=True)
+        ref_losses = []
+        for _ in range(epochs):
+            r = one.epoch()
+            ref_losses.append(r["loss"])
+
+        def rel(a, b):
+            return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+        out = {"epochs": epochs, "cuda_graph": graphed, "fused_stores": tr.fused_stores, "exchange": tr.exchange,
+               "dropout": shape.dropout,
+               "max_rel_err_loss": max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(losses, ref_losses)),
+               "max_rel_err_W2": rel(params["layers.1.weight"], gcn.layers[1].weight.data),
+               "max_rel_err_W1": rel(params["layers.0.weight"], tr.part.to_old(gcn.layers[0].weight.data)),
+               "val_loss": [val["val_loss"], r["val_loss"]],
+               "reference": "single-GPU TextGCNTrainer (eager) on the renumbered graph, same seed / weights / Philox indices"}
+        del one, gcn, gp
+    tr._graph = None
+    del tr
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # bench entry for N > 1 (called by bench.py under torchrun)
 # --------------------------------------------------------------------------------------
-def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: torch.device):
+def _timed_dist_workload(g, shape, args, rank, local_rank, world, dev, K, W, sample_clocks: bool):
+    """Warm-up, K device-timed epochs (max over ranks), then the same epochs end to end with host buffers."""
     import torch.distributed as dist
     from . import _native
-    from .synthetic import SHAPES, make_graph
     lib = _native.load()
-    shape = SHAPES[args.workload]
-    K, W = args.steps, max(args.warmup, 3)
-    g = make_graph(shape, seed=args.seed)          # same graph on every rank (same seed)
-    n = int(g.x.shape[0])
     tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad,
                             rank, world, dev, seed=args.seed, use_cuda_graph=not getattr(args, "no_cuda_graph", False),
                             exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False),
                             fuse_adam=not getattr(args, "no_fuse_adam", False), keep_w1_grad=False)
     epoch = tr.epoch
-
     for _ in range(W):
         epoch()
     torch.cuda.synchronize()
     dist.barrier()
+    # stretch the timed region to >= 1 s in whole multiples of K (same count on every rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(3):
+        epoch()
+    ev1.record()
+    torch.cuda.synchronize()
+    est = torch.tensor([ev0.elapsed_time(ev1) / 3], device=dev, dtype=torch.float64)
+    dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    rounds = max(1, int(-(-1000.0 // max(K * float(est.item()), 1e-6)))) if sample_clocks else 1
     sampler = None
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         from bench import ClockSampler
         sampler = ClockSampler(local_rank)
         sampler.start()
     l0 = lib.tgcn_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     dist.barrier()
     ev0.record()
-    for _ in range(K):
+    for _ in range(rounds * K):
         epoch()
     ev1.record()
     torch.cuda.synchronize()
@@ -586,8 +697,8 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = int(lib.tgcn_launch_count() - l0)
     if tr._graph is not None:
-        launches = tr.launches_per_epoch * K
-    ms_per_step = float(ms.item()) / K
+        launches = tr.launches_per_epoch * rounds * K
+    ms_per_step = float(ms.item()) / (rounds * K)
 
     # e2e: labels/masks from pinned host memory each epoch, losses + local argmax read back
     nl = tr.part.n_loc
@@ -606,35 +717,86 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
+    for _ in range(rounds * K):
         last = epoch_e2e()
     torch.cuda.synchronize()
     dist.barrier()
-    e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / K], device=dev, dtype=torch.float64)
+    e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / (rounds * K)], device=dev, dtype=torch.float64)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler is not None else None
     nnz_loc = torch.tensor([tr.shard.nnz], device=dev, dtype=torch.float64)
     nnz_all = [torch.zeros_like(nnz_loc) for _ in range(world)]
     dist.all_gather(nnz_all, nnz_loc)
+    rec = dict(ms_per_step=ms_per_step, e2e_ms=float(e2e.item()), launches=launches, timed_steps=rounds * K, clocks=clocks,
+               nl=nl, nnz_per_rank=[int(t.item()) for t in nnz_all], bytes_per_train_step=tr.bytes_per_train_step(),
+               last=last, cuda_graph=tr._graph is not None, graph_error=tr.graph_error, exchange=tr.exchange,
+               exchange_error=tr.exchange_error, fused_stores=tr.fused_stores, share_h1=tr.share_h1,
+               multicast=bool(tr.px is not None and any(tr.px.multicast.values())), launches_per_epoch=tr.launches_per_epoch)
+    tr._graph = None
+    del tr
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: torch.device):
+    import torch.distributed as dist
+    from .synthetic import SHAPES, make_graph
+    from bench import METRIC, UNIT, resolve_workload, workload_config
+    specs = resolve_workload(args.workload)
+    if len(specs) != 1 or specs[0][2] is not None:
+        raise NotImplementedError("the row-partitioned bench covers the flat workloads (x = I)")
+    label, shape, _ = specs[0]
+    K, W = args.steps, max(args.warmup, 5)
+    g = make_graph(shape, seed=args.seed)          # same graph on every rank (same seed)
+    main = _timed_dist_workload(g, shape, args, rank, local_rank, world, dev, K, W, sample_clocks=True)
+    extra = {"nnz_per_rank": main["nnz_per_rank"], "rows_per_rank": main["nl"],
+             "collective_bytes_received_per_rank_per_train_step": main["bytes_per_train_step"],
+             "last_epoch": main["last"], "cuda_graph": main["cuda_graph"], "cuda_graph_error": main["graph_error"],
+             "exchange": main["exchange"], "exchange_error": main["exchange_error"], "fused_stores": main["fused_stores"],
+             "multicast": main["multicast"], "share_h1": main["share_h1"], "timed_steps": main["timed_steps"],
+             "kernels_per_epoch": main["launches_per_epoch"]}
+    if not getattr(args, "no_extras", False):
+        # (1) the shipped N-rank configuration (CUDA graph + multimem stores + dropout) against the single-GPU trainer
+        try:
+            extra["parity"] = parity_against_single_gpu(
+                g, shape, rank, world, dev, args.seed, epochs=5, use_cuda_graph=not getattr(args, "no_cuda_graph", False),
+                exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False),
+                fuse_adam=not getattr(args, "no_fuse_adam", False), keep_w1_grad=False)
+        except Exception as e:
+            extra["parity"] = {"error": repr(e)}
+        # (2) the >= 1 M-node configuration north_star names for scaling, at this N
+        if args.workload != "scale":
+            try:
+                del g
+                sc = SHAPES["scale"]
+                gs = make_graph(sc, seed=args.seed)
+                r = _timed_dist_workload(gs, sc, args, rank, local_rank, world, dev, 10, 5, sample_clocks=False)
+                extra["scale_config"] = {"epochs_per_s": 1e3 / r["ms_per_step"], "ms_per_step": r["ms_per_step"], "steps": 10,
+                                         "n_nodes": int(gs.x.shape[0]), "n_edges": int(gs.edge_index.shape[1]),
+                                         "hidden": sc.hidden, "nnz_per_rank": r["nnz_per_rank"],
+                                         "collective_bytes_received_per_rank_per_train_step": r["bytes_per_train_step"],
+                                         "e2e_epochs_per_s": 1e3 / r["e2e_ms"], "cuda_graph": r["cuda_graph"]}
+                g = gs
+            except Exception as e:
+                extra["scale_config"] = {"error": repr(e)}
     if rank == 0:
-        from bench import METRIC, UNIT, workload_config
-        clocks = sampler.stop()
-        cfg = workload_config(shape, g)
+        g_cfg = make_graph(shape, seed=args.seed) if args.workload != "scale" and not getattr(args, "no_extras", False) else g
+        cfg = workload_config(args.workload, specs, g_cfg)
         cfg["parallelism"] = (f"1D row partition x{world} (snake order by nnz); exchange between layers: " +
-                              (("multimem stores fused into the producer kernels + device barrier" if tr.fused_stores else
-                                "peer-store push kernel into symmetric buffers + device barrier") if tr.exchange == "peer"
+                              (("multimem stores fused into the producer kernels + device barrier" if main["fused_stores"] else
+                                "peer-store push kernel into symmetric buffers + device barrier") if main["exchange"] == "peer"
                                else "NCCL all_gather_into_tensor"))
+        nl = main["nl"]
         line = {
-            "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": {"value": 1e3 / float(e2e.item()), "unit": UNIT, "h2d_bytes_per_step": int(nl * 10) * world,
-                    "d2h_bytes_per_step": int(nl * 4 + 16) * world, "ms_per_step": float(e2e.item())},
-            "gpu_launches": launches,
-            "extra": {"nnz_per_rank": [int(t.item()) for t in nnz_all], "rows_per_rank": nl,
-                      "collective_bytes_received_per_rank_per_train_step": tr.bytes_per_train_step(),
-                      "last_epoch": last, "cuda_graph": tr._graph is not None, "cuda_graph_error": tr.graph_error,
-                      "exchange": tr.exchange, "exchange_error": tr.exchange_error, "fused_stores": tr.fused_stores,
-                      "multicast": bool(tr.px is not None and any(tr.px.multicast.values()))},
+            "metric": METRIC, "value": 1e3 / main["ms_per_step"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": main["clocks"],
+            "e2e": {"value": 1e3 / main["e2e_ms"], "unit": UNIT, "h2d_bytes_per_step": int(nl * 10) * world,
+                    "d2h_bytes_per_step": int(nl * 4 + 16) * world, "ms_per_step": main["e2e_ms"]},
+            "gpu_launches": main["launches"], "timed_steps": main["timed_steps"],
+            "extra": extra,
         }
         print(json.dumps(line), flush=True)
-    shutdown(tr)
+    shutdown(None)

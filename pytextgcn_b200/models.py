@@ -109,13 +109,25 @@ def _identity_operand(W: torch.Tensor, feat: _FeatInfo) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # fused 2-layer TextGCN:  logits = A (drop(act(A (X W1) + b1)) W2) + b2
 # --------------------------------------------------------------------------------------
+class _HiddenCache:
+    """Pre-dropout hidden activation act(A_hat (X W1) + b1) of the last eval forward, keyed by the state of
+    W1/b1 (version counters + storage) and the graph.  The reference loop runs step -> eval -> next step
+    (flat_amazon.py:100-110): the eval forward of epoch k and the training forward of epoch k+1 see the same
+    W1/b1, and F.dropout comes after the product (models.py:20-23), so the next training forward only has to
+    apply its dropout mask -- bit-identical to recomputing the propagation."""
+    __slots__ = ("key", "h1")
+
+    def __init__(self):
+        self.key, self.h1 = None, None
+
+
 class _GCN2Function(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, W1, b1, W2, b2, graph: GraphCSR, feat: _FeatInfo, act: int, drop: DropoutSpec):
+    def forward(ctx, W1, b1, W2, b2, graph: GraphCSR, feat: _FeatInfo, act: int, drop: DropoutSpec,
+                cache: Optional[_HiddenCache] = None, cache_key=None):
         n = graph.n_nodes
         H, C = int(W1.shape[1]), int(W2.shape[1])
         Hp, Cp = ops.pad4(H), ops.pad4(C)
-        B1 = _identity_operand(W1, feat)
         if drop.mode == ops.DROP_MASK and int(drop.mask.shape[1]) != Hp:
             m = torch.zeros((n, Hp), dtype=torch.uint8, device=W1.device)     # pad the caller's keep-mask
             m[:, :drop.mask.shape[1]].copy_(drop.mask)
@@ -129,10 +141,16 @@ class _GCN2Function(torch.autograd.Function):
         P = torch.zeros((n, Cp), dtype=torch.float32, device=W1.device) if Cp != C else \
             torch.empty((n, Cp), dtype=torch.float32, device=W1.device)
         # layer 1: propagation + bias + (act) + dropout, layer 2's thin projection fused in the epilogue
-        fuse = C <= ops.FUSED_PROJ_MAX_CLASSES
-        H1d, _ = ops.spmm(graph, B1, F=Hp, bias=b1, act=act, drop_mode=drop.mode, drop_p=drop.p,
-                          keep_mask=drop.mask, philox_seed=drop.seed, philox_offset=drop.offset,
-                          W_proj=W2p if fuse else None, P=P if fuse else None)
+        hit = cache is not None and cache.h1 is not None and cache.key == cache_key
+        fuse = C <= ops.FUSED_PROJ_MAX_CLASSES and not hit
+        dkw = dict(drop_mode=drop.mode, drop_p=drop.p, keep_mask=drop.mask, philox_seed=drop.seed, philox_offset=drop.offset)
+        if hit:
+            H1d = cache.h1 if (drop.mode == ops.DROP_NONE or drop.p <= 0.0) else ops.dropout_apply(cache.h1, F=Hp, **dkw)
+        else:
+            B1 = _identity_operand(W1, feat)
+            H1d, _ = ops.spmm(graph, B1, F=Hp, bias=b1, act=act, W_proj=W2p if fuse else None, P=P if fuse else None, **dkw)
+            if cache is not None and (drop.mode == ops.DROP_NONE or drop.p <= 0.0):
+                cache.key, cache.h1 = cache_key, H1d          # pre-dropout activation of this parameter state
         if not fuse:
             ops.project(H1d, W2p, K=Hp, out=P)
         # layer 2: propagation of the projected rows + bias
@@ -170,7 +188,7 @@ class _GCN2Function(torch.autograd.Function):
             else:
                 ops.hier_backward(G1[:, :H].contiguous(), n, feat.n_vocab, feat.Fdoc, H, tail)
             dW1[n:].copy_(tail)
-        return dW1, r["db_hidden"][:H], r["dW2"][:H], r["db_out"], None, None, None, None
+        return dW1, r["db_hidden"][:H], r["dW2"][:H], r["db_out"], None, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------
@@ -281,6 +299,18 @@ class GCN(nn.Module):
         self._drop_calls = 0
         self.drop_mask_override = None    # list of bool keep-masks, one per hidden layer (parity tests)
         self.seed = None                  # Philox key; drawn from torch's generator on first use
+        self.share_hidden = True          # reuse the eval forward's hidden activation in the next training forward
+        self._hidden_cache = _HiddenCache()
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_hidden_cache"] = _HiddenCache()       # th.save(gcn) (flat_amazon.py:128) must not pickle a cached activation
+        return d
+
+    def invalidate_cache(self) -> None:
+        """Forget the cached hidden activation (needed only when W1/b1 are changed behind torch's back, e.g. through
+        raw device pointers; in-place torch ops such as optimizer.step() are seen through the version counters)."""
+        self._hidden_cache = _HiddenCache()
 
     def _dropout_spec(self, layer_idx: int) -> DropoutSpec:
         if not self.training or self.dropout <= 0.0:
@@ -304,7 +334,14 @@ class GCN(nn.Module):
         if len(self.layers) == 2 and feat is not None:
             graph = get_graph(g.edge_index, g.edge_attr, int(x.shape[0]), holder=g)
             l0, l1 = self.layers[0], self.layers[1]
-            return _GCN2Function.apply(l0.weight, l0.bias, l1.weight, l1.bias, graph, feat, act, self._dropout_spec(0))
+            cache, key = None, None
+            if self.share_hidden:
+                cache = getattr(self, "_hidden_cache", None)
+                if cache is None:                      # modules unpickled from an older checkpoint
+                    cache = self._hidden_cache = _HiddenCache()
+                key = (l0.weight._version, l0.bias._version, l0.weight.data_ptr(), l0.bias.data_ptr(), id(graph), act)
+            return _GCN2Function.apply(l0.weight, l0.bias, l1.weight, l1.bias, graph, feat, act, self._dropout_spec(0),
+                                       cache, key)
         # generic depth / dense features: layer by layer (activation/dropout as torch elementwise ops)
         for i, layer in enumerate(self.layers):
             x = layer(x, g.edge_index, g.edge_attr, n_vocab=n_vocab, holder=g)

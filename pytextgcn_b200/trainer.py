@@ -137,6 +137,12 @@ class TextGCNTrainer:
             self.val_mask.copy_(val_mask, non_blocking=True)
         n_train = int(train_mask.sum().item())
         n_val = int(val_mask.sum().item()) if val_mask is not None else 0
+        # labels of the rows the loss reads must be class ids (CrossEntropyLoss raises on anything else,
+        # flat_amazon.py:102); rows outside the masks may hold -1 (perlabel_amazon.py:108-109) and are never read
+        used = self.train_mask | self.val_mask
+        bad = used & ((self.y < 0) | (self.y >= self.C))
+        if bool(bad.any().item()):
+            raise RuntimeError(f"labels of masked rows must lie in [0, {self.C}): found {int(bad.sum().item())} outside")
         if getattr(self, "n_train", n_train) != n_train or getattr(self, "n_val", n_val) != n_val:
             self._graphs = {}      # the divisor is baked into the captured launches
             self._warm = {}
@@ -280,7 +286,9 @@ class TextGCNTrainer:
             self._run("train_reuse", lambda: self._train_body(True))
         else:
             self._run("train", self._train_body)
-        self._h1_key = None          # W1/b1 have just been updated
+        self._h1_key = None          # W1/b1 have just been updated ...
+        if hasattr(self.gcn, "invalidate_cache"):
+            self.gcn.invalidate_cache()   # ... through raw pointers: the module's own cache cannot see that
         return self.loss_train
 
     def eval_step(self) -> Dict[str, torch.Tensor]:

@@ -61,3 +61,23 @@ def test_two_rank_nccl_matches_oracle():
            "--master-port", "29633", os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_renumbered_single_gpu_run_is_the_oracle_of_the_partitioned_run(cuda):
+    """world_size 1 (runs on any box): the partitioned trainer with dropout, CUDA graph and the shared hidden
+    activation against the single-GPU trainer on the renumbered graph -- the check `bench.py --gpus N` prints."""
+    from pytextgcn_b200.dist import parity_against_single_gpu
+    from pytextgcn_b200.synthetic import make_graph, GraphShape
+    if not torch.distributed.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29641")
+        torch.distributed.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        shape = GraphShape("t", 500, 433, 8000, 20, 6, 32, dropout=0.5, amsgrad=True, lr=0.02)
+        g = make_graph(shape, seed=6)
+        par = parity_against_single_gpu(g, shape, 0, 1, cuda, seed=2, epochs=6, use_cuda_graph=True, keep_w1_grad=False)
+        assert par["cuda_graph"]
+        # one rank, same kernels, same order of every sum: bit-identical up to the plan's chunk length
+        assert par["max_rel_err_loss"] < 1e-5 and par["max_rel_err_W2"] < 1e-4 and par["max_rel_err_W1"] < 1e-4, par
+    finally:
+        torch.distributed.destroy_process_group()

@@ -238,3 +238,43 @@ def test_end_to_end_text_pipeline_learns(cuda, fast, monkeypatch):
     torch.manual_seed(0)
     acc_val, acc_test = mod.main()
     assert acc_val > 0.85 and acc_test > 0.85      # chance = 0.17
+
+
+def test_module_reuses_the_eval_hidden_activation_bit_identically(cuda):
+    """The reference loop (flat_amazon.py:99-117: step -> eval -> next step) on the drop-in module with
+    torch.optim.Adam: with share_hidden the training forward after an eval forward skips the hidden-wide
+    propagation.  Every loss and parameter must be bit-identical to the module without the cache."""
+    import io
+    from pytextgcn_b200 import GCN
+    from pytextgcn_b200.synthetic import make_graph
+    g = make_graph("small", seed=4).to(cuda)
+    n = int(g.x.shape[0])
+    runs = []
+    for share in (False, True):
+        torch.manual_seed(0)
+        gcn = GCN(n, 6, n_hidden_gcn=64, dropout=0.5).to(cuda)
+        gcn.share_hidden = share
+        gcn.seed = 123
+        opt = torch.optim.Adam(gcn.parameters(), lr=0.05, amsgrad=True)
+        crit = torch.nn.CrossEntropyLoss()
+        hist = []
+        for ep in range(5):
+            gcn.train()
+            loss = crit(gcn(g)[g.train_mask], g.y[g.train_mask])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            gcn.eval()
+            with torch.no_grad():
+                logits = gcn(g)
+                hist.append((loss.item(), crit(logits[g.val_mask], g.y[g.val_mask]).item()))
+        runs.append((hist, [p.detach().clone() for p in gcn.parameters()], logits.clone()))
+        if share:
+            assert gcn._hidden_cache.h1 is not None
+            buf = io.BytesIO()
+            torch.save(gcn, buf)                                  # whole-module save (flat_amazon.py:128)
+            assert buf.getbuffer().nbytes < 2 * sum(p.numel() * 4 for p in gcn.parameters())   # cache not pickled
+    assert runs[0][0] == runs[1][0]
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert torch.equal(a, b)
+    assert torch.equal(runs[0][2], runs[1][2])
