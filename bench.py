@@ -478,9 +478,7 @@ def run_own_arm(args):
         out = None
         for st in e2e_state:
             t = st["lv"].tr
-            t.y.copy_(st["y_pin"], non_blocking=True)                # labels + masks: the per-call inputs of the loss
-            t.train_mask.copy_(st["tm_pin"], non_blocking=True)
-            t.val_mask.copy_(st["vm_pin"], non_blocking=True)
+            t.update_inputs(st["y_pin"], st["tm_pin"], st["vm_pin"])   # labels + masks: the per-call inputs of the loss
             t.train_step()
             t.eval_step()
             st["pred_pin"].copy_(t.pred, non_blocking=True)

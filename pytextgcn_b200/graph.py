@@ -116,6 +116,37 @@ class GraphCSR:
         self._plans[key] = p
         return p
 
+    # ---- restrictions to the rows / columns a masked loss can reach ----
+    def plan_for_rows(self, row_mask: torch.Tensor, base: Optional[SpmmPlan] = None) -> SpmmPlan:
+        """The chunks of `base` (default: the whole-matrix plan) whose row is selected by the boolean `row_mask`:
+        the SpMM then computes exactly those output rows and leaves the others untouched.  Split rows keep
+        their scratch slots and arrival counters (a row is in or out as a whole)."""
+        base = base or self.plan()
+        keep = row_mask.to(self.device)[base.chunks[:, 0].to(torch.int64) - 0]
+        chunks = base.chunks[keep].contiguous()
+        return SpmmPlan(base.row_begin, base.row_end, base.chunk_nnz, chunks, int(chunks.shape[0]), base.split_rows,
+                        base.n_split_rows, base.n_slots, base.max_row_nnz, slot_owner=base.slot_owner,
+                        counters=base.counters, _scratch=base._scratch)
+
+    def select_columns(self, col_mask: torch.Tensor) -> "GraphCSR":
+        """CSR of the same rows with only the entries whose COLUMN is selected (entry order kept).  For an
+        operand that is zero outside the selected rows -- the loss gradient dZ2 outside the training rows --
+        A_hat B and this matrix times B are the same sums without the zero terms."""
+        keep = col_mask.to(self.device)[self.colidx.to(torch.int64)]
+        rows = self.row_ids()[keep]
+        counts = torch.bincount(rows, minlength=self.n_nodes)
+        rowptr = torch.zeros(self.n_nodes + 1, dtype=torch.int32, device=self.device)
+        rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        sub = GraphCSR(self.n_nodes, rowptr, self.colidx[keep].contiguous(), self.val[keep].contiguous(), self.dis,
+                       n_cols=self.n_cols)
+        sub._symmetric = False
+        return sub
+
+    def plan_nonempty(self, chunk_nnz: Optional[int] = DEFAULT_CHUNK_NNZ) -> SpmmPlan:
+        """Plan over the rows that hold at least one entry (rows without entries are never written)."""
+        nonempty = (self.rowptr[1:] - self.rowptr[:-1]) > 0
+        return self.plan_for_rows(nonempty, self.plan(chunk_nnz=chunk_nnz))
+
     # ---- transpose handling for the backward pass ----
     def row_ids(self) -> torch.Tensor:
         counts = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)

@@ -25,7 +25,7 @@ class TextGCNTrainer:
     def __init__(self, gcn: GCN, g, lr: float = 0.05, amsgrad: bool = True, betas=(0.9, 0.999), eps: float = 1e-8,
                  use_cuda_graph: bool = True, seed: int = 0, chunk_nnz: Optional[int] = None,
                  graph: Optional[GraphCSR] = None, assume_symmetric: bool = False, eval_mode: str = "layered",
-                 fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True):
+                 fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True, restrict_rows: bool = True):
         if len(gcn.layers) != 2:
             raise NotImplementedError("TextGCNTrainer fuses the 2-layer TextGCN (the configuration of every reference script)")
         l0, l1 = gcn.layers
@@ -44,6 +44,13 @@ class TextGCNTrainer:
         kw = {} if chunk_nnz is None else dict(chunk_nnz=chunk_nnz)
         self.plan = self.graph.plan(**kw)
         self.plan_t = self.plan if self.graph_t is self.graph else self.graph_t.plan(**kw)
+        # The loss and the metrics only ever read the logits of MASKED rows (gcn(g)[g.train_mask], logits[g.val_mask],
+        # flat_amazon.py:101,110-112), and the loss gradient dZ2 is zero outside the training rows.  With restrict_rows
+        # the class-wide propagations skip what nothing reads: the forward computes the logits of the rows selected by
+        # any of the masks (train | val | test -- the document rows), the backward multiplies only the columns that
+        # carry a non-zero gradient.  Same sums without the terms that are exactly zero; `logits`/`pred` are then
+        # defined on masked rows only (eval_step(full=True) computes every row).
+        self.restrict_rows = bool(restrict_rows)
         self.lr, self.amsgrad, self.betas, self.eps = float(lr), bool(amsgrad), betas, float(eps)
         self.act = ops.ACT_RELU if gcn.apply_activation else ops.ACT_NONE
         self.p = float(gcn.dropout)
@@ -100,9 +107,9 @@ class TextGCNTrainer:
         self.T = torch.zeros((n, Cp), **f32)          # collapsed eval: A_hat Q + 1 (b1^T W2)
         self.c_row = torch.zeros((1, Cp), **f32)
         self.eval_mode = "layered"
-        self.set_masks(g.y, g.train_mask, getattr(g, "val_mask", None))
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._warm: Dict[str, int] = {}
+        self.set_masks(g.y, g.train_mask, getattr(g, "val_mask", None), getattr(g, "test_mask", None))
         self.launches_per_train_step = 0
         self.launches_per_train_step_reuse = 0
         self.launches_per_eval = 0
@@ -124,34 +131,68 @@ class TextGCNTrainer:
         self.eval_mode = mode
 
     # ---- labels / masks (per-call inputs of the loss, flat_amazon.py:101-102,110) ----
-    def set_masks(self, y: torch.Tensor, train_mask: torch.Tensor, val_mask: Optional[torch.Tensor]) -> None:
-        """Copies into static device buffers (so captured graphs stay valid) and recounts."""
+    def set_masks(self, y: torch.Tensor, train_mask: torch.Tensor, val_mask: Optional[torch.Tensor],
+                  test_mask: Optional[torch.Tensor] = None) -> None:
+        """Copies labels and masks into static device buffers (so captured graphs stay valid), recounts, and
+        rebuilds the mask-dependent work lists when a mask changed.  One host sync."""
         dev = self.dev
-        if not hasattr(self, "y"):
+        first = not hasattr(self, "y")
+        if first:
             self.y = torch.empty(self.n, dtype=torch.int64, device=dev)
-            self.train_mask = torch.empty(self.n, dtype=torch.bool, device=dev)
+            self.train_mask = torch.zeros(self.n, dtype=torch.bool, device=dev)
             self.val_mask = torch.zeros(self.n, dtype=torch.bool, device=dev)
+            self.test_mask = torch.zeros(self.n, dtype=torch.bool, device=dev)
+        old = None if first else (self.train_mask.clone(), self.val_mask.clone(), self.test_mask.clone())
         self.y.copy_(y, non_blocking=True)
         self.train_mask.copy_(train_mask, non_blocking=True)
         if val_mask is not None:
             self.val_mask.copy_(val_mask, non_blocking=True)
-        n_train = int(train_mask.sum().item())
-        n_val = int(val_mask.sum().item()) if val_mask is not None else 0
+        if test_mask is not None:
+            self.test_mask.copy_(test_mask, non_blocking=True)
+        n_train = int(self.train_mask.sum().item())
+        n_val = int(self.val_mask.sum().item())
         # labels of the rows the loss reads must be class ids (CrossEntropyLoss raises on anything else,
         # flat_amazon.py:102); rows outside the masks may hold -1 (perlabel_amazon.py:108-109) and are never read
         used = self.train_mask | self.val_mask
         bad = used & ((self.y < 0) | (self.y >= self.C))
         if bool(bad.any().item()):
             raise RuntimeError(f"labels of masked rows must lie in [0, {self.C}): found {int(bad.sum().item())} outside")
-        if getattr(self, "n_train", n_train) != n_train or getattr(self, "n_val", n_val) != n_val:
-            self._graphs = {}      # the divisor is baked into the captured launches
+        changed = first or not all(torch.equal(a, b) for a, b in zip(old, (self.train_mask, self.val_mask, self.test_mask)))
+        if getattr(self, "n_train", n_train) != n_train or getattr(self, "n_val", n_val) != n_val or (changed and self.restrict_rows):
+            self._graphs = {}      # the divisor / the work lists are baked into the captured launches
             self._warm = {}
         self.n_train, self.n_val = n_train, n_val
         if n_train == 0:
             raise RuntimeError("train_mask selects no rows")
+        if changed:
+            self._build_restricted()
+
+    def _build_restricted(self) -> None:
+        if not self.restrict_rows:
+            self.plan_z2, self.graph_g2, self.plan_g2 = self.plan, self.graph_t, self.plan_t
+            return
+        rows = self.train_mask | self.val_mask | self.test_mask
+        self.plan_z2 = self.graph.plan_for_rows(rows, self.plan)                 # logits of the masked rows
+        self.graph_g2 = self.graph_t.select_columns(self.train_mask)             # A_hat^T restricted to the columns where dZ2 != 0
+        self.plan_g2 = self.graph_g2.plan_nonempty()
+        self.G2.zero_()                                                          # rows without such a column stay zero
+        self.Z2.zero_()
+
+    def update_inputs(self, y_host: torch.Tensor, train_mask_host: torch.Tensor, val_mask_host: torch.Tensor) -> None:
+        """Per-epoch inputs of the loss from (pinned) HOST memory: asynchronous H2D copies into the static buffers.
+        The masks are compared with the previous call's on the host (a few microseconds); only a changed mask goes
+        through set_masks (recount + rebuild of the restricted work lists)."""
+        last = getattr(self, "_host_masks", None)
+        if last is not None and torch.equal(last[0], train_mask_host) and torch.equal(last[1], val_mask_host):
+            self.y.copy_(y_host, non_blocking=True)
+            self.train_mask.copy_(train_mask_host, non_blocking=True)
+            self.val_mask.copy_(val_mask_host, non_blocking=True)
+            return
+        self.set_masks(y_host, train_mask_host, val_mask_host)
+        self._host_masks = (train_mask_host.clone(), val_mask_host.clone())
 
     # ---- the step bodies (eager; captured once warmed up) ----
-    def _forward_collapsed(self) -> None:
+    def _forward_collapsed(self, full: bool = False) -> None:
         l0, l1 = self.gcn.layers
         W1, b1, W2, b2 = l0.weight.data, l0.bias.data, l1.weight.data, l1.bias.data
         if self.feat.Fdoc is not None:
@@ -162,7 +203,7 @@ class TextGCNTrainer:
         ops.project(B1, W2, K=self.H, out=self.Q)                       # Q = (X W1) W2
         ops.project(b1.view(1, self.H), W2, K=self.H, out=self.c_row)    # c = b1^T W2
         ops.spmm(self.graph, self.Q, F=self.Cp, plan=self.plan, out=self.T, bias=self.c_row[0, :self.C])
-        ops.spmm(self.graph, self.T, F=self.Cp, plan=self.plan, out=self.Z2, bias=b2)
+        ops.spmm(self.graph, self.T, F=self.Cp, plan=self.plan if full else self.plan_z2, out=self.Z2, bias=b2)
 
     def _param_key(self):
         l0 = self.gcn.layers[0]
@@ -173,11 +214,11 @@ class TextGCNTrainer:
         in-place torch ops on the Parameters such as load_state_dict are detected through their version counters)."""
         self._h1_key = None
 
-    def _forward(self, training: bool, reuse_h1: bool = False) -> None:
+    def _forward(self, training: bool, reuse_h1: bool = False, full: bool = False) -> None:
         l0, l1 = self.gcn.layers
         W1, b1, W2, b2 = l0.weight.data, l0.bias.data, l1.weight.data, l1.bias.data
         if not training and self.eval_mode == "collapsed":
-            self._forward_collapsed()
+            self._forward_collapsed(full)
             return
         drop = training and self.p > 0.0
         dkw = dict(drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
@@ -199,7 +240,7 @@ class TextGCNTrainer:
                      W_proj=W2 if fuse else None, P=self.P if fuse else None, **dkw)
         if not fuse:
             ops.project(h_out, W2, K=self.H, out=self.P)
-        ops.spmm(self.graph, self.P, F=self.Cp, plan=self.plan, out=self.Z2, bias=b2)
+        ops.spmm(self.graph, self.P, F=self.Cp, plan=self.plan if full else self.plan_z2, out=self.Z2, bias=b2)
 
     def _train_body(self, reuse_h1: bool = False) -> None:
         l0, l1 = self.gcn.layers
@@ -207,7 +248,7 @@ class TextGCNTrainer:
         self._forward(True, reuse_h1)
         ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2,
                        loss_out=self.loss_train, workspace=self._nll_ws)
-        ops.spmm(self.graph_t, self.dZ2, F=self.Cp, plan=self.plan_t, out=self.G2)
+        ops.spmm(self.graph_g2, self.dZ2, F=self.Cp, plan=self.plan_g2, out=self.G2)
         drop = self.p > 0.0
         r = ops.dense_bwd(self.G2, self.H1d, W2, self.dZ2, H=self.H, n_classes=self.C, act=self.act,
                           drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p,
@@ -233,10 +274,10 @@ class TextGCNTrainer:
         ops.adam_step_small([p_.data for p_ in self.params[1:]], self.grads[1:], self.exp_avg[1:], self.exp_avg_sq[1:],
                             self.max_exp_avg_sq[1:], **kw)
 
-    def _eval_body(self) -> None:
-        """eval forward, val loss, argmax of every row, #correct on the val and train rows
+    def _eval_body(self, full: bool = False) -> None:
+        """eval forward, val loss, argmax, #correct on the val and train rows
         (flat_amazon.py:107-114 without the D2H copies)."""
-        self._forward(False)
+        self._forward(False, full=full)
         if self.n_val > 0:
             ops.masked_nll(self.Z2, self.C, self.y, self.val_mask, self.n_val, want_grad=False,
                            loss_out=self.loss_val, workspace=self._nll_ws, pred=self.pred, correct=self.correct_val)
@@ -291,10 +332,14 @@ class TextGCNTrainer:
             self.gcn.invalidate_cache()   # ... through raw pointers: the module's own cache cannot see that
         return self.loss_train
 
-    def eval_step(self) -> Dict[str, torch.Tensor]:
-        """Eval forward + val loss + on-device argmax/accuracy counts (device tensors, no sync)."""
+    def eval_step(self, full: bool = False) -> Dict[str, torch.Tensor]:
+        """Eval forward + val loss + on-device argmax/accuracy counts (device tensors, no sync).  `logits` / `pred`
+        hold the rows selected by any of the masks; full=True computes the logits of every row (word rows included)."""
         self.gcn.eval()
-        self._run("eval", self._eval_body)
+        if full and self.restrict_rows:
+            self._run("eval_full", lambda: self._eval_body(True))
+        else:
+            self._run("eval", self._eval_body)
         if self.share_h1 and self.eval_mode == "layered":
             self._h1_key = self._param_key()      # H1 now holds act(A_hat (X W1) + b1) for the current W1/b1
         return dict(logits=self.logits, val_loss=self.loss_val, pred=self.pred, correct_val=self.correct_val,

@@ -87,18 +87,19 @@ def test_fused_training_epochs_at_full_size(big, cuda):
     assert losses[0] == losses[1]                                   # identical run-to-run
     # layered and re-associated eval forward agree at full size too
     tr.set_eval_mode("layered")
-    z1 = tr.eval_step()["logits"].clone()
+    z1 = tr.eval_step(full=True)["logits"].clone()
     tr.set_eval_mode("collapsed")
-    z2 = tr.eval_step()["logits"].clone()
+    z2 = tr.eval_step(full=True)["logits"].clone()
     assert rel_err(z2, z1) < 1e-5
 
 
 def test_full_train_step_and_eval_against_the_oracle_at_full_size(big, cuda):
     """One whole training step (forward with an explicit dropout keep-mask, masked cross-entropy, backward)
     and the eval forward on the BASELINE 20NG-shape graph, compared element for element with
-    oracle.gcn_oracle (the restated GCNConv path, flat_amazon.py:99-110): logits, loss and all four
-    gradients within 1e-5 relative (max-norm).  The oracle materialises the (E+N) x 200 message tensors
-    (~17 GB each), so this needs ~50 GB of host memory and ~1 min of CPU time."""
+    oracle.gcn_oracle (the restated GCNConv path, flat_amazon.py:99-110) and with an fp64 evaluation of the same
+    formulas: logits, loss and all four gradients within 1e-5 relative (max-norm) of fp64, within 2e-5 of the fp32
+    oracle (whose own rounding at this size is measured).  The oracle materialises the (E+N) x 200 message tensors
+    (~17 GB each), so this needs ~40 GB of host memory and ~1 min of CPU time."""
     from pytextgcn_b200 import GCN
     g, n, csr, ei, ea = big
     H, C, p = 200, 20, 0.5
@@ -131,17 +132,50 @@ def test_full_train_step_and_eval_against_the_oracle_at_full_size(big, cuda):
     del z, loss
     torch.cuda.empty_cache()
 
-    # ---- oracle ----
+    # ---- fp64 evaluation of the same formulas (torch sparse CSR on the device, values = gcn_norm's fp32 A_hat):
+    #      the yardstick for "whose rounding is it" at this size ----
+    rowptr, col, val, _, _ = O.csr_from_gcn_norm(g.edge_index, g.edge_attr, n)
+    rows = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    A64 = torch.sparse_coo_tensor(torch.stack([rows, col]).to(cuda), val.double().to(cuda), size=(n, n)).coalesce()
+    P64 = [p_.detach().double().to(cuda).requires_grad_() for p_ in ref.parameters()]
+    keep64 = keep.to(cuda).double() * (1.0 / (1.0 - p))
+
+    def fwd64(train):
+        h = torch.sparse.mm(A64, P64[0]) + P64[1]
+        if train:
+            h = h * keep64
+        return torch.sparse.mm(A64, h @ P64[2]) + P64[3]
+    z64 = fwd64(True)
+    l64 = torch.nn.functional.cross_entropy(z64[gd.train_mask], gd.y[gd.train_mask])
+    l64.backward()
+    g64 = [p_.grad.cpu() for p_ in P64]
+    z64_train, l64 = z64.detach().cpu(), float(l64.item())
+    with torch.no_grad():
+        z64_eval = fwd64(False).cpu()
+    del A64, z64, keep64
+    torch.cuda.empty_cache()
+    # the CUDA path against fp64: logits, loss and every gradient within the 1e-5 bar
+    assert rel_err(z_train, z64_train) < 1e-5 and rel_err(z_eval, z64_eval) < 1e-5
+    assert abs(loss_train - l64) < 1e-5 * abs(l64)
+    for name, gm, g6 in zip(("W1", "b1", "W2", "b2"), grads, g64):
+        assert rel_err(gm, g6) < 1e-5, name
+
+    # ---- the oracle (fp32, CPU): sequential index_add over rows of up to 14 k terms carries ~1e-5 of rounding of its
+    #      own at this size (its distance to fp64 is asserted to be of that order), so two correct fp32 summation
+    #      orders can be 2e-5 apart; the CUDA path must be at least as close to fp64 as the oracle is ----
     ref.train()
     zr = ref(g, drop_masks=[keep])
     lr = O.masked_cross_entropy(zr, g.y, g.train_mask)
     lr.backward()
-    assert rel_err(z_train, zr.detach()) < 1e-5
+    e_oracle = rel_err(zr.detach(), z64_train)
+    assert e_oracle < 2e-5
+    assert rel_err(z_train, z64_train) <= max(e_oracle, 2e-6)
+    assert rel_err(z_train, zr.detach()) < 2e-5
     assert abs(loss_train - lr.item()) < 1e-5 * abs(lr.item())
     for name, gm, pr in zip(("W1", "b1", "W2", "b2"), grads, ref.parameters()):
-        assert rel_err(gm, pr.grad) < 1e-5, name
+        assert rel_err(gm, pr.grad) < 2e-5, name
     del zr, lr
     ref.eval()
     with torch.no_grad():
         zr = ref(g)
-    assert rel_err(z_eval, zr) < 1e-5
+    assert rel_err(z_eval, zr) < 2e-5

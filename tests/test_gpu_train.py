@@ -178,7 +178,7 @@ def test_collapsed_eval_matches_layered_eval_and_oracle(cuda, hier):
     for mode in ("layered", "collapsed"):
         tr.set_eval_mode(mode)
         for _ in range(4):                       # eager, eager, capture, replay
-            r = tr.eval_step()
+            r = tr.eval_step(full=True)
         out[mode] = (r["logits"].clone(), r["val_loss"].clone(), int(r["correct_val"].item()))
         assert rel_err(out[mode][0], z_ref) < 1e-5, mode
     assert rel_err(out["collapsed"][0], out["layered"][0]) < 1e-5
@@ -300,3 +300,34 @@ def test_shared_hidden_activation_is_bit_identical_and_saves_a_wide_spmm(cuda, g
     if not graph_mode:
         # 3 wide propagations per epoch without sharing; with it 2, plus one for the very first step and one after the edit
         assert wide_calls[False] == 18 and wide_calls[True] == 14
+
+
+
+@pytest.mark.parametrize("graph_mode", [False, True])
+def test_restricted_class_wide_propagations_change_nothing_that_is_read(cuda, graph_mode):
+    """restrict_rows: logits only for the rows a mask selects, backward only over the columns where dZ2 != 0.
+    Losses, accuracies, every gradient and the parameters must equal the unrestricted run (the skipped terms are
+    exact zeros); the masked rows of `logits`/`pred` must equal the full eval; changing a mask rebuilds the lists."""
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    res = {}
+    for restrict in (False, True):
+        g, gd, ref, mod, shape = _make_pair(cuda, p=0.5)
+        tr = TextGCNTrainer(mod, gd, lr=0.05, amsgrad=True, seed=11, restrict_rows=restrict, use_cuda_graph=graph_mode)
+        hist = [tuple(tr.epoch().values()) for _ in range(5)]
+        rows = gd.train_mask | gd.val_mask | gd.test_mask
+        masked_logits, masked_pred = tr.logits[rows].clone(), tr.pred[rows].clone()
+        full = tr.eval_step(full=True)["logits"].clone()
+        assert torch.equal(full[rows], masked_logits)
+        # move 50 validation rows into the training set: counts, divisor and work lists must follow
+        tm, vm = gd.train_mask.clone(), gd.val_mask.clone()
+        idx = torch.nonzero(vm).view(-1)[:50]
+        tm[idx], vm[idx] = True, False
+        tr.set_masks(gd.y, tm, vm, gd.test_mask)
+        hist += [tuple(tr.epoch().values()) for _ in range(4)]
+        res[restrict] = (hist, [g_.clone() for g_ in tr.grads], [p_.detach().clone() for p_ in mod.parameters()],
+                         masked_logits, masked_pred)
+    assert res[True][0] == res[False][0]
+    for k in (1, 2):
+        for a, b in zip(res[True][k], res[False][k]):
+            assert torch.equal(a, b)
+    assert torch.equal(res[True][3], res[False][3]) and torch.equal(res[True][4], res[False][4])
