@@ -133,8 +133,31 @@ typedef struct {
    * adam_param_mirror_mc: multicast mapping of the parameter (row-partitioned mode) or NULL. */
   float* adam_param; float* adam_exp_avg; float* adam_exp_avg_sq; float* adam_max_exp_avg_sq; int64_t adam_ld;
   const float* adam_hyper_dev; float adam_beta1; float adam_beta2; float adam_eps; void* adam_param_mirror_mc;
+  /* optional dense-tile contributions computed by tgcn_spmm_tc (2b): when tc_part != NULL the CSR holds only the
+   * entries OUTSIDE the dense tiles and, before the epilogue, row r adds part[s][tc_rank[r] % 128][:] for the slots
+   * s in [tc_slot_ptr[tc_rank[r] / 128], tc_slot_ptr[tc_rank[r] / 128 + 1]), in slot order. */
+  const float* tc_part; int64_t tc_ld; const int32_t* tc_rank; const int32_t* tc_slot_ptr;
 } tgcn_spmm_args;
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
+
+/* (2b) Dense-tile part of a hybrid propagation on the tensor cores (csrc/spmm_tc.cu).  The nodes are ranked by
+ * degree; the 128 x 32 blocks of A_hat (in rank space) that are dense enough are stored as dense TF32 hi/lo tiles and
+ * multiplied with tcgen05.mma (3xTF32: fp32 accuracy), everything else stays in the CSR that tgcn_spmm gathers.
+ * tgcn_spmm_tc packs the operand (transpose to K-major + hi/lo split, `Bt` workspace of
+ * tgcn_spmm_tc_workspace_elems floats) and writes one 128 x F partial result per unit into part[unit slot]; the
+ * following tgcn_spmm call (tc_part/tc_rank/tc_slot_ptr) adds them to the gathered remainder and runs the epilogue.
+ * Replaces GCNConv.propagate for the dense blocks (models.py:20).  Plan: pytextgcn_b200/tc_plan.py. */
+typedef struct {
+  const float* A_tiles;     /* [n_tiles][2][128][32] fp32, 128-byte swizzle pre-applied (see spmm_tc.cu) */
+  const int32_t* tile_kb;   /* [n_tiles] column block of each tile */
+  const int32_t* units;     /* [n_units][4] = {tile_begin, tile_end, slot, row_block}; empty units (begin == end) allowed */
+  int32_t n_units;
+  const int32_t* perm;      /* [n_col_blocks * 32] node id of each rank, -1 past the last node */
+  int32_t n_col_blocks;
+} tgcn_tc_plan;
+int tgcn_spmm_tc(const tgcn_tc_plan* plan, const float* B, int64_t ldb, int32_t F, float* Bt, float* part, int64_t ldp,
+                 void* stream);
+int tgcn_spmm_tc_workspace_elems(int32_t F, int64_t n_col_blocks, int64_t* bt_elems_out);
 
 /* ------------------------------------------------------------------------------------------
  * (3) Masked log-softmax / NLL and its gradient, one pass over the logits.

@@ -37,6 +37,15 @@ class SpmmArgs(C.Structure):
         ("adam_param", c_void), ("adam_exp_avg", c_void), ("adam_exp_avg_sq", c_void), ("adam_max_exp_avg_sq", c_void),
         ("adam_ld", C.c_int64), ("adam_hyper_dev", c_void), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float),
         ("adam_eps", C.c_float), ("adam_param_mirror_mc", c_void),
+        ("tc_part", c_void), ("tc_ld", C.c_int64), ("tc_rank", c_void), ("tc_slot_ptr", c_void),
+    ]
+
+
+class TcPlanArgs(C.Structure):
+    """Mirror of tgcn_tc_plan."""
+    _fields_ = [
+        ("A_tiles", c_void), ("tile_kb", c_void), ("units", c_void), ("n_units", C.c_int32),
+        ("perm", c_void), ("n_col_blocks", C.c_int32),
     ]
 
 
@@ -72,6 +81,8 @@ SIGNATURES = {
                                  c_void, C.c_size_t, c_void]),
     "tgcn_spmm_plan_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "tgcn_spmm": (C.c_int, [C.POINTER(SpmmArgs), c_void]),
+    "tgcn_spmm_tc": (C.c_int, [C.POINTER(TcPlanArgs), c_void, C.c_int64, C.c_int32, c_void, c_void, C.c_int64, c_void]),
+    "tgcn_spmm_tc_workspace_elems": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_int64)]),
     "tgcn_masked_nll": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int32, c_void, c_void, C.c_int64,
                                   c_void, c_void, c_void, C.c_int64, c_void, c_void, c_void,
                                   c_void, C.c_size_t, c_void]),

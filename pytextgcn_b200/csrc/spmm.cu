@@ -156,6 +156,27 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
       }
     }
   }
+  if constexpr (E == 4) {
+    if (p.tc_part != nullptr) {
+      // hybrid propagation: the dense blocks of this row were multiplied on the tensor cores (spmm_tc.cu); their
+      // partial rows are added here in slot order (fixed order: deterministic), once per row (last chunk of a split row)
+      const int rk = __ldg(p.tc_rank + ch.x);
+      const int s0 = __ldg(p.tc_slot_ptr + (rk >> 7)), s1 = __ldg(p.tc_slot_ptr + (rk >> 7) + 1);
+      if (lane < LPR) {
+        for (int sl = s0; sl < s1; ++sl) {
+          const float* src = p.tc_part + ((int64_t)sl * 128 + (rk & 127)) * p.tc_ld;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            const int c0 = (l + v * LPR) * E;
+            if (c0 < F) {
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(src + c0));
+              acc[v][0] += t.x; acc[v][1] += t.y; acc[v][2] += t.z; acc[v][3] += t.w;
+            }
+          }
+        }
+      }
+    }
+  }
   row_epilogue<LPR, VPL, E, EPI>(p, ch.x, lane, acc, smem_w);
   }
 }

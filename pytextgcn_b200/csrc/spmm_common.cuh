@@ -24,6 +24,8 @@ struct SpmmParams {
   // fused Adam/AMSGrad on the finished row (backward of layer 1 with X = I: the row IS dW1[row])
   float* ad_p; float* ad_m; float* ad_v; float* ad_x; int64_t ad_ld; const float* __restrict__ ad_hyp;
   float ad_b1, ad_b2, ad_eps; float* ad_mirror;
+  // dense-tile partial results of tgcn_spmm_tc, added to the row before the epilogue (hybrid propagation)
+  const float* __restrict__ tc_part; int64_t tc_ld; const int32_t* __restrict__ tc_rank; const int32_t* __restrict__ tc_slot_ptr;
 };
 
 // ---- loads of 16 bytes of the dense operand -> 4 (fp32) or 8 (bf16) floats ----
@@ -209,6 +211,12 @@ static inline int fill_spmm_params(const tgcn_spmm_args* a, SpmmParams* p) {
   p->ad_p = a->adam_param; p->ad_m = a->adam_exp_avg; p->ad_v = a->adam_exp_avg_sq; p->ad_x = a->adam_max_exp_avg_sq;
   p->ad_ld = a->adam_ld; p->ad_hyp = a->adam_hyper_dev; p->ad_b1 = a->adam_beta1; p->ad_b2 = a->adam_beta2; p->ad_eps = a->adam_eps;
   p->ad_mirror = (float*)a->adam_param_mirror_mc;
+  p->tc_part = a->tc_part; p->tc_ld = a->tc_ld; p->tc_rank = a->tc_rank; p->tc_slot_ptr = a->tc_slot_ptr;
+  if (p->tc_part) {
+    TGCN_CHECK_ARG(p->tc_rank && p->tc_slot_ptr && p->tc_ld % 4 == 0 && p->tc_ld >= a->F && ((uintptr_t)p->tc_part & 15) == 0,
+                   "spmm: dense-tile partials need tc_rank, tc_slot_ptr and a 16-byte aligned buffer with tc_ld %% 4 == 0");
+    TGCN_CHECK_ARG(a->b_dtype == TGCN_F32, "spmm: dense-tile partials need an fp32 operand");
+  }
   if (p->ad_p) {
     TGCN_CHECK_ARG(p->ad_m && p->ad_v && p->ad_hyp, "spmm: fused Adam needs exp_avg, exp_avg_sq and the hyper buffer");
     TGCN_CHECK_ARG(a->P == nullptr && a->b_dtype == TGCN_F32 && p->ad_ld % 4 == 0 && p->ad_ld >= a->F,

@@ -56,8 +56,10 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
          drop_mode: int = DROP_NONE, drop_p: float = 0.0, keep_mask: Optional[torch.Tensor] = None,
          philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0,
          W_proj: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
-         want_out: bool = True, adam: Optional[dict] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+         want_out: bool = True, adam: Optional[dict] = None, tc=None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """C = epi(A_hat[rows of plan] @ B[:, :F]) (+ P = C @ W_proj).  See tgcn_spmm.
+    tc: a TcPlan whose dense-tile partial rows (already computed by tgcn_spmm_tc for this B, see spmm_hybrid) are
+    added to every row before the epilogue; `graph` must then be the plan's remainder.
 
     B: [>= n_nodes, >= F] fp32/bf16, row stride a multiple of 4 (fp32) / 8 (bf16) elements.
     Returns (C or None, P or None).  C has plan.row_end - plan.row_begin rows.
@@ -120,9 +122,32 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
         if P is None:
             P = torch.zeros((n_out, pad4(n_proj)), dtype=torch.float32, device=B.device)
         a.W_proj, a.n_proj, a.P, a.ldp = W_proj.data_ptr(), n_proj, P.data_ptr(), P.stride(0)
+    if tc is not None:
+        if graph is not tc.remainder:
+            raise RuntimeError("spmm: with tc=..., graph must be the plan's remainder CSR")
+        part = tc.buffers(F)[1]
+        a.tc_part, a.tc_ld, a.tc_rank, a.tc_slot_ptr = part.data_ptr(), part.stride(0), tc.rank.data_ptr(), tc.slot_ptr.data_ptr()
     with torch.cuda.device(B.device):
         _native.check(lib.tgcn_spmm(C.byref(a), _stream()))
     return out, P
+
+
+def spmm_hybrid(tc, B: torch.Tensor, *, F: Optional[int] = None, **kw):
+    """The same operation as spmm() on the graph `tc` was built from, computed in two parts: the dense blocks on the
+    tensor cores (tgcn_spmm_tc: operand pack + tcgen05 3xTF32 tiles -> partial rows), the remaining entries by the gather
+    kernel, whose epilogue adds the partial rows before bias / activation / dropout / Adam.  Same keyword arguments as
+    spmm() (bias, act, dropout, out, adam, ...); fp32 operands with 8 <= F <= 256 only."""
+    _need_cuda(B)
+    lib = _native.load()
+    F = int(B.shape[1]) if F is None else int(F)
+    if B.dtype != torch.float32 or B.stride(1) != 1:
+        raise RuntimeError("spmm_hybrid: B must be a row-major fp32 matrix")
+    bt, part = tc.buffers(F)
+    cp = tc.c_struct()
+    with torch.cuda.device(B.device):
+        _native.check(lib.tgcn_spmm_tc(C.byref(cp), B.data_ptr(), B.stride(0), F, bt.data_ptr(), part.data_ptr(), part.stride(0),
+                                       _stream()))
+    return spmm(tc.remainder, B, F=F, tc=tc, **kw)
 
 
 def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[torch.Tensor], n_mask_total: int,

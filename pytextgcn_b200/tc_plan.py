@@ -1,0 +1,170 @@
+"""Plan of the hybrid propagation: which blocks of A_hat go to the tensor cores (csrc/spmm_tc.cu) and which
+entries stay in the CSR the gather kernel walks (csrc/spmm.cu).  Built once per graph with torch index ops
+(device-agnostic: the CPU tests rebuild A_hat from the plan and compare it entry for entry).
+
+The word-word part of a Text2GraphTransformer graph (PMI edges, text2graph.py:156-166) is dominated by hub
+words: ranked by degree, the blocks that pair a hub with anything are 5-40 % dense while the matrix as a whole
+is < 1 % dense.  Nodes are therefore ranked by degree (rank space is only a view: inputs and outputs stay in
+node order -- the operand is permuted while it is packed, partial rows are fetched by rank), the matrix is cut
+into 128 x 32 blocks, and a block becomes a dense tile when it holds at least `min_density` * 4096 entries.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+
+TILE_M, TILE_K = 128, 32
+MAX_TILES_PER_UNIT = 48
+
+
+@dataclass
+class TcPlan:
+    n_nodes: int
+    n_row_blocks: int
+    n_col_blocks: int
+    rank: torch.Tensor          # int32 [N]: rank of each node (0 = largest degree)
+    perm: torch.Tensor          # int32 [n_col_blocks * 32]: node of each rank, -1 past the end
+    tile_rb: torch.Tensor       # int32 [n_tiles] row block of each tile (sorted by (row block, column block))
+    tile_kb: torch.Tensor       # int32 [n_tiles]
+    A_tiles: torch.Tensor       # fp32 [n_tiles, 2, 128, 32], swizzled
+    units: torch.Tensor         # int32 [n_units, 4] = {tile_begin, tile_end, slot, row_block}
+    slot_ptr: torch.Tensor      # int32 [n_row_blocks + 1]
+    n_slots: int
+    n_tiles: int
+    nnz_dense: int
+    remainder: "object"         # GraphCSR of the entries outside the tiles
+    min_density: float
+    _bufs: Dict[int, tuple] = field(default_factory=dict)
+
+    @property
+    def n_units(self) -> int:
+        return int(self.units.shape[0])
+
+    def buffers(self, F: int):
+        """(Bt workspace, partial-row buffer) for operand width F, allocated once."""
+        b = self._bufs.get(F)
+        if b is None:
+            Fp = (F + 7) // 8 * 8
+            dev = self.A_tiles.device
+            bt = torch.empty(self.n_col_blocks * 2 * Fp * TILE_K, dtype=torch.float32, device=dev)
+            part = torch.empty((max(self.n_slots, 1) * TILE_M, F), dtype=torch.float32, device=dev)
+            b = (bt, part)
+            self._bufs[F] = b
+        return b
+
+    def c_struct(self):
+        from . import _native
+        p = _native.TcPlanArgs()
+        p.A_tiles, p.tile_kb, p.units = self.A_tiles.data_ptr(), self.tile_kb.data_ptr(), self.units.data_ptr()
+        p.n_units, p.perm, p.n_col_blocks = self.n_units, self.perm.data_ptr(), self.n_col_blocks
+        return p
+
+
+def tf32_split(v: torch.Tensor):
+    """(hi, lo): hi = v rounded to TF32 (10 explicit mantissa bits, round to nearest, ties away -- cvt.rna.tf32.f32),
+    lo = v - hi exactly."""
+    bits = v.contiguous().view(torch.int32)
+    hi = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    return hi, v - hi
+
+
+def swizzled_offset(r: torch.Tensor, k: torch.Tensor) -> torch.Tensor:
+    """Float offset of element (row r, column k) inside a [rows][32] fp32 tile stored with the 128-byte swizzle:
+    the 16-byte chunk k // 4 of row r sits at chunk position (k // 4) ^ (r % 8)."""
+    return r * TILE_K + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3))
+
+
+def build_tc_plan(graph, min_density: float = 0.03, max_bytes: int = 2 << 30, n_sms: int = 148) -> Optional[TcPlan]:
+    """Returns None when no block of the graph qualifies."""
+    from .graph import GraphCSR
+    dev = graph.rowptr.device
+    n = graph.n_nodes
+    if graph.n_cols != n:
+        raise RuntimeError("build_tc_plan needs a square matrix (full graph)")
+    rows = graph.row_ids()
+    cols = graph.colidx.to(torch.int64)
+    val = graph.val
+    nnz = int(cols.numel())
+    # ---- degree ranking ----
+    score = (graph.rowptr[1:] - graph.rowptr[:-1]).to(torch.int64) + torch.bincount(cols, minlength=n)
+    order = torch.sort(score, descending=True, stable=True).indices
+    rank = torch.empty(n, dtype=torch.int64, device=dev)
+    rank[order] = torch.arange(n, device=dev)
+    n_rb = (n + TILE_M - 1) // TILE_M
+    n_kb = n_rb * (TILE_M // TILE_K)
+    perm = torch.full((n_kb * TILE_K,), -1, dtype=torch.int32, device=dev)
+    perm[:n] = order.to(torch.int32)
+    # ---- block census ----
+    rr, rc = rank[rows], rank[cols]
+    key = (rr >> 7) * n_kb + (rc >> 5)
+    # duplicate (row, col) entries (possible in a general COO graph, never emitted by Text2GraphTransformer) cannot share
+    # a dense cell: all but the first of each pair stay in the remainder
+    full_key = rows * n + cols
+    srt = torch.sort(full_key, stable=True)
+    dup_sorted = torch.zeros(nnz, dtype=torch.bool, device=dev)
+    if nnz > 1:
+        dup_sorted[1:] = srt.values[1:] == srt.values[:-1]
+    is_dup = torch.zeros(nnz, dtype=torch.bool, device=dev)
+    is_dup[srt.indices] = dup_sorted
+    ukeys, counts = torch.unique(key[~is_dup], return_counts=True)
+    thr = max(1, int(round(min_density * TILE_M * TILE_K)))
+    cand = counts >= thr
+    if int(cand.sum().item()) == 0:
+        return None
+    ck, cc = ukeys[cand], counts[cand]
+    max_tiles = max(1, int(max_bytes // (2 * TILE_M * TILE_K * 4)))
+    if ck.numel() > max_tiles:                       # memory cap: keep the densest blocks
+        top = torch.topk(cc, max_tiles).indices
+        ck = torch.sort(ck[top]).values
+    sel_keys = ck                                     # sorted by (row block, column block)
+    n_tiles = int(sel_keys.numel())
+    tile_rb = (sel_keys // n_kb).to(torch.int32)
+    tile_kb = (sel_keys % n_kb).to(torch.int32)
+    # ---- split the entries ----
+    pos = torch.searchsorted(sel_keys, key).clamp_(max=n_tiles - 1)
+    dense = (sel_keys[pos] == key) & ~is_dup
+    A = torch.zeros((n_tiles, 2, TILE_M * TILE_K), dtype=torch.float32, device=dev)
+    t = pos[dense]
+    off = swizzled_offset(rr[dense] & (TILE_M - 1), rc[dense] & (TILE_K - 1))
+    hi, lo = tf32_split(val[dense])
+    flat = A.view(-1)                                 # tile t: hi at t * 2 * 4096, lo right behind it
+    flat[t * (2 * TILE_M * TILE_K) + off] = hi
+    flat[t * (2 * TILE_M * TILE_K) + TILE_M * TILE_K + off] = lo
+    keep = ~dense
+    r_rows = rows[keep]
+    rp = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    rp[1:] = torch.cumsum(torch.bincount(r_rows, minlength=n), 0).to(torch.int32)
+    rem = GraphCSR(n, rp, graph.colidx[keep].contiguous(), val[keep].contiguous(), graph.dis)
+    rem._symmetric = False
+    # ---- units: <= MAX_TILES_PER_UNIT consecutive tiles of one row block; slots consecutive per row block ----
+    per_rb = torch.bincount(tile_rb.to(torch.int64), minlength=n_rb)
+    n_u = (per_rb + MAX_TILES_PER_UNIT - 1) // MAX_TILES_PER_UNIT
+    slot_ptr = torch.zeros(n_rb + 1, dtype=torch.int64, device=dev)
+    slot_ptr[1:] = torch.cumsum(n_u, 0)
+    n_slots = int(slot_ptr[-1].item())
+    tile_ptr = torch.zeros(n_rb + 1, dtype=torch.int64, device=dev)
+    tile_ptr[1:] = torch.cumsum(per_rb, 0)
+    u_rb = torch.repeat_interleave(torch.arange(n_rb, device=dev), n_u)
+    u_j = torch.arange(n_slots, device=dev) - slot_ptr[u_rb]
+    u_begin = tile_ptr[u_rb] + (u_j * per_rb[u_rb]) // n_u[u_rb]
+    u_end = tile_ptr[u_rb] + ((u_j + 1) * per_rb[u_rb]) // n_u[u_rb]
+    u_slot = torch.arange(n_slots, device=dev)
+    # longest units first, dealt to the CTAs in snake order; CTA c walks entries c, c + G, c + 2G, ... of the list
+    G = max(1, min(n_sms, n_slots))
+    by_len = torch.sort(u_end - u_begin, descending=True, stable=True).indices
+    i = torch.arange(n_slots, device=dev)
+    wave, p_in = i // G, i % G
+    cta = torch.where(wave % 2 == 0, p_in, G - 1 - p_in)
+    n_list = int(((n_slots + G - 1) // G) * G)
+    units = torch.zeros((n_list, 4), dtype=torch.int32, device=dev)
+    units[:, 2] = -1
+    dst = wave * G + cta
+    units[dst, 0] = u_begin[by_len].to(torch.int32)
+    units[dst, 1] = u_end[by_len].to(torch.int32)
+    units[dst, 2] = u_slot[by_len].to(torch.int32)
+    units[dst, 3] = u_rb[by_len].to(torch.int32)
+    return TcPlan(n, n_rb, n_kb, rank.to(torch.int32), perm, tile_rb, tile_kb, A.view(n_tiles, 2, TILE_M, TILE_K), units,
+                  slot_ptr.to(torch.int32), n_slots, n_tiles, int(dense.sum().item()), rem, float(min_density))
