@@ -25,7 +25,8 @@ class TextGCNTrainer:
     def __init__(self, gcn: GCN, g, lr: float = 0.05, amsgrad: bool = True, betas=(0.9, 0.999), eps: float = 1e-8,
                  use_cuda_graph: bool = True, seed: int = 0, chunk_nnz: Optional[int] = None,
                  graph: Optional[GraphCSR] = None, assume_symmetric: bool = False, eval_mode: str = "layered",
-                 fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True, restrict_rows: bool = True):
+                 fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True, restrict_rows: bool = True,
+                 tensor_cores: Optional[bool] = None, tc_min_density: float = 0.03):
         if len(gcn.layers) != 2:
             raise NotImplementedError("TextGCNTrainer fuses the 2-layer TextGCN (the configuration of every reference script)")
         l0, l1 = gcn.layers
@@ -52,6 +53,19 @@ class TextGCNTrainer:
         # defined on masked rows only (eval_step(full=True) computes every row).
         self.restrict_rows = bool(restrict_rows)
         self.lr, self.amsgrad, self.betas, self.eps = float(lr), bool(amsgrad), betas, float(eps)
+        # Hybrid hidden-wide propagation (csrc/spmm_tc.cu): the dense blocks of A_hat on the tensor cores (3xTF32, fp32
+        # accuracy), the rest gathered as before.  None = use it when the graph has dense blocks worth it.
+        self.tc = self.tc_t = None
+        Hh = int(gcn.layers[0].weight.shape[1])
+        if tensor_cores is not False and Hh % 4 == 0 and 64 <= Hh <= 256 and self.graph.nnz >= 200_000:
+            from .tc_plan import build_tc_plan
+            n_sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+            tc = build_tc_plan(self.graph, min_density=tc_min_density, n_sms=n_sms)
+            if tc is not None and (tensor_cores or tc.nnz_dense >= 0.15 * self.graph.nnz):
+                self.tc = tc
+                self.tc_t = tc if self.graph_t is self.graph else build_tc_plan(self.graph_t, min_density=tc_min_density, n_sms=n_sms)
+        elif tensor_cores:
+            raise RuntimeError("tensor_cores=True needs a hidden width that is a multiple of 4 in [64, 256]")
         self.act = ops.ACT_RELU if gcn.apply_activation else ops.ACT_NONE
         self.p = float(gcn.dropout)
         self.seed = int(seed)
@@ -205,6 +219,14 @@ class TextGCNTrainer:
         ops.spmm(self.graph, self.Q, F=self.Cp, plan=self.plan, out=self.T, bias=self.c_row[0, :self.C])
         ops.spmm(self.graph, self.T, F=self.Cp, plan=self.plan if full else self.plan_z2, out=self.Z2, bias=b2)
 
+    def _wide_spmm(self, transposed: bool, B: torch.Tensor, **kw):
+        """Hidden-wide propagation A_hat B (or A_hat^T B) with the fused epilogue `kw`: hybrid when a plan exists."""
+        tc = self.tc_t if transposed else self.tc
+        if tc is not None and kw.get("W_proj") is None:
+            return ops.spmm_hybrid(tc, B, F=self.H, plan=tc.remainder.plan(), **kw)
+        graph, plan = (self.graph_t, self.plan_t) if transposed else (self.graph, self.plan)
+        return ops.spmm(graph, B, F=self.H, plan=plan, **kw)
+
     def _param_key(self):
         l0 = self.gcn.layers[0]
         return (l0.weight._version, l0.bias._version, l0.weight.data_ptr(), l0.bias.data_ptr())
@@ -236,8 +258,8 @@ class TextGCNTrainer:
             else:
                 B1 = W1[:self.n]
             h_out = self.H1d if training else self.H1
-            ops.spmm(self.graph, B1, F=self.H, plan=self.plan, out=h_out, bias=b1, act=self.act,
-                     W_proj=W2 if fuse else None, P=self.P if fuse else None, **dkw)
+            self._wide_spmm(False, B1, out=h_out, bias=b1, act=self.act,
+                            W_proj=W2 if fuse else None, P=self.P if fuse else None, **dkw)
         if not fuse:
             ops.project(h_out, W2, K=self.H, out=self.P)
         ops.spmm(self.graph, self.P, F=self.Cp, plan=self.plan if full else self.plan_z2, out=self.Z2, bias=b2)
@@ -259,13 +281,13 @@ class TextGCNTrainer:
         kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad, step_dev=self.step_dev)
         if self.fuse_adam:
             ops.adam_prepare(self.step_dev, self.adam_hyper, self.lr, self.betas[0], self.betas[1])     # step += 1
-            ops.spmm(self.graph_t, self.dZ1, F=self.H, plan=self.plan_t, out=self.grads[0] if self.keep_w1_grad else None,
-                     want_out=self.keep_w1_grad,
-                     adam=dict(param=self.params[0].data, exp_avg=self.exp_avg[0], exp_avg_sq=self.exp_avg_sq[0],
-                               max_exp_avg_sq=self.max_exp_avg_sq[0], hyper=self.adam_hyper, beta1=self.betas[0],
-                               beta2=self.betas[1], eps=self.eps))
+            self._wide_spmm(True, self.dZ1, out=self.grads[0] if self.keep_w1_grad else None,
+                            want_out=self.keep_w1_grad,
+                            adam=dict(param=self.params[0].data, exp_avg=self.exp_avg[0], exp_avg_sq=self.exp_avg_sq[0],
+                                      max_exp_avg_sq=self.max_exp_avg_sq[0], hyper=self.adam_hyper, beta1=self.betas[0],
+                                      beta2=self.betas[1], eps=self.eps))
         else:
-            ops.spmm(self.graph_t, self.dZ1, F=self.H, plan=self.plan_t, out=self.grads[0])
+            self._wide_spmm(True, self.dZ1, out=self.grads[0])
             if self.feat.Fdoc is not None:
                 ops.hier_backward(self.grads[0], self.n, self.feat.n_vocab, self.feat.Fdoc, self.H, self.hier_tail)
                 self.grads[0][self.n:].copy_(self.hier_tail)
