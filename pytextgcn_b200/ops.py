@@ -74,7 +74,13 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
     if B.shape[0] < graph.n_cols:
         raise RuntimeError(f"spmm: B has {B.shape[0]} rows, the graph has {graph.n_cols} columns")
     a = _native.SpmmArgs()
-    a.rowptr, a.colidx, a.val = graph.rowptr.data_ptr(), graph.colidx.data_ptr(), graph.val.data_ptr()
+    if graph.nnz == 0:      # e.g. the remainder of a hybrid plan whose every entry sits in a dense tile: rows are all empty
+        if "_empty_entries" not in graph.buffers:
+            graph.buffers["_empty_entries"] = torch.zeros(4, dtype=torch.int32, device=graph.device)
+        e = graph.buffers["_empty_entries"]
+        a.rowptr, a.colidx, a.val = graph.rowptr.data_ptr(), e.data_ptr(), e.data_ptr()
+    else:
+        a.rowptr, a.colidx, a.val = graph.rowptr.data_ptr(), graph.colidx.data_ptr(), graph.val.data_ptr()
     a.chunks, a.n_chunks = plan.chunks.data_ptr(), plan.n_chunks
     a.split_rows, a.n_split_rows = (plan.split_rows.data_ptr() if plan.n_split_rows else None), plan.n_split_rows
     scratch = plan.scratch(F)

@@ -57,15 +57,16 @@ class TextGCNTrainer:
         # accuracy), the rest gathered as before.  None = use it when the graph has dense blocks worth it.
         self.tc = self.tc_t = None
         Hh = int(gcn.layers[0].weight.shape[1])
-        if tensor_cores is not False and Hh % 4 == 0 and 64 <= Hh <= 256 and self.graph.nnz >= 200_000:
+        if tensor_cores and not (Hh % 4 == 0 and 64 <= Hh <= 256):
+            raise RuntimeError("tensor_cores=True needs a hidden width that is a multiple of 4 in [64, 256]")
+        if (tensor_cores or (tensor_cores is None and self.graph.nnz >= 200_000)) and Hh % 4 == 0 and 64 <= Hh <= 256:
             from .tc_plan import build_tc_plan
             n_sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
             tc = build_tc_plan(self.graph, min_density=tc_min_density, n_sms=n_sms)
             if tc is not None and (tensor_cores or tc.nnz_dense >= 0.15 * self.graph.nnz):
                 self.tc = tc
                 self.tc_t = tc if self.graph_t is self.graph else build_tc_plan(self.graph_t, min_density=tc_min_density, n_sms=n_sms)
-        elif tensor_cores:
-            raise RuntimeError("tensor_cores=True needs a hidden width that is a multiple of 4 in [64, 256]")
+
         self.act = ops.ACT_RELU if gcn.apply_activation else ops.ACT_NONE
         self.p = float(gcn.dropout)
         self.seed = int(seed)
