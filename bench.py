@@ -330,21 +330,28 @@ class Level:
         tr = self.tr
         return (tr.launches_per_train_step_reuse or tr.launches_per_train_step) + tr.launches_per_eval
 
-    def time_spmm(self, F: int, k: int, warm: int = 3) -> float:
-        """Mean device time of the propagation kernel at width F (CUDA events around the launch, on the launch stream).
-        A whole eval pass runs between two timed launches, so the CSR (>L2 together with the operands) is cold."""
+    def time_spmm(self, F: int, k: int, warm: int = 3, gather_only: bool = False) -> float:
+        """Mean device time of the propagation at width F (CUDA events around the launches, on the launch stream).
+        F = hidden: the operation the trainer runs (hybrid tensor-core + gather when a plan exists; gather_only=True
+        forces the pure gather kernel over the whole CSR).  A whole eval pass runs between two timed launches, so the
+        CSR (>L2 together with the operands) is cold."""
         from pytextgcn_b200 import ops
         tr = self.tr
         if F == tr.H:
             B = self.gcn.layers[0].weight.data[:self.n] if tr.XW is None else tr.XW
             kw = dict(out=tr.H1, bias=self.gcn.layers[0].bias.data)
+            if gather_only:
+                fn = lambda: ops.spmm(self.graph, B, F=F, plan=tr.plan, **kw)
+            else:
+                fn = lambda: tr._wide_spmm(False, B, **kw)
         else:
             B, kw = tr.P, dict(out=tr.Z2, bias=self.gcn.layers[1].bias.data)
+            fn = lambda: ops.spmm(self.graph, B, F=F, plan=tr.plan, **kw)
         evs = []
         for _ in range(warm + k):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            ops.spmm(self.graph, B, F=F, plan=tr.plan, **kw)
+            fn()
             b.record()
             tr.eval_step()
             evs.append((a, b))
@@ -404,9 +411,11 @@ def other_shape_record(label, shape, hier, seed, dev, k: int = 15):
     F = shape.hidden
     k_ms = lv.time_spmm(F, 6)
     alg = spmm_alg_bytes(lv.graph.nnz, lv.n, F)
+    tc = lv.tr.tc
     rec = {"n_nodes": lv.n, "nnz": lv.graph.nnz, "hidden": F, "n_classes": shape.n_classes, "hierarchy_feats": hier,
            "ms_per_epoch": ms, "epochs_per_s": 1e3 / ms, "kernels_per_epoch": lv.kernels_per_epoch(),
            "hidden_spmm_ms": k_ms, "hidden_spmm_frac_of_hbm_peak": alg / (k_ms * 1e-3) / 1e9 / peak,
+           "tensor_core_share_of_nnz": (tc.nnz_dense / lv.graph.nnz) if tc is not None else 0.0,
            "graph_upload_ms": lv.upload_ms}
     del lv
     torch.cuda.empty_cache()
@@ -531,6 +540,7 @@ def run_own_arm(args):
     # ---- dominant kernel (hidden-wide propagation) and the class-wide one, CUDA events on the launch stream ----
     F = shape.hidden
     k_ms = lv0.time_spmm(F, max(K, 10))
+    g_ms = lv0.time_spmm(F, max(K, 10), gather_only=True) if tr.tc is not None else k_ms
     n_ms = lv0.time_spmm(tr.Cp, max(K, 10))
     alg = spmm_alg_bytes(graph.nnz, n, F)
     alg_n = spmm_alg_bytes(graph.nnz, n, tr.Cp)
@@ -541,13 +551,16 @@ def run_own_arm(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": prof.get("dram_bytes_per_launch"),
                 "traffic_source": prof.get("source", None),
-                "kernel": "k_spmm<float,32,2,*> hidden-wide propagation A_hat (X W1) + b1, F=%d (%d launches per epoch: eval "
-                          "forward -- shared with the next train forward -- and the backward that carries W1's Adam update)" % (F, wide_per_epoch),
-                "kernel_ms": k_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
+                "kernel": ("hidden-wide propagation A_hat (X W1) + b1, F=%d, as the trainer runs it: " % F) +
+                          ("hybrid = k_tc_pack + k_tc_mma (dense 128x32 blocks of A_hat on tcgen05, 3xTF32, %.0f %% of the non-zeros) + "
+                           "k_spmm<float,32,2,*> (gathered remainder + epilogue)" % (100.0 * tr.tc.nnz_dense / graph.nnz) if tr.tc is not None
+                           else "k_spmm<float,32,2,*> (gather kernel)") +
+                          "; %d such propagations per epoch (eval forward -- shared with the next train forward -- and the backward "
+                          "that carries W1's Adam update)" % wide_per_epoch,
+                "kernel_ms": k_ms, "gather_only_kernel_ms": g_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
                 "share_of_epoch": wide_per_epoch * k_ms / ms_per_step,
-                "note": "algorithmic bytes count each dense row once; the kernel is bound by L2->SM gather bandwidth "
-                        "(nnz*F*4 = %.1f GB per launch), see DESIGN.md" % (graph.nnz * F * 4 / 1e9),
-                "l2_gather_gbs": graph.nnz * F * 4 / (k_ms * 1e-3) / 1e9}
+                "note": "algorithmic bytes count each dense row once; the gather part is bound by L2->SM fill bandwidth "
+                        "(800 B per gathered non-zero), the dense part by the tensor pipe / its operand tiles, see DESIGN.md"}
     extra["narrow_spmm"] = {"kernel_ms": n_ms, "F": tr.Cp, "algorithmic_bytes": alg_n, "frac": alg_n / (n_ms * 1e-3) / 1e9 / peak,
                             "launches_per_epoch": 3}
 

@@ -148,7 +148,7 @@ int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
  * following tgcn_spmm call (tc_part/tc_rank/tc_slot_ptr) adds them to the gathered remainder and runs the epilogue.
  * Replaces GCNConv.propagate for the dense blocks (models.py:20).  Plan: pytextgcn_b200/tc_plan.py. */
 typedef struct {
-  const float* A_tiles;     /* [n_tiles][2][128][32] fp32, 128-byte swizzle pre-applied (see spmm_tc.cu) */
+  const float* A_tiles;     /* [n_tiles][128][32] fp32 values of A_hat, 128-byte swizzle pre-applied (see spmm_tc.cu) */
   const int32_t* tile_kb;   /* [n_tiles] column block of each tile */
   const int32_t* units;     /* [n_units][4] = {tile_begin, tile_end, slot, row_block}; empty units (begin == end) allowed */
   int32_t n_units;

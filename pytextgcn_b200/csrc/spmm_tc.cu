@@ -16,9 +16,11 @@
 // per product -- below the fp32 rounding of the 349-term sums themselves (tests/test_gpu_spmm_tc.py).
 //
 // Data (built once per graph by pytextgcn_b200/tc_plan.py, rank = position in the degree order):
-//   A_tiles  [n_tiles][2 (hi, lo)][128 rows][32 cols] fp32, each 128-byte row stored with the 128-byte
+//   A_tiles  [n_tiles][128 rows][32 cols] fp32 values of A_hat, each 128-byte row stored with the 128-byte
 //            shared-memory swizzle already applied (16-byte chunk c of row r sits at chunk c ^ (r & 7)), so a
-//            tile is ONE 32 KB bulk copy into the layout the UMMA descriptor expects (K-major, SWIZZLE_128B);
+//            tile is ONE 16 KB bulk copy; four "splitter" warps turn it into the hi / lo operand tiles in
+//            shared memory (elementwise, same positions: the layout the UMMA descriptor expects, K-major
+//            SWIZZLE_128B) -- half the HBM / L2->SM bytes of shipping hi and lo separately;
 //   tile_kb  [n_tiles] column block (32 ranks) of each tile; tiles of one row block are consecutive;
 //   units    {tile_begin, tile_end, slot, row_block}: <= 48 tiles of one row block; a unit's 128 x F partial
 //            result goes to part[slot]; the slots of a row block are consecutive and tgcn_spmm's epilogue
@@ -26,11 +28,12 @@
 //   Bt       [n_col_blocks][2 (hi, lo)][Fp features][32 ranks] fp32, same swizzle: the operand transposed
 //            to K-major and split into hi/lo by k_tc_pack at every launch (B changes every step).
 //
-// Kernel k_tc_mma: persistent, one CTA per SM, 192 threads.  warp 0 = producer (cp.async.bulk into a 2-stage
-// ring, mbarrier complete_tx), warp 1 = MMA issuer (one thread; tcgen05.commit releases the stage and, after
-// the last tile of a unit, publishes the accumulator), warps 2-5 = epilogue (tcgen05.ld 32 lanes x 32 columns
-// per warp -> fp32 partial rows in global memory).  Two 256-column accumulators in TMEM: the epilogue of
-// unit i overlaps the MMAs of unit i+1.
+// Kernel k_tc_mma: persistent, one CTA per SM, 320 threads.  warp 0 = producer (cp.async.bulk into a 2-stage
+// ring {A values, Bt tile}, mbarrier complete_tx), warp 1 = MMA issuer (one thread; tcgen05.commit releases the
+// stage and, after the last tile of a unit, publishes the accumulator), warps 2-5 = epilogue (tcgen05.ld 32
+// lanes x 32 columns per warp -> fp32 partial rows in global memory), warps 6-9 = splitters (A values -> TF32
+// hi + residual lo tiles, fence.proxy.async, mbarrier arrive).  Two 256-column accumulators in TMEM: the
+// epilogue of unit i overlaps the MMAs of unit i+1.
 #include "common.cuh"
 
 namespace tgcn {
@@ -38,8 +41,8 @@ namespace tgcn {
 constexpr int TC_M = 128;
 constexpr int TC_K = 32;
 constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 192;
-constexpr uint32_t TC_A_PART = TC_M * TC_K * 4;      // 16 KB: one of (hi, lo)
+constexpr int TC_THREADS = 320;
+constexpr uint32_t TC_A_PART = TC_M * TC_K * 4;      // 16 KB: the values of a tile, or one of its (hi, lo) operand tiles
 constexpr uint32_t TC_ACC_COLS = 256;                // TMEM columns per accumulator (F <= 256)
 
 struct TcParams {
@@ -115,14 +118,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
   const uint32_t raw = tc_smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t b_part = (uint32_t)p.Fp * 128u;               // bytes of one of (hi, lo) of an operand tile
-  const uint32_t stage_bytes = 2u * TC_A_PART + 2u * b_part;
-  const uint32_t bars = base + TC_STAGES * stage_bytes;        // 8-byte mbarriers
-  const uint32_t full0 = bars, empty0 = bars + 8 * TC_STAGES, tfull0 = bars + 16 * TC_STAGES, tempty0 = tfull0 + 16;
-  const uint32_t holder = tempty0 + 16;                        // TMEM base address written by tcgen05.alloc
+  const uint32_t stage_bytes = TC_A_PART + 2u * b_part;        // ring stage: A values, Bt hi, Bt lo
+  const uint32_t split0 = base + TC_STAGES * stage_bytes;      // two {A hi, A lo} operand buffers
+  const uint32_t bars = split0 + 2u * 2u * TC_A_PART;          // 8-byte mbarriers
+  const uint32_t full0 = bars, empty0 = bars + 16, afull0 = bars + 32, aempty0 = bars + 48, tfull0 = bars + 64, tempty0 = bars + 80;
+  const uint32_t holder = bars + 96;                           // TMEM base address written by tcgen05.alloc
   volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(tc_smem_raw + (holder - raw));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(full0 + 8 * s, 1); tc_mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < TC_STAGES; ++s) {
+      tc_mbar_init(full0 + 8 * s, 1);          // producer's arrive.expect_tx (+ the bytes of both bulk copies)
+      tc_mbar_init(empty0 + 8 * s, 1 + 128);   // tcgen05.commit (Bt read) + the 128 splitter threads (A values read)
+      tc_mbar_init(afull0 + 8 * s, 128);       // splitter threads: hi / lo tiles written
+      tc_mbar_init(aempty0 + 8 * s, 1);        // tcgen05.commit: hi / lo tiles read
+    }
     for (int a = 0; a < 2; ++a) { tc_mbar_init(tfull0 + 8 * a, 1); tc_mbar_init(tempty0 + 8 * a, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -144,12 +153,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
         for (int t = un.x; t < un.y; ++t, ++it) {
           const int s = it % TC_STAGES;
           const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-          tc_mbar_wait(empty0 + 8 * s, ph ^ 1u);               // the MMAs that read this stage have completed
+          tc_mbar_wait(empty0 + 8 * s, ph ^ 1u);               // MMAs and splitters are done with this stage
           const uint32_t st = base + s * stage_bytes;
           tc_mbar_arrive_expect_tx(full0 + 8 * s, stage_bytes);
-          tc_bulk_g2s(st, p.A_tiles + (int64_t)t * (2 * TC_M * TC_K), 2u * TC_A_PART, full0 + 8 * s);
+          tc_bulk_g2s(st, p.A_tiles + (int64_t)t * (TC_M * TC_K), TC_A_PART, full0 + 8 * s);
           const int kb = __ldg(p.tile_kb + t);
-          tc_bulk_g2s(st + 2u * TC_A_PART, reinterpret_cast<const char*>(p.Bt) + (int64_t)kb * (2 * b_part), 2u * b_part, full0 + 8 * s);
+          tc_bulk_g2s(st + TC_A_PART, reinterpret_cast<const char*>(p.Bt) + (int64_t)kb * (2 * b_part), 2u * b_part, full0 + 8 * s);
         }
       }
     }
@@ -170,11 +179,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
         for (int t = un.x; t < un.y; ++t, ++it) {
           const int s = it % TC_STAGES;
           const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-          tc_mbar_wait(full0 + 8 * s, ph);                     // both bulk copies of this stage have landed
+          tc_mbar_wait(full0 + 8 * s, ph);                     // the Bt tile has landed
+          tc_mbar_wait(afull0 + 8 * s, ph);                    // the splitters have written A hi / lo
           tc_fence_after();
-          const uint32_t st = base + s * stage_bytes;
-          const uint64_t a_hi = tc_smem_desc(st), a_lo = tc_smem_desc(st + TC_A_PART);
-          const uint64_t b_hi = tc_smem_desc(st + 2u * TC_A_PART), b_lo = tc_smem_desc(st + 2u * TC_A_PART + b_part);
+          const uint32_t st = base + s * stage_bytes, sp = split0 + s * (2u * TC_A_PART);
+          const uint64_t a_hi = tc_smem_desc(sp), a_lo = tc_smem_desc(sp + TC_A_PART);
+          const uint64_t b_hi = tc_smem_desc(st + TC_A_PART), b_lo = tc_smem_desc(st + TC_A_PART + b_part);
 #pragma unroll
           for (int ks = 0; ks < TC_K / 8; ++ks) {              // 8 TF32 columns (32 bytes) per instruction
             const uint64_t adv = (uint64_t)(ks * 2);           // +32 bytes on the 16-byte start-address field
@@ -182,10 +192,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
             tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
             tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
           }
-          tc_commit(empty0 + 8 * s);                           // stage reusable once these MMAs are done
+          tc_commit(empty0 + 8 * s);                           // ring stage reusable once these MMAs are done
+          tc_commit(aempty0 + 8 * s);                          // so are the hi / lo tiles
         }
         tc_commit(tfull0 + 8 * as);                            // accumulator complete
         ++ui;
+      }
+    }
+  } else if (warp >= 6) {
+    // ---------------- splitters: A values -> TF32 hi + residual lo, same (swizzled) positions ----------------
+    const int ts = threadIdx.x - 6 * 32;
+    int it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int4 un = __ldg(p.units + u);
+      for (int t = un.x; t < un.y; ++t, ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+        tc_mbar_wait(full0 + 8 * s, ph);                       // the tile's values have landed
+        tc_mbar_wait(aempty0 + 8 * s, ph ^ 1u);                // the MMAs that read the previous hi / lo tiles are done
+        const uint32_t src = base + s * stage_bytes, hi = split0 + s * (2u * TC_A_PART), lo = hi + TC_A_PART;
+#pragma unroll
+        for (int j = 0; j < (TC_M * TC_K / 4) / 128; ++j) {
+          const uint32_t o = (uint32_t)(ts + 128 * j) * 16u;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + o));
+          uint32_t h0, h1, h2, h3;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(v.x));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1) : "f"(v.y));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h2) : "f"(v.z));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h3) : "f"(v.w));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi + o), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + o), "f"(v.x - __uint_as_float(h0)), "f"(v.y - __uint_as_float(h1)),
+                       "f"(v.z - __uint_as_float(h2)), "f"(v.w - __uint_as_float(h3)) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's reads
+        tc_mbar_arrive(afull0 + 8 * s);
+        tc_mbar_arrive(empty0 + 8 * s);
       }
     }
   } else {
@@ -304,8 +346,8 @@ extern "C" int tgcn_spmm_tc(const tgcn_tc_plan* plan, const float* B, int64_t ld
   TcParams p;
   p.A_tiles = plan->A_tiles; p.tile_kb = plan->tile_kb; p.units = reinterpret_cast<const int4*>(plan->units);
   p.n_units = plan->n_units; p.Bt = Bt; p.part = part; p.ldp = ldp; p.Fp = Fp; p.F = F;
-  const size_t stage = 2 * (size_t)TC_A_PART + 2 * (size_t)Fp * 128;
-  const size_t smem = TC_STAGES * stage + 1024 /* alignment slack */ + 256 /* barriers */;
+  const size_t stage = (size_t)TC_A_PART + 2 * (size_t)Fp * 128;
+  const size_t smem = TC_STAGES * stage + 4 * (size_t)TC_A_PART + 1024 /* alignment slack */ + 256 /* barriers */;
   TGCN_CHECK_ARG(smem <= 227 * 1024, "spmm_tc: F = %d needs %zu bytes of shared memory", F, smem);
   TGCN_CUDA(cudaFuncSetAttribute(k_tc_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min<int>(sm_count(), plan->n_units);

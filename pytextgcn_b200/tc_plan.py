@@ -29,7 +29,7 @@ class TcPlan:
     perm: torch.Tensor          # int32 [n_col_blocks * 32]: node of each rank, -1 past the end
     tile_rb: torch.Tensor       # int32 [n_tiles] row block of each tile (sorted by (row block, column block))
     tile_kb: torch.Tensor       # int32 [n_tiles]
-    A_tiles: torch.Tensor       # fp32 [n_tiles, 2, 128, 32], swizzled
+    A_tiles: torch.Tensor       # fp32 [n_tiles, 128, 32]: the values of A_hat, rows swizzled (split into TF32 hi/lo in the kernel)
     units: torch.Tensor         # int32 [n_units, 4] = {tile_begin, tile_end, slot, row_block}
     slot_ptr: torch.Tensor      # int32 [n_row_blocks + 1]
     n_slots: int
@@ -61,14 +61,6 @@ class TcPlan:
         p.A_tiles, p.tile_kb, p.units = self.A_tiles.data_ptr(), self.tile_kb.data_ptr(), self.units.data_ptr()
         p.n_units, p.perm, p.n_col_blocks = self.n_units, self.perm.data_ptr(), self.n_col_blocks
         return p
-
-
-def tf32_split(v: torch.Tensor):
-    """(hi, lo): hi = v rounded to TF32 (10 explicit mantissa bits, round to nearest, ties away -- cvt.rna.tf32.f32),
-    lo = v - hi exactly."""
-    bits = v.contiguous().view(torch.int32)
-    hi = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
-    return hi, v - hi
 
 
 def swizzled_offset(r: torch.Tensor, k: torch.Tensor) -> torch.Tensor:
@@ -115,7 +107,7 @@ def build_tc_plan(graph, min_density: float = 0.03, max_bytes: int = 2 << 30, n_
     if int(cand.sum().item()) == 0:
         return None
     ck, cc = ukeys[cand], counts[cand]
-    max_tiles = max(1, int(max_bytes // (2 * TILE_M * TILE_K * 4)))
+    max_tiles = max(1, int(max_bytes // (TILE_M * TILE_K * 4)))
     if ck.numel() > max_tiles:                       # memory cap: keep the densest blocks
         top = torch.topk(cc, max_tiles).indices
         ck = torch.sort(ck[top]).values
@@ -126,13 +118,10 @@ def build_tc_plan(graph, min_density: float = 0.03, max_bytes: int = 2 << 30, n_
     # ---- split the entries ----
     pos = torch.searchsorted(sel_keys, key).clamp_(max=n_tiles - 1)
     dense = (sel_keys[pos] == key) & ~is_dup
-    A = torch.zeros((n_tiles, 2, TILE_M * TILE_K), dtype=torch.float32, device=dev)
+    A = torch.zeros((n_tiles, TILE_M * TILE_K), dtype=torch.float32, device=dev)
     t = pos[dense]
     off = swizzled_offset(rr[dense] & (TILE_M - 1), rc[dense] & (TILE_K - 1))
-    hi, lo = tf32_split(val[dense])
-    flat = A.view(-1)                                 # tile t: hi at t * 2 * 4096, lo right behind it
-    flat[t * (2 * TILE_M * TILE_K) + off] = hi
-    flat[t * (2 * TILE_M * TILE_K) + TILE_M * TILE_K + off] = lo
+    A.view(-1)[t * (TILE_M * TILE_K) + off] = val[dense]
     keep = ~dense
     r_rows = rows[keep]
     rp = torch.zeros(n + 1, dtype=torch.int32, device=dev)
@@ -166,5 +155,5 @@ def build_tc_plan(graph, min_density: float = 0.03, max_bytes: int = 2 << 30, n_
     units[dst, 1] = u_end[by_len].to(torch.int32)
     units[dst, 2] = u_slot[by_len].to(torch.int32)
     units[dst, 3] = u_rb[by_len].to(torch.int32)
-    return TcPlan(n, n_rb, n_kb, rank.to(torch.int32), perm, tile_rb, tile_kb, A.view(n_tiles, 2, TILE_M, TILE_K), units,
+    return TcPlan(n, n_rb, n_kb, rank.to(torch.int32), perm, tile_rb, tile_kb, A.view(n_tiles, TILE_M, TILE_K), units,
                   slot_ptr.to(torch.int32), n_slots, n_tiles, int(dense.sum().item()), rem, float(min_density))

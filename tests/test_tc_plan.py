@@ -1,13 +1,12 @@
-"""Host logic of the hybrid propagation (pytextgcn_b200/tc_plan.py) on the CPU: the dense tiles (un-swizzled,
-hi + lo) plus the remainder CSR must rebuild A_hat entry for entry, every tile must belong to exactly one unit,
-and the TF32 split must be exact."""
+"""Host logic of the hybrid propagation (pytextgcn_b200/tc_plan.py) on the CPU: the dense tiles (un-swizzled)
+plus the remainder CSR must rebuild A_hat entry for entry, and every tile must belong to exactly one unit."""
 import pytest
 import torch
 
 from oracle import gcn_oracle as O
 from pytextgcn_b200.graph import GraphCSR
 from pytextgcn_b200.synthetic import make_graph
-from pytextgcn_b200.tc_plan import TILE_K, TILE_M, build_tc_plan, swizzled_offset, tf32_split
+from pytextgcn_b200.tc_plan import TILE_K, TILE_M, build_tc_plan, swizzled_offset
 
 
 def _csr(name, seed):
@@ -35,9 +34,7 @@ def test_plan_rebuilds_a_hat_exactly(name, density, n_sms):
     assert sorted(off.view(-1).tolist()) == list(range(TILE_M * TILE_K))          # the swizzle is a permutation of the tile
     A = _dense(n, tc.remainder.rowptr, tc.remainder.colidx, tc.remainder.val)
     for t in range(tc.n_tiles):
-        hi, lo = tc.A_tiles[t, 0].reshape(-1)[off], tc.A_tiles[t, 1].reshape(-1)[off]
-        assert bool(((hi.view(torch.int32) & 0x1FFF) == 0).all())                  # hi is a TF32 number
-        tile = hi.double() + lo.double()
+        tile = tc.A_tiles[t].reshape(-1)[off].double()
         rn = perm[int(tc.tile_rb[t]) * TILE_M:][:TILE_M]
         cn = perm[int(tc.tile_kb[t]) * TILE_K:][:TILE_K]
         vr, vc = rn >= 0, cn >= 0
@@ -70,11 +67,3 @@ def test_duplicate_entries_stay_in_the_remainder():
 def test_no_dense_block_gives_no_plan():
     n, rowptr, col, val, gr = _csr("tiny", 1)
     assert build_tc_plan(gr, min_density=0.9) is None
-
-
-def test_tf32_split_is_exact():
-    torch.manual_seed(0)
-    v = torch.randn(100000) * torch.logspace(-20, 20, 100000)
-    hi, lo = tf32_split(v)
-    assert torch.equal(hi + lo, v) and bool(((hi.view(torch.int32) & 0x1FFF) == 0).all())
-    assert bool((lo.abs() <= v.abs() * 2.0 ** -11).all())
