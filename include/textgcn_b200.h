@@ -141,18 +141,19 @@ typedef struct {
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
 
 /* (2b) Dense-tile part of a hybrid propagation on the tensor cores (csrc/spmm_tc.cu).  The nodes are ranked by
- * degree; the 128 x 32 blocks of A_hat (in rank space) that are dense enough are stored as dense TF32 hi/lo tiles and
+ * degree; the 128 x 16 blocks of A_hat (in rank space) that are dense enough are stored as dense TF32 hi/lo tiles and
  * multiplied with tcgen05.mma (3xTF32: fp32 accuracy), everything else stays in the CSR that tgcn_spmm gathers.
  * tgcn_spmm_tc packs the operand (transpose to K-major + hi/lo split, `Bt` workspace of
  * tgcn_spmm_tc_workspace_elems floats) and writes one 128 x F partial result per unit into part[unit slot]; the
  * following tgcn_spmm call (tc_part/tc_rank/tc_slot_ptr) adds them to the gathered remainder and runs the epilogue.
  * Replaces GCNConv.propagate for the dense blocks (models.py:20).  Plan: pytextgcn_b200/tc_plan.py. */
 typedef struct {
-  const float* A_tiles;     /* [n_tiles][128][32] fp32 values of A_hat, 128-byte swizzle pre-applied (see spmm_tc.cu) */
-  const int32_t* tile_kb;   /* [n_tiles] column block of each tile */
+  const float* A_tiles;     /* [n_tiles][128][16] fp32 values of A_hat, 64-byte swizzle pre-applied (see spmm_tc.cu) */
+  const int32_t* tile_kb;   /* [n_tiles] column block (16 ranks) of each tile */
+  int32_t n_tiles;
   const int32_t* units;     /* [n_units][4] = {tile_begin, tile_end, slot, row_block}; empty units (begin == end) allowed */
   int32_t n_units;
-  const int32_t* perm;      /* [n_col_blocks * 32] node id of each rank, -1 past the last node */
+  const int32_t* perm;      /* [n_col_blocks * 16] node id of each rank, -1 past the last node */
   int32_t n_col_blocks;
 } tgcn_tc_plan;
 int tgcn_spmm_tc(const tgcn_tc_plan* plan, const float* B, int64_t ldb, int32_t F, float* Bt, float* part, int64_t ldp,

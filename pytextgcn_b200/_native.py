@@ -44,7 +44,7 @@ class SpmmArgs(C.Structure):
 class TcPlanArgs(C.Structure):
     """Mirror of tgcn_tc_plan."""
     _fields_ = [
-        ("A_tiles", c_void), ("tile_kb", c_void), ("units", c_void), ("n_units", C.c_int32),
+        ("A_tiles", c_void), ("tile_kb", c_void), ("n_tiles", C.c_int32), ("units", c_void), ("n_units", C.c_int32),
         ("perm", c_void), ("n_col_blocks", C.c_int32),
     ]
 

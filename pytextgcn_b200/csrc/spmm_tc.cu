@@ -16,16 +16,16 @@
 // per product -- below the fp32 rounding of the 349-term sums themselves (tests/test_gpu_spmm_tc.py).
 //
 // Data (built once per graph by pytextgcn_b200/tc_plan.py, rank = position in the degree order):
-//   A_tiles  [n_tiles][128 rows][32 cols] fp32 values of A_hat, each 128-byte row stored with the 128-byte
-//            shared-memory swizzle already applied (16-byte chunk c of row r sits at chunk c ^ (r & 7)), so a
-//            tile is ONE 16 KB bulk copy; four "splitter" warps turn it into the hi / lo operand tiles in
+//   A_tiles  [n_tiles][128 rows][16 cols] fp32 values of A_hat, each 64-byte row stored with the 64-byte
+//            shared-memory swizzle already applied (16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)), so a
+//            tile is ONE 8 KB bulk copy; four "splitter" warps turn it into the hi / lo operand tiles in
 //            shared memory (elementwise, same positions: the layout the UMMA descriptor expects, K-major
-//            SWIZZLE_128B) -- half the HBM / L2->SM bytes of shipping hi and lo separately;
-//   tile_kb  [n_tiles] column block (32 ranks) of each tile; tiles of one row block are consecutive;
-//   units    {tile_begin, tile_end, slot, row_block}: <= 48 tiles of one row block; a unit's 128 x F partial
+//            SWIZZLE_64B) -- half the HBM / L2->SM bytes of shipping hi and lo separately;
+//   tile_kb  [n_tiles] column block (16 ranks) of each tile; tiles of one row block are consecutive;
+//   units    {tile_begin, tile_end, slot, row_block}: <= 96 tiles of one row block; a unit's 128 x F partial
 //            result goes to part[slot]; the slots of a row block are consecutive and tgcn_spmm's epilogue
 //            adds them, in slot order, to the gathered remainder of the row (deterministic);
-//   Bt       [n_col_blocks][2 (hi, lo)][Fp features][32 ranks] fp32, same swizzle: the operand transposed
+//   Bt       [n_col_blocks][2 (hi, lo)][Fp features][16 ranks] fp32, same swizzle: the operand transposed
 //            to K-major and split into hi/lo by k_tc_pack at every launch (B changes every step).
 //
 // Kernel k_tc_mma: persistent, one CTA per SM, 320 threads.  warp 0 = producer (cp.async.bulk into a 2-stage
@@ -39,10 +39,11 @@
 namespace tgcn {
 
 constexpr int TC_M = 128;
-constexpr int TC_K = 32;
-constexpr int TC_STAGES = 2;
+constexpr int TC_K = 16;             // 64-byte operand rows (SWIZZLE_64B): small stages, so that 4-5 of them are in flight
+constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_PREFETCH = 8;       // A tiles requested into L2 this many tiles ahead of their bulk copy
 constexpr int TC_THREADS = 320;
-constexpr uint32_t TC_A_PART = TC_M * TC_K * 4;      // 16 KB: the values of a tile, or one of its (hi, lo) operand tiles
+constexpr uint32_t TC_A_PART = TC_M * TC_K * 4;      // 8 KB: the values of a tile, or one of its (hi, lo) operand tiles
 constexpr uint32_t TC_ACC_COLS = 256;                // TMEM columns per accumulator (F <= 256)
 
 struct TcParams {
@@ -54,6 +55,8 @@ struct TcParams {
   float* part; int64_t ldp;
   int32_t Fp;      // MMA N: F rounded up to a multiple of 8
   int32_t F;       // columns stored
+  int32_t n_stages;
+  int32_t n_tiles;
 };
 
 // ---- PTX helpers: mbarrier, bulk copy, tcgen05 ----
@@ -89,15 +92,18 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
   asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
                ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// shared-memory matrix descriptor: K-major operand, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 bytes apart
+// shared-memory matrix descriptor: K-major operand, 64-byte rows, SWIZZLE_64B, 8-row groups 512 bytes apart
 // (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor; version 1 = Blackwell)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
   uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);   // start address, 16-byte units
   d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major layouts)
-  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                            // descriptor version
-  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  d |= (uint64_t)4 << 61;                            // SWIZZLE_64B
   return d;
+}
+__device__ __forceinline__ void tc_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 #define TC_LD_REGS8(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -117,22 +123,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
   // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic shared memory by hand
   const uint32_t raw = tc_smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t b_part = (uint32_t)p.Fp * 128u;               // bytes of one of (hi, lo) of an operand tile
+  const uint32_t b_part = (uint32_t)p.Fp * (TC_K * 4u);        // bytes of one of (hi, lo) of an operand tile
+  const int S = p.n_stages;
   const uint32_t stage_bytes = TC_A_PART + 2u * b_part;        // ring stage: A values, Bt hi, Bt lo
-  const uint32_t split0 = base + TC_STAGES * stage_bytes;      // two {A hi, A lo} operand buffers
+  const uint32_t split0 = base + (uint32_t)S * stage_bytes;    // two {A hi, A lo} operand buffers
   const uint32_t bars = split0 + 2u * 2u * TC_A_PART;          // 8-byte mbarriers
-  const uint32_t full0 = bars, empty0 = bars + 16, afull0 = bars + 32, aempty0 = bars + 48, tfull0 = bars + 64, tempty0 = bars + 80;
-  const uint32_t holder = bars + 96;                           // TMEM base address written by tcgen05.alloc
+  const uint32_t full0 = bars, empty0 = bars + 8 * TC_MAX_STAGES, afull0 = empty0 + 8 * TC_MAX_STAGES, aempty0 = afull0 + 16,
+                 tfull0 = aempty0 + 16, tempty0 = tfull0 + 16;
+  const uint32_t holder = tempty0 + 16;                        // TMEM base address written by tcgen05.alloc
   volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(tc_smem_raw + (holder - raw));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < S; ++s) {
       tc_mbar_init(full0 + 8 * s, 1);          // producer's arrive.expect_tx (+ the bytes of both bulk copies)
       tc_mbar_init(empty0 + 8 * s, 1 + 128);   // tcgen05.commit (Bt read) + the 128 splitter threads (A values read)
-      tc_mbar_init(afull0 + 8 * s, 128);       // splitter threads: hi / lo tiles written
-      tc_mbar_init(aempty0 + 8 * s, 1);        // tcgen05.commit: hi / lo tiles read
     }
-    for (int a = 0; a < 2; ++a) { tc_mbar_init(tfull0 + 8 * a, 1); tc_mbar_init(tempty0 + 8 * a, 128); }
+    for (int a = 0; a < 2; ++a) {
+      tc_mbar_init(afull0 + 8 * a, 128);       // splitter threads: hi / lo tiles written
+      tc_mbar_init(aempty0 + 8 * a, 1);        // tcgen05.commit: hi / lo tiles read
+      tc_mbar_init(tfull0 + 8 * a, 1);
+      tc_mbar_init(tempty0 + 8 * a, 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {   // one warp allocates both accumulators (512 columns = all of this SM's tensor memory)
@@ -150,9 +161,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
       int it = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const int4 un = __ldg(p.units + u);
+        for (int t = un.x; t < min(un.y, un.x + TC_PREFETCH); ++t) tc_prefetch_l2(p.A_tiles + (int64_t)t * (TC_M * TC_K), TC_A_PART);
         for (int t = un.x; t < un.y; ++t, ++it) {
-          const int s = it % TC_STAGES;
-          const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          if (t + TC_PREFETCH < p.n_tiles) tc_prefetch_l2(p.A_tiles + (int64_t)(t + TC_PREFETCH) * (TC_M * TC_K), TC_A_PART);
           tc_mbar_wait(empty0 + 8 * s, ph ^ 1u);               // MMAs and splitters are done with this stage
           const uint32_t st = base + s * stage_bytes;
           tc_mbar_arrive_expect_tx(full0 + 8 * s, stage_bytes);
@@ -177,12 +190,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * TC_ACC_COLS;
         for (int t = un.x; t < un.y; ++t, ++it) {
-          const int s = it % TC_STAGES;
-          const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+          const int s = it % S, a = it & 1;
+          const uint32_t ph = (uint32_t)(it / S) & 1u, sph = (uint32_t)(it >> 1) & 1u;
           tc_mbar_wait(full0 + 8 * s, ph);                     // the Bt tile has landed
-          tc_mbar_wait(afull0 + 8 * s, ph);                    // the splitters have written A hi / lo
+          tc_mbar_wait(afull0 + 8 * a, sph);                   // the splitters have written A hi / lo
           tc_fence_after();
-          const uint32_t st = base + s * stage_bytes, sp = split0 + s * (2u * TC_A_PART);
+          const uint32_t st = base + s * stage_bytes, sp = split0 + a * (2u * TC_A_PART);
           const uint64_t a_hi = tc_smem_desc(sp), a_lo = tc_smem_desc(sp + TC_A_PART);
           const uint64_t b_hi = tc_smem_desc(st + TC_A_PART), b_lo = tc_smem_desc(st + TC_A_PART + b_part);
 #pragma unroll
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
             tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
           }
           tc_commit(empty0 + 8 * s);                           // ring stage reusable once these MMAs are done
-          tc_commit(aempty0 + 8 * s);                          // so are the hi / lo tiles
+          tc_commit(aempty0 + 8 * a);                          // so are the hi / lo tiles
         }
         tc_commit(tfull0 + 8 * as);                            // accumulator complete
         ++ui;
@@ -206,11 +219,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int4 un = __ldg(p.units + u);
       for (int t = un.x; t < un.y; ++t, ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+        const int s = it % S, a = it & 1;
+        const uint32_t ph = (uint32_t)(it / S) & 1u, sph = (uint32_t)(it >> 1) & 1u;
         tc_mbar_wait(full0 + 8 * s, ph);                       // the tile's values have landed
-        tc_mbar_wait(aempty0 + 8 * s, ph ^ 1u);                // the MMAs that read the previous hi / lo tiles are done
-        const uint32_t src = base + s * stage_bytes, hi = split0 + s * (2u * TC_A_PART), lo = hi + TC_A_PART;
+        tc_mbar_wait(aempty0 + 8 * a, sph ^ 1u);               // the MMAs that read the previous hi / lo tiles are done
+        const uint32_t src = base + s * stage_bytes, hi = split0 + a * (2u * TC_A_PART), lo = hi + TC_A_PART;
 #pragma unroll
         for (int j = 0; j < (TC_M * TC_K / 4) / 128; ++j) {
           const uint32_t o = (uint32_t)(ts + 128 * j) * 16u;
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
                        "f"(v.z - __uint_as_float(h2)), "f"(v.w - __uint_as_float(h3)) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's reads
-        tc_mbar_arrive(afull0 + 8 * s);
+        tc_mbar_arrive(afull0 + 8 * a);
         tc_mbar_arrive(empty0 + 8 * s);
       }
     }
@@ -278,11 +291,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
   }
 }
 
-// Bt[kb][hi|lo][f][k] = split(B[perm[32 kb + k]][f]), swizzled: transposes the operand to K-major (the feature index
-// becomes the tile row, the 32 ranks of a column block its 128-byte row) and splits it into TF32 hi / residual lo.
+// Bt[kb][hi|lo][f][k] = split(B[perm[16 kb + k]][f]), swizzled: transposes the operand to K-major (the feature index
+// becomes the tile row, the 16 ranks of a column block its 64-byte row) and splits it into TF32 hi / residual lo.
 __global__ void __launch_bounds__(256) k_tc_pack(const float* __restrict__ B, int64_t ldb, const int32_t* __restrict__ perm,
                                                  int F, int Fp, float* __restrict__ Bt) {
-  extern __shared__ float tc_pack_smem[];          // [32][F + 1]
+  extern __shared__ float tc_pack_smem[];          // [TC_K][F + 1]
   const int kb = blockIdx.x;
   const int FS = F + 1;
   const int FQ = F >> 2;
@@ -295,10 +308,10 @@ __global__ void __launch_bounds__(256) k_tc_pack(const float* __restrict__ B, in
     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
   __syncthreads();
-  char* out_hi = reinterpret_cast<char*>(Bt) + (int64_t)kb * (2 * Fp * 128);
-  char* out_lo = out_hi + Fp * 128;
-  for (int i = threadIdx.x; i < Fp * 8; i += blockDim.x) {
-    const int f = i >> 3, ch = i & 7;
+  char* out_hi = reinterpret_cast<char*>(Bt) + (int64_t)kb * (2 * Fp * TC_K * 4);
+  char* out_lo = out_hi + Fp * TC_K * 4;
+  for (int i = threadIdx.x; i < Fp * (TC_K / 4); i += blockDim.x) {
+    const int f = i / (TC_K / 4), ch = i % (TC_K / 4);
     float hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -308,7 +321,7 @@ __global__ void __launch_bounds__(256) k_tc_pack(const float* __restrict__ B, in
       hi[j] = __uint_as_float(h);
       lo[j] = v - hi[j];
     }
-    const int off = f * 128 + ((ch ^ (f & 7)) << 4);
+    const int off = f * (TC_K * 4) + ((ch ^ ((f >> 1) & 3)) << 4);      // SWIZZLE_64B: 16-byte chunk ^= bits [1,3) of the row
     *reinterpret_cast<float4*>(out_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<float4*>(out_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
   }
@@ -346,9 +359,12 @@ extern "C" int tgcn_spmm_tc(const tgcn_tc_plan* plan, const float* B, int64_t ld
   TcParams p;
   p.A_tiles = plan->A_tiles; p.tile_kb = plan->tile_kb; p.units = reinterpret_cast<const int4*>(plan->units);
   p.n_units = plan->n_units; p.Bt = Bt; p.part = part; p.ldp = ldp; p.Fp = Fp; p.F = F;
-  const size_t stage = (size_t)TC_A_PART + 2 * (size_t)Fp * 128;
-  const size_t smem = TC_STAGES * stage + 4 * (size_t)TC_A_PART + 1024 /* alignment slack */ + 256 /* barriers */;
-  TGCN_CHECK_ARG(smem <= 227 * 1024, "spmm_tc: F = %d needs %zu bytes of shared memory", F, smem);
+  const size_t stage = (size_t)TC_A_PART + 2 * (size_t)Fp * TC_K * 4;
+  const size_t fixed = 4 * (size_t)TC_A_PART + 1024 /* alignment slack */ + 512 /* barriers */;
+  const int n_stages = (int)std::min<size_t>(TC_MAX_STAGES - 1, (227 * 1024 - fixed) / stage);
+  TGCN_CHECK_ARG(n_stages >= 2, "spmm_tc: F = %d does not leave room for two pipeline stages", F);
+  const size_t smem = n_stages * stage + fixed;
+  p.n_stages = n_stages; p.n_tiles = plan->n_tiles;
   TGCN_CUDA(cudaFuncSetAttribute(k_tc_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min<int>(sm_count(), plan->n_units);
   k_tc_mma<<<grid, TC_THREADS, smem, stream>>>(p);

@@ -6,7 +6,7 @@ The word-word part of a Text2GraphTransformer graph (PMI edges, text2graph.py:15
 words: ranked by degree, the blocks that pair a hub with anything are 5-40 % dense while the matrix as a whole
 is < 1 % dense.  Nodes are therefore ranked by degree (rank space is only a view: inputs and outputs stay in
 node order -- the operand is permuted while it is packed, partial rows are fetched by rank), the matrix is cut
-into 128 x 32 blocks, and a block becomes a dense tile when it holds at least `min_density` * 4096 entries.
+into 128 x 16 blocks, and a block becomes a dense tile when it holds at least `min_density` * 2048 entries.
 """
 from __future__ import annotations
 
@@ -16,8 +16,8 @@ from typing import Dict, Optional
 
 import torch
 
-TILE_M, TILE_K = 128, 32
-MAX_TILES_PER_UNIT = 48
+TILE_M, TILE_K = 128, 16
+MAX_TILES_PER_UNIT = 96
 
 
 @dataclass
@@ -26,10 +26,10 @@ class TcPlan:
     n_row_blocks: int
     n_col_blocks: int
     rank: torch.Tensor          # int32 [N]: rank of each node (0 = largest degree)
-    perm: torch.Tensor          # int32 [n_col_blocks * 32]: node of each rank, -1 past the end
+    perm: torch.Tensor          # int32 [n_col_blocks * 16]: node of each rank, -1 past the end
     tile_rb: torch.Tensor       # int32 [n_tiles] row block of each tile (sorted by (row block, column block))
     tile_kb: torch.Tensor       # int32 [n_tiles]
-    A_tiles: torch.Tensor       # fp32 [n_tiles, 128, 32]: the values of A_hat, rows swizzled (split into TF32 hi/lo in the kernel)
+    A_tiles: torch.Tensor       # fp32 [n_tiles, 128, 16]: the values of A_hat, rows swizzled (split into TF32 hi/lo in the kernel)
     units: torch.Tensor         # int32 [n_units, 4] = {tile_begin, tile_end, slot, row_block}
     slot_ptr: torch.Tensor      # int32 [n_row_blocks + 1]
     n_slots: int
@@ -59,14 +59,16 @@ class TcPlan:
         from . import _native
         p = _native.TcPlanArgs()
         p.A_tiles, p.tile_kb, p.units = self.A_tiles.data_ptr(), self.tile_kb.data_ptr(), self.units.data_ptr()
+        p.n_tiles = self.n_tiles
         p.n_units, p.perm, p.n_col_blocks = self.n_units, self.perm.data_ptr(), self.n_col_blocks
         return p
 
 
 def swizzled_offset(r: torch.Tensor, k: torch.Tensor) -> torch.Tensor:
-    """Float offset of element (row r, column k) inside a [rows][32] fp32 tile stored with the 128-byte swizzle:
-    the 16-byte chunk k // 4 of row r sits at chunk position (k // 4) ^ (r % 8)."""
-    return r * TILE_K + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3))
+    """Float offset of element (row r, column k) inside a [rows][16] fp32 tile stored with the 64-byte swizzle
+    (Swizzle<2,4,3>: address bits [4,6) ^= bits [7,9)): the 16-byte chunk k // 4 of the 64-byte row r sits at chunk
+    position (k // 4) ^ ((r // 2) % 4)."""
+    return r * TILE_K + ((((k >> 2) ^ ((r >> 1) & 3)) << 2) | (k & 3))
 
 
 def build_tc_plan(graph, min_density: float = 0.03, max_bytes: int = 2 << 30, n_sms: int = 148) -> Optional[TcPlan]:
@@ -91,7 +93,7 @@ def build_tc_plan(graph, min_density: float = 0.03, max_bytes: int = 2 << 30, n_
     perm[:n] = order.to(torch.int32)
     # ---- block census ----
     rr, rc = rank[rows], rank[cols]
-    key = (rr >> 7) * n_kb + (rc >> 5)
+    key = (rr >> 7) * n_kb + (rc >> 4)
     # duplicate (row, col) entries (possible in a general COO graph, never emitted by Text2GraphTransformer) cannot share
     # a dense cell: all but the first of each pair stay in the remainder
     full_key = rows * n + cols

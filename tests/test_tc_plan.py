@@ -46,7 +46,7 @@ def test_plan_rebuilds_a_hat_exactly(name, density, n_sms):
     for b, e, s, rb in tc.units.tolist():
         if e > b:
             cover[b:e] += 1
-            assert bool((tc.tile_rb[b:e] == rb).all()) and int(tc.slot_ptr[rb]) <= s < int(tc.slot_ptr[rb + 1]) and e - b <= 48
+            assert bool((tc.tile_rb[b:e] == rb).all()) and int(tc.slot_ptr[rb]) <= s < int(tc.slot_ptr[rb + 1]) and e - b <= 96
     assert bool((cover == 1).all())
     assert sorted(set(tc.units[:, 2].tolist()) - {-1}) == list(range(tc.n_slots))
     assert tc.n_units % min(n_sms, tc.n_slots) == 0
