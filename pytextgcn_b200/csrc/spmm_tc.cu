@@ -19,8 +19,7 @@
 //   A_tiles  [n_tiles][128 rows][16 cols] fp32 values of A_hat, each 64-byte row stored with the 64-byte
 //            shared-memory swizzle already applied (16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)), so a
 //            tile is ONE 8 KB bulk copy; four "splitter" warps turn it into the hi / lo operand tiles in
-//            shared memory (elementwise, same positions: the layout the UMMA descriptor expects, K-major
-//            SWIZZLE_64B) -- half the HBM / L2->SM bytes of shipping hi and lo separately;
+//            tensor memory -- half the HBM / L2->SM bytes of shipping hi and lo separately;
 //   tile_kb  [n_tiles] column block (16 ranks) of each tile; tiles of one row block are consecutive;
 //   units    {tile_begin, tile_end, slot, row_block}: <= 96 tiles of one row block; a unit's 128 x F partial
 //            result goes to part[slot]; the slots of a row block are consecutive and tgcn_spmm's epilogue
@@ -28,11 +27,13 @@
 //   Bt       [n_col_blocks][2 (hi, lo)][Fp features][16 ranks] fp32, same swizzle: the operand transposed
 //            to K-major and split into hi/lo by k_tc_pack at every launch (B changes every step).
 //
-// Kernel k_tc_mma: persistent, one CTA per SM, 320 threads.  warp 0 = producer (cp.async.bulk into a 2-stage
-// ring {A values, Bt tile}, mbarrier complete_tx), warp 1 = MMA issuer (one thread; tcgen05.commit releases the
-// stage and, after the last tile of a unit, publishes the accumulator), warps 2-5 = epilogue (tcgen05.ld 32
-// lanes x 32 columns per warp -> fp32 partial rows in global memory), warps 6-9 = splitters (A values -> TF32
-// hi + residual lo tiles, fence.proxy.async, mbarrier arrive).  Two 256-column accumulators in TMEM: the
+// Kernel k_tc_mma: persistent, one CTA per SM, 320 threads.  warp 0 = producer (cp.async.bulk into a 5-6 stage
+// ring {A values, Bt tile}, mbarrier complete_tx; A tiles prefetched into L2 ahead of time), warp 1 = MMA issuer
+// (one thread; A operand from TMEM, B operand from shared memory; tcgen05.commit releases the stage and, after
+// the last tile of a unit, publishes the accumulator), warps 2-5 = epilogue (tcgen05.ld 32 lanes x 32 columns
+// per warp -> fp32 partial rows in global memory), warps 6-9 = splitters (A values from shared memory -> TF32
+// hi + residual lo, tcgen05.st into TMEM).  Shared-memory bandwidth bounds 3xTF32 (every pass re-reads its
+// operands): with A in TMEM only the Bt tiles are read by the tensor core.  Two accumulators in TMEM: the
 // epilogue of unit i overlaps the MMAs of unit i+1.
 #include "common.cuh"
 
@@ -44,7 +45,7 @@ constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_PREFETCH = 8;       // A tiles requested into L2 this many tiles ahead of their bulk copy
 constexpr int TC_THREADS = 320;
 constexpr uint32_t TC_A_PART = TC_M * TC_K * 4;      // 8 KB: the values of a tile, or one of its (hi, lo) operand tiles
-constexpr uint32_t TC_ACC_COLS = 256;                // TMEM columns per accumulator (F <= 256)
+constexpr uint32_t TC_TMEM_COLS = 512;               // all of the SM's tensor memory: accumulator(s) + two {A hi, A lo} tiles
 
 struct TcParams {
   const float* __restrict__ A_tiles;
@@ -53,7 +54,8 @@ struct TcParams {
   int32_t n_units;
   const float* __restrict__ Bt;
   float* part; int64_t ldp;
-  int32_t Fp;      // MMA N: F rounded up to a multiple of 8
+  int32_t Fp;      // MMA N: F rounded up to a multiple of 16 (also the TMEM column stride of the accumulators)
+  int32_t n_acc;   // accumulators in TMEM: 2 (epilogue of unit i overlaps the MMAs of unit i+1) when 2 Fp + 64 <= 512, else 1
   int32_t F;       // columns stored
   int32_t n_stages;
   int32_t n_tiles;
@@ -87,11 +89,19 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], TF32 inputs, fp32 accumulate; issued by ONE thread for the CTA
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+// D[tmem] (+)= A[tmem] * B[smem], TF32 inputs, fp32 accumulate; issued by ONE thread for the CTA.  The A operand is
+// read from tensor memory (lane = row, one 32-bit column per K element): the A tile is then not re-read from shared
+// memory by each of the three passes -- shared-memory bandwidth is what bounds 3xTF32
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+               "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // shared-memory matrix descriptor: K-major operand, 64-byte rows, SWIZZLE_64B, 8-row groups 512 bytes apart
 // (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor; version 1 = Blackwell)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
@@ -126,8 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
   const uint32_t b_part = (uint32_t)p.Fp * (TC_K * 4u);        // bytes of one of (hi, lo) of an operand tile
   const int S = p.n_stages;
   const uint32_t stage_bytes = TC_A_PART + 2u * b_part;        // ring stage: A values, Bt hi, Bt lo
-  const uint32_t split0 = base + (uint32_t)S * stage_bytes;    // two {A hi, A lo} operand buffers
-  const uint32_t bars = split0 + 2u * 2u * TC_A_PART;          // 8-byte mbarriers
+  const uint32_t bars = base + (uint32_t)S * stage_bytes;      // 8-byte mbarriers
   const uint32_t full0 = bars, empty0 = bars + 8 * TC_MAX_STAGES, afull0 = empty0 + 8 * TC_MAX_STAGES, aempty0 = afull0 + 16,
                  tfull0 = aempty0 + 16, tempty0 = tfull0 + 16;
   const uint32_t holder = tempty0 + 16;                        // TMEM base address written by tcgen05.alloc
@@ -139,21 +148,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
       tc_mbar_init(empty0 + 8 * s, 1 + 128);   // tcgen05.commit (Bt read) + the 128 splitter threads (A values read)
     }
     for (int a = 0; a < 2; ++a) {
-      tc_mbar_init(afull0 + 8 * a, 128);       // splitter threads: hi / lo tiles written
+      tc_mbar_init(afull0 + 8 * a, 128);       // splitter threads: hi / lo tiles stored to TMEM
       tc_mbar_init(aempty0 + 8 * a, 1);        // tcgen05.commit: hi / lo tiles read
       tc_mbar_init(tfull0 + 8 * a, 1);
       tc_mbar_init(tempty0 + 8 * a, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {   // one warp allocates both accumulators (512 columns = all of this SM's tensor memory)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder), "r"(2u * TC_ACC_COLS) : "memory");
+  if (warp == 2) {   // one warp allocates all 512 columns of this SM's tensor memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder), "r"(TC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
+  const uint32_t tmem_a0 = tmem_base + (uint32_t)(p.n_acc * p.Fp);   // two {hi[16 cols], lo[16 cols]} A tiles behind the accumulators
 
   if (warp == 0) {
     // ---------------- producer: one thread issues two bulk copies per tile ----------------
@@ -184,26 +194,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const int4 un = __ldg(p.units + u);
         if (un.x >= un.y) continue;
-        const int as = ui & 1;
-        const uint32_t aph = (uint32_t)(ui >> 1) & 1u;
+        const int as = (p.n_acc == 2) ? (ui & 1) : 0;
+        const uint32_t aph = (uint32_t)((p.n_acc == 2) ? (ui >> 1) : ui) & 1u;
         tc_mbar_wait(tempty0 + 8 * as, aph ^ 1u);              // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * TC_ACC_COLS;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.Fp);
         for (int t = un.x; t < un.y; ++t, ++it) {
           const int s = it % S, a = it & 1;
           const uint32_t ph = (uint32_t)(it / S) & 1u, sph = (uint32_t)(it >> 1) & 1u;
           tc_mbar_wait(full0 + 8 * s, ph);                     // the Bt tile has landed
-          tc_mbar_wait(afull0 + 8 * a, sph);                   // the splitters have written A hi / lo
+          tc_mbar_wait(afull0 + 8 * a, sph);                   // the splitters have stored A hi / lo to TMEM
           tc_fence_after();
-          const uint32_t st = base + s * stage_bytes, sp = split0 + a * (2u * TC_A_PART);
-          const uint64_t a_hi = tc_smem_desc(sp), a_lo = tc_smem_desc(sp + TC_A_PART);
+          const uint32_t st = base + s * stage_bytes;
+          const uint32_t a_hi = tmem_a0 + (uint32_t)a * (2 * TC_K), a_lo = a_hi + TC_K;
           const uint64_t b_hi = tc_smem_desc(st + TC_A_PART), b_lo = tc_smem_desc(st + TC_A_PART + b_part);
 #pragma unroll
-          for (int ks = 0; ks < TC_K / 8; ++ks) {              // 8 TF32 columns (32 bytes) per instruction
-            const uint64_t adv = (uint64_t)(ks * 2);           // +32 bytes on the 16-byte start-address field
-            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (t > un.x || ks > 0) ? 1u : 0u);
-            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+          for (int ks = 0; ks < TC_K / 8; ++ks) {              // 8 TF32 columns per instruction
+            const uint64_t adv = (uint64_t)(ks * 2);           // B: +32 bytes on the 16-byte start-address field
+            const uint32_t ac = (uint32_t)(ks * 8);            // A: +8 TMEM columns
+            tc_mma_tf32_ts(d_tmem, a_hi + ac, b_hi + adv, idesc, (t > un.x || ks > 0) ? 1u : 0u);
+            tc_mma_tf32_ts(d_tmem, a_hi + ac, b_lo + adv, idesc, 1u);
+            tc_mma_tf32_ts(d_tmem, a_lo + ac, b_hi + adv, idesc, 1u);
           }
           tc_commit(empty0 + 8 * s);                           // ring stage reusable once these MMAs are done
           tc_commit(aempty0 + 8 * a);                          // so are the hi / lo tiles
@@ -213,8 +224,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
       }
     }
   } else if (warp >= 6) {
-    // ---------------- splitters: A values -> TF32 hi + residual lo, same (swizzled) positions ----------------
-    const int ts = threadIdx.x - 6 * 32;
+    // ---------------- splitters: A values (shared memory) -> TF32 hi + residual lo (tensor memory) ----------------
+    // thread = row of the tile = TMEM lane (warps 6..9 own the lane quarters 2, 3, 0, 1); a 64-byte row is 4 chunks of
+    // 16 bytes, logical chunk c stored at chunk c ^ ((row >> 1) & 3) (the swizzle keeps these row-wise reads conflict-free)
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t xr = (uint32_t)((row >> 1) & 3);
     int it = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int4 un = __ldg(p.units + u);
@@ -222,25 +236,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
         const int s = it % S, a = it & 1;
         const uint32_t ph = (uint32_t)(it / S) & 1u, sph = (uint32_t)(it >> 1) & 1u;
         tc_mbar_wait(full0 + 8 * s, ph);                       // the tile's values have landed
-        tc_mbar_wait(aempty0 + 8 * a, sph ^ 1u);               // the MMAs that read the previous hi / lo tiles are done
-        const uint32_t src = base + s * stage_bytes, hi = split0 + a * (2u * TC_A_PART), lo = hi + TC_A_PART;
+        const uint32_t src = base + s * stage_bytes + (uint32_t)row * (TC_K * 4);
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < (TC_M * TC_K / 4) / 128; ++j) {
-          const uint32_t o = (uint32_t)(ts + 128 * j) * 16u;
+        for (int c = 0; c < 4; ++c) {
           float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + o));
-          uint32_t h0, h1, h2, h3;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(v.x));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1) : "f"(v.y));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h2) : "f"(v.z));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h3) : "f"(v.w));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi + o), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + o), "f"(v.x - __uint_as_float(h0)), "f"(v.y - __uint_as_float(h1)),
-                       "f"(v.z - __uint_as_float(h2)), "f"(v.w - __uint_as_float(h3)) : "memory");
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + (((uint32_t)c ^ xr) << 4)));
+          const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi[4 * c + j]) : "f"(f[j]));
+            lo[4 * c + j] = __float_as_uint(f[j] - __uint_as_float(hi[4 * c + j]));
+          }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's reads
+        tc_mbar_arrive(empty0 + 8 * s);                        // this thread is done with the stage's A values
+        tc_mbar_wait(aempty0 + 8 * a, sph ^ 1u);               // the MMAs that read the previous tiles in this TMEM buffer are done
+        tc_fence_after();
+        const uint32_t ta = tmem_a0 + (uint32_t)a * (2 * TC_K) + ((uint32_t)(q * 32) << 16);
+        tc_st16(ta, hi);
+        tc_st16(ta + TC_K, lo);
+        tc_wait_st();
+        tc_fence_before();
         tc_mbar_arrive(afull0 + 8 * a);
-        tc_mbar_arrive(empty0 + 8 * s);
       }
     }
   } else {
@@ -250,13 +267,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int4 un = __ldg(p.units + u);
       if (un.x >= un.y) continue;
-      const int as = ui & 1;
-      const uint32_t aph = (uint32_t)(ui >> 1) & 1u;
+      const int as = (p.n_acc == 2) ? (ui & 1) : 0;
+      const uint32_t aph = (uint32_t)((p.n_acc == 2) ? (ui >> 1) : ui) & 1u;
       tc_mbar_wait(tfull0 + 8 * as, aph);
       tc_fence_after();
       const int row = q * 32 + lane;
       float* dst = p.part + ((int64_t)un.z * TC_M + row) * p.ldp;
-      const uint32_t taddr = tmem_base + (uint32_t)as * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(as * p.Fp) + ((uint32_t)(q * 32) << 16);
       int c = 0;
       for (; c + 32 <= p.Fp; c += 32) {
         uint32_t v[32];
@@ -287,7 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * TC_ACC_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
 }
 
@@ -333,7 +350,7 @@ using namespace tgcn;
 
 extern "C" int tgcn_spmm_tc_workspace_elems(int32_t F, int64_t n_col_blocks, int64_t* bt_elems_out) {
   TGCN_CHECK_ARG(bt_elems_out && F > 0 && n_col_blocks >= 0, "spmm_tc_workspace_elems: bad arguments");
-  const int64_t Fp = (F + 7) / 8 * 8;
+  const int64_t Fp = (F + 15) / 16 * 16;
   *bt_elems_out = n_col_blocks * 2 * Fp * TC_K;
   return TGCN_OK;
 }
@@ -349,7 +366,7 @@ extern "C" int tgcn_spmm_tc(const tgcn_tc_plan* plan, const float* B, int64_t ld
   TGCN_CHECK_ARG((((uintptr_t)plan->A_tiles | (uintptr_t)Bt) & 127) == 0, "spmm_tc: A_tiles / Bt must be 128-byte aligned");
   TGCN_CHECK_ARG(plan->n_units >= 0 && plan->n_col_blocks > 0, "spmm_tc: bad plan sizes");
   if (plan->n_units == 0) return TGCN_OK;
-  const int Fp = (F + 7) / 8 * 8;
+  const int Fp = (F + 15) / 16 * 16;      // tcgen05.mma with A in TMEM and M = 128: N must be a multiple of 16
   {
     const size_t smem = (size_t)TC_K * (F + 1) * sizeof(float);
     if (smem > 48 * 1024) TGCN_CUDA(cudaFuncSetAttribute(k_tc_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -360,8 +377,9 @@ extern "C" int tgcn_spmm_tc(const tgcn_tc_plan* plan, const float* B, int64_t ld
   p.A_tiles = plan->A_tiles; p.tile_kb = plan->tile_kb; p.units = reinterpret_cast<const int4*>(plan->units);
   p.n_units = plan->n_units; p.Bt = Bt; p.part = part; p.ldp = ldp; p.Fp = Fp; p.F = F;
   const size_t stage = (size_t)TC_A_PART + 2 * (size_t)Fp * TC_K * 4;
-  const size_t fixed = 4 * (size_t)TC_A_PART + 1024 /* alignment slack */ + 512 /* barriers */;
-  const int n_stages = (int)std::min<size_t>(TC_MAX_STAGES - 1, (227 * 1024 - fixed) / stage);
+  const size_t fixed = 1024 /* alignment slack */ + 512 /* barriers */;
+  const int n_stages = (int)std::min<size_t>(TC_MAX_STAGES, (227 * 1024 - fixed) / stage);
+  p.n_acc = (2 * Fp + 4 * TC_K <= (int)TC_TMEM_COLS) ? 2 : 1;
   TGCN_CHECK_ARG(n_stages >= 2, "spmm_tc: F = %d does not leave room for two pipeline stages", F);
   const size_t smem = n_stages * stage + fixed;
   p.n_stages = n_stages; p.n_tiles = plan->n_tiles;

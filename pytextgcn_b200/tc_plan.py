@@ -47,7 +47,7 @@ class TcPlan:
         """(Bt workspace, partial-row buffer) for operand width F, allocated once."""
         b = self._bufs.get(F)
         if b is None:
-            Fp = (F + 7) // 8 * 8
+            Fp = (F + 15) // 16 * 16
             dev = self.A_tiles.device
             bt = torch.empty(self.n_col_blocks * 2 * Fp * TILE_K, dtype=torch.float32, device=dev)
             part = torch.empty((max(self.n_slots, 1) * TILE_M, F), dtype=torch.float32, device=dev)
