@@ -137,10 +137,6 @@ typedef struct {
    * entries OUTSIDE the dense tiles and, before the epilogue, row r adds part[s][tc_rank[r] % 128][:] for the slots
    * s in [tc_slot_ptr[tc_rank[r] / 128], tc_slot_ptr[tc_rank[r] / 128 + 1]), in slot order. */
   const float* tc_part; int64_t tc_ld; const int32_t* tc_rank; const int32_t* tc_slot_ptr;
-  /* optional raw partial result of another tgcn_spmm call over part of the entries (fp32 [rows][raw_ld], no epilogue
-   * applied): added to the row before the dense-tile partials and the epilogue.  Lets the gathered part and the
-   * tensor-core part of a hybrid propagation run concurrently on two streams, joined by a call over an empty CSR. */
-  const float* raw_in; int64_t raw_ld;
 } tgcn_spmm_args;
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
 

@@ -26,7 +26,6 @@ struct SpmmParams {
   float ad_b1, ad_b2, ad_eps; float* ad_mirror;
   // dense-tile partial results of tgcn_spmm_tc, added to the row before the epilogue (hybrid propagation)
   const float* __restrict__ tc_part; int64_t tc_ld; const int32_t* __restrict__ tc_rank; const int32_t* __restrict__ tc_slot_ptr;
-  const float* __restrict__ raw_in; int64_t raw_ld;   // raw partial rows of another launch, added before the epilogue
 };
 
 // ---- loads of 16 bytes of the dense operand -> 4 (fp32) or 8 (bf16) floats ----
@@ -213,11 +212,6 @@ static inline int fill_spmm_params(const tgcn_spmm_args* a, SpmmParams* p) {
   p->ad_ld = a->adam_ld; p->ad_hyp = a->adam_hyper_dev; p->ad_b1 = a->adam_beta1; p->ad_b2 = a->adam_beta2; p->ad_eps = a->adam_eps;
   p->ad_mirror = (float*)a->adam_param_mirror_mc;
   p->tc_part = a->tc_part; p->tc_ld = a->tc_ld; p->tc_rank = a->tc_rank; p->tc_slot_ptr = a->tc_slot_ptr;
-  p->raw_in = a->raw_in; p->raw_ld = a->raw_ld;
-  if (p->raw_in) {
-    TGCN_CHECK_ARG(p->raw_ld % 4 == 0 && p->raw_ld >= a->F && ((uintptr_t)p->raw_in & 15) == 0 && a->b_dtype == TGCN_F32,
-                   "spmm: raw_in needs fp32 operands and a 16-byte aligned buffer with raw_ld %% 4 == 0");
-  }
   if (p->tc_part) {
     TGCN_CHECK_ARG(p->tc_rank && p->tc_slot_ptr && p->tc_ld % 4 == 0 && p->tc_ld >= a->F && ((uintptr_t)p->tc_part & 15) == 0,
                    "spmm: dense-tile partials need tc_rank, tc_slot_ptr and a 16-byte aligned buffer with tc_ld %% 4 == 0");

@@ -56,8 +56,7 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
          drop_mode: int = DROP_NONE, drop_p: float = 0.0, keep_mask: Optional[torch.Tensor] = None,
          philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0,
          W_proj: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
-         want_out: bool = True, adam: Optional[dict] = None, tc=None, tc_graph_ok: bool = False,
-         raw_in: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+         want_out: bool = True, adam: Optional[dict] = None, tc=None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """C = epi(A_hat[rows of plan] @ B[:, :F]) (+ P = C @ W_proj).  See tgcn_spmm.
     tc: a TcPlan whose dense-tile partial rows (already computed by tgcn_spmm_tc for this B, see spmm_hybrid) are
     added to every row before the epilogue; `graph` must then be the plan's remainder.
@@ -129,12 +128,8 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
         if P is None:
             P = torch.zeros((n_out, pad4(n_proj)), dtype=torch.float32, device=B.device)
         a.W_proj, a.n_proj, a.P, a.ldp = W_proj.data_ptr(), n_proj, P.data_ptr(), P.stride(0)
-    if raw_in is not None:
-        if raw_in.dtype != torch.float32 or raw_in.stride(1) != 1 or raw_in.shape[0] < n_out or raw_in.shape[1] < F:
-            raise RuntimeError("spmm: bad raw_in tensor")
-        a.raw_in, a.raw_ld = raw_in.data_ptr(), raw_in.stride(0)
     if tc is not None:
-        if graph is not tc.remainder and not tc_graph_ok:
+        if graph is not tc.remainder:
             raise RuntimeError("spmm: with tc=..., graph must be the plan's remainder CSR")
         part = tc.buffers(F)[1]
         a.tc_part, a.tc_ld, a.tc_rank, a.tc_slot_ptr = part.data_ptr(), part.stride(0), tc.rank.data_ptr(), tc.slot_ptr.data_ptr()
@@ -143,16 +138,11 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
     return out, P
 
 
-def spmm_hybrid(tc, B: torch.Tensor, *, F: Optional[int] = None, side_stream: Optional[torch.cuda.Stream] = None, **kw):
+def spmm_hybrid(tc, B: torch.Tensor, *, F: Optional[int] = None, **kw):
     """The same operation as spmm() on the graph `tc` was built from, computed in two parts: the dense blocks on the
     tensor cores (tgcn_spmm_tc: operand pack + tcgen05 3xTF32 tiles -> partial rows), the remaining entries by the gather
-    kernel; the partial rows are added before bias / activation / dropout / Adam.  Same keyword arguments as spmm()
-    (bias, act, dropout, out, adam, ...); fp32 operands with 8 <= F <= 256 only.
-
-    side_stream=None: three launches in a row (pack + MMA, then the gather kernel whose epilogue adds the partial rows).
-    side_stream=<stream>: the tensor-core part runs on that stream WHILE the gather kernel accumulates the remaining
-    entries into a raw buffer on the current stream (the two parts use different units of the SM: tensor pipe + bulk
-    copies vs L1 fills); a last launch over an empty CSR joins the two and runs the epilogue."""
+    kernel, whose epilogue adds the partial rows before bias / activation / dropout / Adam.  Same keyword arguments as
+    spmm() (bias, act, dropout, out, adam, ...); fp32 operands with 8 <= F <= 256 only."""
     _need_cuda(B)
     lib = _native.load()
     F = int(B.shape[1]) if F is None else int(F)
@@ -160,24 +150,10 @@ def spmm_hybrid(tc, B: torch.Tensor, *, F: Optional[int] = None, side_stream: Op
         raise RuntimeError("spmm_hybrid: B must be a row-major fp32 matrix")
     bt, part = tc.buffers(F)
     cp = tc.c_struct()
-
-    def dense_part():
-        with torch.cuda.device(B.device):
-            _native.check(lib.tgcn_spmm_tc(C.byref(cp), B.data_ptr(), B.stride(0), F, bt.data_ptr(), part.data_ptr(), part.stride(0),
-                                           _stream()))
-    plan = kw.pop("plan", None) or tc.remainder.plan()
-    if side_stream is None:
-        dense_part()
-        return spmm(tc.remainder, B, F=F, tc=tc, plan=plan, **kw)
-    main = torch.cuda.current_stream()
-    side_stream.wait_stream(main)
-    with torch.cuda.stream(side_stream):
-        dense_part()
-    raw = tc.raw_buffer(F)
-    spmm(tc.remainder, B, F=F, plan=plan, out=raw)                        # gathered part, no epilogue
-    main.wait_stream(side_stream)
-    empty, eplan = tc.empty_graph()
-    return spmm(empty, B, F=F, plan=eplan, tc=tc, tc_graph_ok=True, raw_in=raw, **kw)   # join + epilogue
+    with torch.cuda.device(B.device):
+        _native.check(lib.tgcn_spmm_tc(C.byref(cp), B.data_ptr(), B.stride(0), F, bt.data_ptr(), part.data_ptr(), part.stride(0),
+                                       _stream()))
+    return spmm(tc.remainder, B, F=F, tc=tc, **kw)
 
 
 def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[torch.Tensor], n_mask_total: int,

@@ -37,7 +37,7 @@ class TcPlan:
     nnz_dense: int
     remainder: "object"         # GraphCSR of the entries outside the tiles
     min_density: float
-    _bufs: Dict[object, object] = field(default_factory=dict)
+    _bufs: Dict[int, tuple] = field(default_factory=dict)
 
     @property
     def n_units(self) -> int:
@@ -54,27 +54,6 @@ class TcPlan:
             b = (bt, part)
             self._bufs[F] = b
         return b
-
-    def raw_buffer(self, F: int) -> torch.Tensor:
-        """[N, F] fp32 buffer for the gathered part of a two-stream hybrid propagation."""
-        b = self._bufs.get(("raw", F))
-        if b is None:
-            b = torch.empty((self.n_nodes, F), dtype=torch.float32, device=self.A_tiles.device)
-            self._bufs[("raw", F)] = b
-        return b
-
-    def empty_graph(self):
-        """(CSR without entries, its one-chunk-per-row plan): the join launch of the two-stream mode walks it."""
-        e = self._bufs.get("empty")
-        if e is None:
-            from .graph import GraphCSR
-            dev = self.A_tiles.device
-            g = GraphCSR(self.n_nodes, torch.zeros(self.n_nodes + 1, dtype=torch.int32, device=dev),
-                         torch.zeros(0, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.float32, device=dev), None)
-            g._symmetric = False
-            e = (g, g.plan(chunk_nnz=2048))
-            self._bufs["empty"] = e
-        return e
 
     def c_struct(self):
         from . import _native

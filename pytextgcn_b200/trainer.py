@@ -26,7 +26,7 @@ class TextGCNTrainer:
                  use_cuda_graph: bool = True, seed: int = 0, chunk_nnz: Optional[int] = None,
                  graph: Optional[GraphCSR] = None, assume_symmetric: bool = False, eval_mode: str = "layered",
                  fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True, restrict_rows: bool = True,
-                 tensor_cores: Optional[bool] = None, tc_min_density: float = 0.03, tc_two_streams: bool = True):
+                 tensor_cores: Optional[bool] = None, tc_min_density: float = 0.03):
         if len(gcn.layers) != 2:
             raise NotImplementedError("TextGCNTrainer fuses the 2-layer TextGCN (the configuration of every reference script)")
         l0, l1 = gcn.layers
@@ -56,7 +56,6 @@ class TextGCNTrainer:
         # Hybrid hidden-wide propagation (csrc/spmm_tc.cu): the dense blocks of A_hat on the tensor cores (3xTF32, fp32
         # accuracy), the rest gathered as before.  None = use it when the graph has dense blocks worth it.
         self.tc = self.tc_t = None
-        self._tc_side = torch.cuda.Stream(device=self.dev, priority=-1) if tc_two_streams else None   # tensor-core part
         Hh = int(gcn.layers[0].weight.shape[1])
         if tensor_cores and not (Hh % 4 == 0 and 64 <= Hh <= 256):
             raise RuntimeError("tensor_cores=True needs a hidden width that is a multiple of 4 in [64, 256]")
@@ -225,7 +224,7 @@ class TextGCNTrainer:
         """Hidden-wide propagation A_hat B (or A_hat^T B) with the fused epilogue `kw`: hybrid when a plan exists."""
         tc = self.tc_t if transposed else self.tc
         if tc is not None and kw.get("W_proj") is None:
-            return ops.spmm_hybrid(tc, B, F=self.H, plan=tc.remainder.plan(), side_stream=self._tc_side, **kw)
+            return ops.spmm_hybrid(tc, B, F=self.H, plan=tc.remainder.plan(), **kw)
         graph, plan = (self.graph_t, self.plan_t) if transposed else (self.graph, self.plan)
         return ops.spmm(graph, B, F=self.H, plan=plan, **kw)
 

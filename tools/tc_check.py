@@ -74,14 +74,8 @@ def main():
     def dense_only():
         _native.check(lib.tgcn_spmm_tc(C.byref(cp), B.data_ptr(), B.stride(0), F, bt.data_ptr(), part.data_ptr(), part.stride(0),
                                        torch.cuda.current_stream().cuda_stream))
-    side = torch.cuda.Stream(priority=-1)
-    out3, _ = ops.spmm_hybrid(tc, B, bias=bias, plan=lib_plan, side_stream=side)
-    torch.cuda.synchronize()
-    print(json.dumps({"two_stream_vs_fp64": float((out3.double() - z64).abs().max()) / den,
-                      "two_stream_equals_sequential": bool(torch.equal(out3, out))}), flush=True)
     t = {"gather_ms": timed(lambda: ops.spmm(gr, B, bias=bias, out=ref)),
          "hybrid_ms": timed(lambda: ops.spmm_hybrid(tc, B, bias=bias, plan=lib_plan, out=out)),
-         "hybrid_two_stream_ms": timed(lambda: ops.spmm_hybrid(tc, B, bias=bias, plan=lib_plan, out=out, side_stream=side)),
          "dense_part_ms": timed(dense_only),
          "remainder_part_ms": timed(lambda: ops.spmm(tc.remainder, B, bias=bias, plan=lib_plan, out=out, tc=tc))}
     print(json.dumps(t), flush=True)
