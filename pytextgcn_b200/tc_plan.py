@@ -71,8 +71,17 @@ def swizzled_offset(r: torch.Tensor, k: torch.Tensor) -> torch.Tensor:
     return r * TILE_K + ((((k >> 2) ^ ((r >> 1) & 3)) << 2) | (k & 3))
 
 
-def build_tc_plan(graph, min_density: float = 0.03, max_bytes: int = 2 << 30, n_sms: int = 148) -> Optional[TcPlan]:
-    """Returns None when no block of the graph qualifies."""
+def build_tc_plan(graph, min_density: float = 0.05, max_bytes: int = 2 << 30, n_sms: int = 148,
+                  width: int = 256, max_operand_bytes: int = 104 << 20) -> Optional[TcPlan]:
+    """Returns None when no block of the graph qualifies.
+
+    min_density: a 128 x 16 block becomes a dense tile at >= min_density * 2048 entries.  Measured on B200 (20NG-shape,
+        F = 200, profiles/r02_hybrid_spmm.json): 0.05 -> 0.656 ms per propagation, 0.03 -> 0.682, 0.02 -> 0.716 (gather
+        kernel alone: 0.879): below ~5 % a tile costs more tensor-core time than the gathers it replaces.
+    max_bytes: cap on the tile storage (densest blocks are kept).
+    width / max_operand_bytes: the packed operand Bt (2 x 4 bytes x width per rank) must stay L2-resident while the
+        tiles stream through, so only column blocks of the first max_operand_bytes / (8 * width) ranks become tiles
+        (the hub columns); with Bt in HBM every tile would pull its 2 x 64 x width operand bytes from DRAM."""
     from .graph import GraphCSR
     dev = graph.rowptr.device
     n = graph.n_nodes
@@ -103,7 +112,10 @@ def build_tc_plan(graph, min_density: float = 0.03, max_bytes: int = 2 << 30, n_
         dup_sorted[1:] = srt.values[1:] == srt.values[:-1]
     is_dup = torch.zeros(nnz, dtype=torch.bool, device=dev)
     is_dup[srt.indices] = dup_sorted
-    ukeys, counts = torch.unique(key[~is_dup], return_counts=True)
+    Fp = (int(width) + 15) // 16 * 16
+    kb_limit = max(1, min(n_kb, int(max_operand_bytes // (2 * Fp * TILE_K * 4))))
+    eligible = ~is_dup & ((rc >> 4) < kb_limit)
+    ukeys, counts = torch.unique(key[eligible], return_counts=True)
     thr = max(1, int(round(min_density * TILE_M * TILE_K)))
     cand = counts >= thr
     if int(cand.sum().item()) == 0:
@@ -119,7 +131,7 @@ def build_tc_plan(graph, min_density: float = 0.03, max_bytes: int = 2 << 30, n_
     tile_kb = (sel_keys % n_kb).to(torch.int32)
     # ---- split the entries ----
     pos = torch.searchsorted(sel_keys, key).clamp_(max=n_tiles - 1)
-    dense = (sel_keys[pos] == key) & ~is_dup
+    dense = (sel_keys[pos] == key) & eligible
     A = torch.zeros((n_tiles, TILE_M * TILE_K), dtype=torch.float32, device=dev)
     t = pos[dense]
     off = swizzled_offset(rr[dense] & (TILE_M - 1), rc[dense] & (TILE_K - 1))
@@ -157,5 +169,6 @@ def build_tc_plan(graph, min_density: float = 0.03, max_bytes: int = 2 << 30, n_
     units[dst, 1] = u_end[by_len].to(torch.int32)
     units[dst, 2] = u_slot[by_len].to(torch.int32)
     units[dst, 3] = u_rb[by_len].to(torch.int32)
-    return TcPlan(n, n_rb, n_kb, rank.to(torch.int32), perm, tile_rb, tile_kb, A.view(n_tiles, TILE_M, TILE_K), units,
+    n_kb_used = int(tile_kb.max().item()) + 1            # the operand is packed only up to the last column block in use
+    return TcPlan(n, n_rb, n_kb_used, rank.to(torch.int32), perm, tile_rb, tile_kb, A.view(n_tiles, TILE_M, TILE_K), units,
                   slot_ptr.to(torch.int32), n_slots, n_tiles, int(dense.sum().item()), rem, float(min_density))

@@ -26,7 +26,7 @@ class TextGCNTrainer:
                  use_cuda_graph: bool = True, seed: int = 0, chunk_nnz: Optional[int] = None,
                  graph: Optional[GraphCSR] = None, assume_symmetric: bool = False, eval_mode: str = "layered",
                  fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True, restrict_rows: bool = True,
-                 tensor_cores: Optional[bool] = None, tc_min_density: float = 0.03):
+                 tensor_cores: Optional[bool] = None, tc_min_density: float = 0.05):
         if len(gcn.layers) != 2:
             raise NotImplementedError("TextGCNTrainer fuses the 2-layer TextGCN (the configuration of every reference script)")
         l0, l1 = gcn.layers
@@ -62,10 +62,11 @@ class TextGCNTrainer:
         if (tensor_cores or (tensor_cores is None and self.graph.nnz >= 200_000)) and Hh % 4 == 0 and 64 <= Hh <= 256:
             from .tc_plan import build_tc_plan
             n_sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
-            tc = build_tc_plan(self.graph, min_density=tc_min_density, n_sms=n_sms)
+            tc = build_tc_plan(self.graph, min_density=tc_min_density, n_sms=n_sms, width=Hh)
             if tc is not None and (tensor_cores or tc.nnz_dense >= 0.15 * self.graph.nnz):
                 self.tc = tc
-                self.tc_t = tc if self.graph_t is self.graph else build_tc_plan(self.graph_t, min_density=tc_min_density, n_sms=n_sms)
+                self.tc_t = tc if self.graph_t is self.graph else build_tc_plan(self.graph_t, min_density=tc_min_density,
+                                                                                n_sms=n_sms, width=Hh)
 
         self.act = ops.ACT_RELU if gcn.apply_activation else ops.ACT_NONE
         self.p = float(gcn.dropout)

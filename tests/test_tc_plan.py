@@ -67,3 +67,11 @@ def test_duplicate_entries_stay_in_the_remainder():
 def test_no_dense_block_gives_no_plan():
     n, rowptr, col, val, gr = _csr("tiny", 1)
     assert build_tc_plan(gr, min_density=0.9) is None
+
+
+def test_operand_cap_restricts_tiles_to_hub_column_blocks():
+    n, rowptr, col, val, gr = _csr("small", 2)
+    full = build_tc_plan(gr, min_density=0.01, n_sms=8, width=64)
+    capped = build_tc_plan(gr, min_density=0.01, n_sms=8, width=64, max_operand_bytes=10 * 2 * 64 * TILE_K * 4)   # 10 column blocks
+    assert capped is not None and capped.n_col_blocks <= 10 and int(capped.tile_kb.max()) < 10
+    assert 0 < capped.nnz_dense < full.nnz_dense and capped.nnz_dense + capped.remainder.nnz == gr.nnz

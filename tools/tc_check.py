@@ -24,7 +24,7 @@ def main():
     n = int(g.x.shape[0])
     gr = upload_graph(g.edge_index.T.contiguous().to(dev).T, g.edge_attr.to(dev), n)
     t0 = time.perf_counter()
-    tc = build_tc_plan(gr, min_density=dens, n_sms=torch.cuda.get_device_properties(dev).multi_processor_count)
+    tc = build_tc_plan(gr, min_density=dens, n_sms=torch.cuda.get_device_properties(dev).multi_processor_count, width=F)
     torch.cuda.synchronize()
     info = {"shape": shape, "F": F, "min_density": dens, "plan_s": time.perf_counter() - t0, "nnz": gr.nnz}
     if tc is None:
