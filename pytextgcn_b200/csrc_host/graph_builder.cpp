@@ -26,6 +26,8 @@
 #include <thread>
 #include <vector>
 
+#include "../../include/textgcn_host.h"
+
 namespace {
 
 struct PairTable {              // open addressing, linear probing, key = i * V + j (i <= j), 0xFFFF.. = empty

@@ -59,7 +59,11 @@ class TextGCNTrainer:
         Hh = int(gcn.layers[0].weight.shape[1])
         if tensor_cores and not (Hh % 4 == 0 and 64 <= Hh <= 256):
             raise RuntimeError("tensor_cores=True needs a hidden width that is a multiple of 4 in [64, 256]")
-        if (tensor_cores or (tensor_cores is None and self.graph.nnz >= 200_000)) and Hh % 4 == 0 and 64 <= Hh <= 256:
+        # auto mode: graphs big enough to matter whose gathered operand (N x H fp32) is L2-resident -- beyond that the gather
+        # kernel is bound by L2 misses on the non-hub columns, which the tensor-core part does not relieve (measured on the
+        # 1.2 M-node graph: 11.7 ms hybrid vs 11.4 ms gather, profiles/r02_hybrid_spmm.json)
+        auto = tensor_cores is None and self.graph.nnz >= 200_000 and self.n * ((Hh + 15) // 16 * 16) * 8 <= (104 << 20)
+        if (tensor_cores or auto) and Hh % 4 == 0 and 64 <= Hh <= 256:
             from .tc_plan import build_tc_plan
             n_sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
             tc = build_tc_plan(self.graph, min_density=tc_min_density, n_sms=n_sms, width=Hh)
