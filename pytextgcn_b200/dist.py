@@ -162,15 +162,21 @@ class DistTextGCNTrainer:
                  rank: int, world: int, dev: torch.device, seed: int = 0, betas=(0.9, 0.999), eps: float = 1e-8,
                  graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None,
                  use_cuda_graph: bool = False, exchange: str = "peer", fused_stores: bool = True,
-                 fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True):
+                 fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True, restrict_rows: bool = True):
         import torch.distributed as dist
         from . import ops
         from .graph import upload_graph
         self.dist, self.ops = dist, ops
         self.rank, self.world, self.dev = rank, world, dev
+        from .models import decode_features
         n = int(g.x.shape[0])
-        if int(g.x.shape[1]) != n:
-            raise NotImplementedError("the row-partitioned trainer handles x = I (no hierarchy features)")
+        feat = decode_features(g.x, getattr(g, "n_vocab", None))
+        if feat is None:
+            raise RuntimeError("the row-partitioned trainer expects featureless input x = I or [I | F] (text2graph.py:226-246)")
+        # x = [I | F] (perlevel_dbpedia.py:140-141): W1 has c_prev extra rows.  They are replicated on every rank; the
+        # exchanged layer-1 operand is then X W1 = W1[:N] + F W1[N:] (own rows computed locally) instead of W1 itself.
+        self.c_prev = 0 if feat.Fdoc is None else int(feat.Fdoc.shape[1])
+        self.hier = self.c_prev > 0
         if hidden % 4 != 0:
             raise NotImplementedError("hidden width must be a multiple of 4")
         self.n, self.H, self.C, self.Cp = n, hidden, n_classes, ops.pad4(n_classes)
@@ -191,7 +197,7 @@ class DistTextGCNTrainer:
         # rank takes the peer path or every rank takes the NCCL path -- a rank falling back alone would deadlock the
         # others in the device barrier.
         self.exchange, self.exchange_error, self.px = "nccl", None, None
-        n_small = H + H * n_classes + n_classes                              # packed grads of b1, W2, b2 (one exchange)
+        n_small = H + H * n_classes + n_classes + self.c_prev * H            # packed grads of b1, W2, b2 (+ the [I|F] tail of W1)
         self.n_small = n_small
         self.n_small_pad = (n_small + 3) // 4 * 4
         xshapes = {"W1": (npad, H), "small": (world, self.n_small_pad), "Pt": (npad, Cp), "Pe": (npad, Cp),
@@ -221,32 +227,43 @@ class DistTextGCNTrainer:
         # parameters: same init on every rank (same seed), W1 kept in the NEW row order
         gen = torch.Generator().manual_seed(seed)
         if init_weights is None:
-            a1, a2 = (6.0 / (n + H)) ** 0.5, (6.0 / (H + n_classes)) ** 0.5
-            W1 = (torch.rand(n, H, generator=gen) * 2 - 1) * a1
+            a1, a2 = (6.0 / (n + self.c_prev + H)) ** 0.5, (6.0 / (H + n_classes)) ** 0.5
+            W1 = (torch.rand(n + self.c_prev, H, generator=gen) * 2 - 1) * a1
             W2 = (torch.rand(H, n_classes, generator=gen) * 2 - 1) * a2
             b1, b2 = torch.zeros(H), torch.zeros(n_classes)
         else:
             W1, b1, W2, b2 = (init_weights[k].detach().cpu().float() for k in
                               ("layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias"))
         self.W1_full = xbuf("W1", (npad, H))                                # [N_pad, H]; rows of other ranks are gathered
-        self.W1_full.copy_(self.part.to_new(W1).to(dev))
         lo = rank * nl
-        self.W1_loc = self.W1_full[lo:lo + nl]                               # view: this rank's shard (authoritative)
+        if not self.hier:
+            self.W1_full.copy_(self.part.to_new(W1[:n]).to(dev))
+            self.W1_loc = self.W1_full[lo:lo + nl]                           # view: this rank's shard (authoritative)
+            self.W1_cat = None
+        else:
+            # own rows of W1 followed by the replicated tail; W1_full holds the operand X W1 (see _gather_w1)
+            self.W1_cat = torch.cat([self.part.to_new(W1[:n])[lo:lo + nl], W1[n:]]).to(dev).contiguous()
+            self.W1_loc = self.W1_cat
+            F_full = torch.zeros((n, self.c_prev), dtype=torch.float32)
+            F_full[feat.n_vocab:] = feat.Fdoc.detach().cpu()
+            self.F_loc = self.part.to_new(F_full)[lo:lo + nl].to(dev).contiguous()
+            self.XW_loc = self.W1_full[lo:lo + nl]
         self.b1, self.W2, self.b2 = b1.to(dev), W2.to(dev).contiguous(), b2.to(dev)
         self.small_slots = xbuf("small", (world, self.n_small_pad))          # slot r = rank r's partial sums
         self.small_local = self.small_slots[rank]                             # dense_bwd writes my slot in place
         self.small = torch.zeros(self.n_small_pad, **f32)                     # summed over ranks
         def views(buf):
-            return buf[:H], buf[H:H + H * n_classes].view(H, n_classes), buf[H + H * n_classes:n_small]
-        self.l_b1, self.l_W2, self.l_b2 = views(self.small_local)             # local partials (kernel outputs)
-        self.g_b1, self.g_W2, self.g_b2 = views(self.small)                   # global gradients (Adam inputs)
-        self.g_W1 = torch.zeros((nl, H), **f32)
+            o = H + H * n_classes + n_classes
+            return buf[:H], buf[H:H + H * n_classes].view(H, n_classes), buf[H + H * n_classes:o], buf[o:n_small].view(self.c_prev, H)
+        self.l_b1, self.l_W2, self.l_b2, self.l_tail = views(self.small_local)   # local partials (kernel outputs)
+        self.g_b1, self.g_W2, self.g_b2, self.g_tail = views(self.small)         # global gradients (Adam inputs)
+        self.g_W1 = torch.zeros((nl + self.c_prev, H), **f32)
         def state(t):
             return [torch.zeros_like(t), torch.zeros_like(t), torch.zeros_like(t) if amsgrad else None]
         self.st = [state(self.W1_loc), state(self.b1), state(self.W2), state(self.b2)]
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.adam_hyper = torch.zeros(2, dtype=torch.float32, device=dev)
-        self.fuse_adam, self.keep_w1_grad = bool(fuse_adam), bool(keep_w1_grad)
+        self.fuse_adam, self.keep_w1_grad = bool(fuse_adam) and not self.hier, bool(keep_w1_grad) or self.hier
         # activations
         self.H1d = torch.empty((nl, H), **f32)
         # pre-dropout hidden rows of the last eval forward, reused by the next train step (same W1/b1,
@@ -283,11 +300,21 @@ class DistTextGCNTrainer:
         used = g.train_mask.cpu() | g.val_mask.cpu()
         if bool((used & ((g.y.cpu() < 0) | (g.y.cpu() >= n_classes))).any()):
             raise RuntimeError(f"labels of masked rows must lie in [0, {n_classes})")
-        self.w1_stale = False         # every rank initialised the full W1 identically
+        # class-wide propagations restricted to what the masked loss reads (see TextGCNTrainer.restrict_rows)
+        self.restrict_rows = bool(restrict_rows)
+        self.plan_z2, self.shard_g2, self.plan_g2 = self.plan, self.shard, self.plan
+        if self.restrict_rows:
+            test_new = self.part.to_new(g.test_mask.cpu(), False) if getattr(g, "test_mask", None) is not None else torch.zeros_like(tm_new)
+            rows_loc = (tm_new | vm_new | test_new)[lo:lo + nl].to(dev)
+            self.plan_z2 = self.shard.plan_for_rows(rows_loc, self.plan)
+            self.shard_g2 = self.shard.select_columns(tm_new.to(dev))
+            self.plan_g2 = self.shard_g2.plan_nonempty()
+        self.w1_stale = self.hier     # x = I: every rank initialised the full W1 identically; [I|F]: X W1 is built by the first gather
         self._w1_mirrored = False
         self._pending_reads = set()
         self.fused_stores = bool(fused_stores and self.px is not None and
                                  all(self.px.multicast.get(k, 0) for k in ("W1", "Pt", "Pe", "dZ2", "dZ1")))
+        self._w1_mirror_ok = not self.hier
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._eager_epochs = 0
@@ -377,7 +404,12 @@ class DistTextGCNTrainer:
 
     def _gather_w1(self) -> None:
         if self.w1_stale:
-            self._exchange(self.W1_full, self.W1_loc, "W1", self._w1_mirrored)
+            if self.hier:      # own rows of X W1 = W1[own] + F[own] W1[N:], written into this rank's slice of the exchange buffer
+                self._before_write("W1")
+                self.ops.hier_forward(self.W1_cat, self.part.n_loc, 0, self.F_loc, out=self.XW_loc)
+                self._exchange(self.W1_full, self.XW_loc, "W1", False)
+            else:
+                self._exchange(self.W1_full, self.W1_loc, "W1", self._w1_mirrored)
             self.w1_stale = False
 
     def _forward(self, training: bool) -> None:
@@ -406,7 +438,7 @@ class DistTextGCNTrainer:
         ops.project(h, self.W2, K=self.H, out=P_loc, mirror=mir)     # layer 2's thin X W, stored to all ranks
         self._exchange(P_full, P_loc, pname, mir is not None)
         self._mark("allgather_P")
-        ops.spmm(self.shard, P_full, F=self.Cp, plan=self.plan, out=self.Z2, bias=self.b2)
+        ops.spmm(self.shard, P_full, F=self.Cp, plan=self.plan_z2, out=self.Z2, bias=self.b2)
         self._note_read(pname)
         self._mark("spmm_narrow_fwd")
 
@@ -420,7 +452,7 @@ class DistTextGCNTrainer:
         self._mark("masked_nll")
         self._exchange(self.dZ2_full, self.dZ2_loc, "dZ2", mir is not None)
         self._mark("allgather_dZ2")
-        ops.spmm(self.shard, self.dZ2_full, F=self.Cp, plan=self.plan, out=self.G2)
+        ops.spmm(self.shard_g2, self.dZ2_full, F=self.Cp, plan=self.plan_g2, out=self.G2)
         self._note_read("dZ2")
         self._mark("spmm_narrow_bwd")
         drop = self.p > 0
@@ -434,10 +466,14 @@ class DistTextGCNTrainer:
                           dZ1_mirror=mir)
         self._db_ws = r["workspace"]
         self._mark("dense_bwd")
-        self._all_reduce_small()          # its barrier also publishes the mirrored dZ1 stores
-        self._mark("allreduce_small_grads")
-        if not (mir is not None and self.px is not None):
+        if not self.hier:
+            self._all_reduce_small()          # its barrier also publishes the mirrored dZ1 stores
+            self._mark("allreduce_small_grads")
+        dz1_mirrored = mir is not None and self.px is not None
+        if not dz1_mirrored:
             self._exchange(self.dZ1_full, self.dZ1_loc, "dZ1", False)
+        elif self.hier:
+            self._barrier()                   # publishes the mirrored dZ1 stores (the small all-reduce comes later here)
         self._mark("allgather_dZ1")
         kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad,
                   step_dev=self.step_dev)
@@ -454,6 +490,20 @@ class DistTextGCNTrainer:
                                hyper=self.adam_hyper, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, mirror=mir))
             self._note_read("dZ1")
             self._mark("spmm_wide_bwd")
+        elif self.hier:
+            # [I | F]: dW1[own rows] = A_hat dZ1 on the shard; dW1[N:] = F^T (A_hat dZ1)[docs], summed over the ranks together
+            # with the other small gradients; Adam on (own rows ; replicated tail) in one launch, identical tail on all ranks
+            nl_ = self.part.n_loc
+            ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1[:nl_])
+            self._note_read("dZ1")
+            self._mark("spmm_wide_bwd")
+            ops.hier_backward(self.g_W1[:nl_], nl_, 0, self.F_loc, self.H, self.l_tail)
+            self._all_reduce_small()
+            self._mark("allreduce_small_grads")
+            self.g_W1[nl_:].copy_(self.g_tail)
+            ops.increment_step(self.step_dev)
+            ops.adam_step(self.W1_cat, self.g_W1, *self.st[0], **kw)
+            mir = None
         else:
             ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1)
             self._note_read("dZ1")
@@ -531,9 +581,18 @@ class DistTextGCNTrainer:
 
     def gathered_parameters(self) -> Dict[str, torch.Tensor]:
         """Parameters in the ORIGINAL node order (reference layout: layers.{i}.weight (in,out), bias)."""
-        self._gather_w1()
-        return {"layers.0.weight": self.part.to_old(self.W1_full), "layers.0.bias": self.b1,
-                "layers.1.weight": self.W2, "layers.1.bias": self.b2}
+        if self.hier:
+            nl_ = self.part.n_loc
+            full = torch.zeros((self.part.n_pad, self.H), dtype=torch.float32, device=self.dev)
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(full, self.W1_cat[:nl_].contiguous())
+            else:
+                full[:nl_].copy_(self.W1_cat[:nl_])
+            W1 = torch.cat([self.part.to_old(full), self.W1_cat[nl_:]])
+        else:
+            self._gather_w1()
+            W1 = self.part.to_old(self.W1_full)
+        return {"layers.0.weight": W1, "layers.0.bias": self.b1, "layers.1.weight": self.W2, "layers.1.bias": self.b2}
 
     def logits_old_order(self) -> torch.Tensor:
         """All-gathered logits of the last forward, original node order (host-facing helper)."""
@@ -655,16 +714,21 @@ def parity_against_single_gpu(g, shape, rank: int, world: int, dev: torch.device
 # --------------------------------------------------------------------------------------
 # bench entry for N > 1 (called by bench.py under torchrun)
 # --------------------------------------------------------------------------------------
-def _timed_dist_workload(g, shape, args, rank, local_rank, world, dev, K, W, sample_clocks: bool):
-    """Warm-up, K device-timed epochs (max over ranks), then the same epochs end to end with host buffers."""
+def _timed_dist_workload(levels, args, rank, local_rank, world, dev, K, W, sample_clocks: bool):
+    """Warm-up, K device-timed steps (max over ranks), then the same steps end to end with host buffers.
+    levels = [(graph, shape), ...]: one row-partitioned trainer each; a step = one epoch of every level in turn."""
     import torch.distributed as dist
     from . import _native
     lib = _native.load()
-    tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad,
-                            rank, world, dev, seed=args.seed, use_cuda_graph=not getattr(args, "no_cuda_graph", False),
-                            exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False),
-                            fuse_adam=not getattr(args, "no_fuse_adam", False), keep_w1_grad=False)
-    epoch = tr.epoch
+    trs = [DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad,
+                              rank, world, dev, seed=args.seed, use_cuda_graph=not getattr(args, "no_cuda_graph", False),
+                              exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False),
+                              fuse_adam=not getattr(args, "no_fuse_adam", False), keep_w1_grad=False) for g, shape in levels]
+    tr = trs[-1]
+
+    def epoch():
+        for t in trs:
+            t.epoch()
     for _ in range(W):
         epoch()
     torch.cuda.synchronize()
@@ -696,22 +760,25 @@ def _timed_dist_workload(g, shape, args, rank, local_rank, world, dev, K, W, sam
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = int(lib.tgcn_launch_count() - l0)
-    if tr._graph is not None:
-        launches = tr.launches_per_epoch * rounds * K
+    if all(t._graph is not None for t in trs):
+        launches = sum(t.launches_per_epoch for t in trs) * rounds * K
     ms_per_step = float(ms.item()) / (rounds * K)
 
     # e2e: labels/masks from pinned host memory each epoch, losses + local argmax read back
     nl = tr.part.n_loc
-    y_pin, tm_pin, vm_pin = tr.y.cpu().pin_memory(), tr.train_mask.cpu().pin_memory(), tr.val_mask.cpu().pin_memory()
-    pred_pin = torch.empty(nl, dtype=torch.int32).pin_memory()
+    pins = [(t, t.y.cpu().pin_memory(), t.train_mask.cpu().pin_memory(), t.val_mask.cpu().pin_memory(),
+             torch.empty(t.part.n_loc, dtype=torch.int32).pin_memory()) for t in trs]
 
     def epoch_e2e():
-        tr.y.copy_(y_pin, non_blocking=True)
-        tr.train_mask.copy_(tm_pin, non_blocking=True)
-        tr.val_mask.copy_(vm_pin, non_blocking=True)
-        tr.epoch()
-        pred_pin.copy_(tr.pred, non_blocking=True)
-        return tr.epoch_stats()                      # all-reduce + D2H of the global val loss / accuracy
+        out = None
+        for t, y_pin, tm_pin, vm_pin, pred_pin in pins:
+            t.y.copy_(y_pin, non_blocking=True)
+            t.train_mask.copy_(tm_pin, non_blocking=True)
+            t.val_mask.copy_(vm_pin, non_blocking=True)
+            t.epoch()
+            pred_pin.copy_(t.pred, non_blocking=True)
+            out = t.epoch_stats()                    # all-reduce + D2H of the global val loss / accuracy
+        return out
     for _ in range(2):
         epoch_e2e()
     torch.cuda.synchronize()
@@ -728,12 +795,15 @@ def _timed_dist_workload(g, shape, args, rank, local_rank, world, dev, K, W, sam
     nnz_all = [torch.zeros_like(nnz_loc) for _ in range(world)]
     dist.all_gather(nnz_all, nnz_loc)
     rec = dict(ms_per_step=ms_per_step, e2e_ms=float(e2e.item()), launches=launches, timed_steps=rounds * K, clocks=clocks,
-               nl=nl, nnz_per_rank=[int(t.item()) for t in nnz_all], bytes_per_train_step=tr.bytes_per_train_step(),
-               last=last, cuda_graph=tr._graph is not None, graph_error=tr.graph_error, exchange=tr.exchange,
+               nl=nl, nnz_per_rank=[int(t.item()) for t in nnz_all], bytes_per_train_step=sum(t.bytes_per_train_step() for t in trs),
+               last=last, cuda_graph=all(t._graph is not None for t in trs), graph_error=tr.graph_error, exchange=tr.exchange,
                exchange_error=tr.exchange_error, fused_stores=tr.fused_stores, share_h1=tr.share_h1,
-               multicast=bool(tr.px is not None and any(tr.px.multicast.values())), launches_per_epoch=tr.launches_per_epoch)
-    tr._graph = None
-    del tr
+               restrict_rows=tr.restrict_rows,
+               multicast=bool(tr.px is not None and any(tr.px.multicast.values())),
+               launches_per_epoch=sum(t.launches_per_epoch for t in trs))
+    for t in trs:
+        t._graph = None
+    del tr, trs, pins
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.empty_cache()
@@ -745,21 +815,23 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
     from .synthetic import SHAPES, make_graph
     from bench import METRIC, UNIT, resolve_workload, workload_config
     specs = resolve_workload(args.workload)
-    if len(specs) != 1 or specs[0][2] is not None:
-        raise NotImplementedError("the row-partitioned bench covers the flat workloads (x = I)")
-    label, shape, _ = specs[0]
+    label, shape, hier0 = specs[0]
     K, W = args.steps, max(args.warmup, 5)
-    g = make_graph(shape, seed=args.seed)          # same graph on every rank (same seed)
-    main = _timed_dist_workload(g, shape, args, rank, local_rank, world, dev, K, W, sample_clocks=True)
+    levels = [(make_graph(sh, seed=args.seed, hierarchy_classes=hier), sh) for _, sh, hier in specs]   # same graphs on every rank
+    g = levels[0][0]
+    main = _timed_dist_workload(levels, args, rank, local_rank, world, dev, K, W, sample_clocks=True)
     extra = {"nnz_per_rank": main["nnz_per_rank"], "rows_per_rank": main["nl"],
              "collective_bytes_received_per_rank_per_train_step": main["bytes_per_train_step"],
              "last_epoch": main["last"], "cuda_graph": main["cuda_graph"], "cuda_graph_error": main["graph_error"],
              "exchange": main["exchange"], "exchange_error": main["exchange_error"], "fused_stores": main["fused_stores"],
-             "multicast": main["multicast"], "share_h1": main["share_h1"], "timed_steps": main["timed_steps"],
+             "multicast": main["multicast"], "share_h1": main["share_h1"], "restrict_rows": main["restrict_rows"],
+             "timed_steps": main["timed_steps"],
              "kernels_per_epoch": main["launches_per_epoch"]}
     if not getattr(args, "no_extras", False):
         # (1) the shipped N-rank configuration (CUDA graph + multimem stores + dropout) against the single-GPU trainer
         try:
+            if hier0 is not None:
+                raise NotImplementedError("parity helper covers x = I")
             extra["parity"] = parity_against_single_gpu(
                 g, shape, rank, world, dev, args.seed, epochs=5, use_cuda_graph=not getattr(args, "no_cuda_graph", False),
                 exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False),
@@ -769,10 +841,10 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
         # (2) the >= 1 M-node configuration north_star names for scaling, at this N
         if args.workload != "scale":
             try:
-                del g
+                del g, levels
                 sc = SHAPES["scale"]
                 gs = make_graph(sc, seed=args.seed)
-                r = _timed_dist_workload(gs, sc, args, rank, local_rank, world, dev, 10, 5, sample_clocks=False)
+                r = _timed_dist_workload([(gs, sc)], args, rank, local_rank, world, dev, 10, 5, sample_clocks=False)
                 extra["scale_config"] = {"epochs_per_s": 1e3 / r["ms_per_step"], "ms_per_step": r["ms_per_step"], "steps": 10,
                                          "n_nodes": int(gs.x.shape[0]), "n_edges": int(gs.edge_index.shape[1]),
                                          "hidden": sc.hidden, "nnz_per_rank": r["nnz_per_rank"],
@@ -782,7 +854,8 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
             except Exception as e:
                 extra["scale_config"] = {"error": repr(e)}
     if rank == 0:
-        g_cfg = make_graph(shape, seed=args.seed) if args.workload != "scale" and not getattr(args, "no_extras", False) else g
+        sh_last, hier_last = specs[-1][1], specs[-1][2]
+        g_cfg = make_graph(sh_last, seed=args.seed, hierarchy_classes=hier_last)
         cfg = workload_config(args.workload, specs, g_cfg)
         cfg["parallelism"] = (f"1D row partition x{world} (snake order by nnz); exchange between layers: " +
                               (("multimem stores fused into the producer kernels + device barrier" if main["fused_stores"] else
