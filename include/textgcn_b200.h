@@ -201,10 +201,16 @@ typedef struct {
 int tgcn_dense_bwd(const tgcn_dense_bwd_args* args, void* workspace, size_t workspace_bytes, void* stream);
 int tgcn_dense_bwd_workspace_bytes(int32_t H, int32_t C, size_t* bytes_out);
 
-/* Thin projection P = X W (X [n,K] fp32/bf16, W [K,M]); replaces torch.matmul(x, weight) of a
- * hidden->classes layer when it is not fused into the producing SpMM. */
+/* Thin projection P = X W (+ bias) (X [n,K] fp32/bf16, W [K,M], bias [M] or NULL); replaces torch.matmul(x, weight) of a
+ * hidden->classes layer when it is not fused into the producing SpMM.  With bias it is layer 2 in the
+ * propagate-first order (A_hat H) W2 + b2, used when there are more classes than hidden units (perlevel_dbpedia.py:
+ * 219 classes, hidden 32): the propagation then moves hidden-wide instead of classes-wide rows. */
 int tgcn_project(const void* X, int64_t ldx, int32_t x_dtype, int64_t n_rows, int32_t K,
-                 const float* W, int32_t M, float* P, int64_t ldp, void* P_mirror_mc, void* stream);
+                 const float* W, int32_t M, const float* bias, float* P, int64_t ldp, void* P_mirror_mc, void* stream);
+/* out[c] = sum_r X[r, c] (deterministic two-stage sum): the bias gradient db1 = colsum(dZ1) in the propagate-first order */
+int tgcn_colsum(const float* X, int64_t ldx, int64_t n_rows, int32_t F, float* out, void* workspace, size_t workspace_bytes,
+                void* stream);
+int tgcn_colsum_workspace_bytes(int32_t F, size_t* bytes_out);
 
 /* Y = dropout(X) with exactly the keep decision of the tgcn_spmm epilogue (same mode / seed / offset / element index
  * (row + philox_row_offset) * F + col).  Used to reuse the pre-dropout hidden activation A_hat (X W1) + b1 of an eval

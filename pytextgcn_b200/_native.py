@@ -89,8 +89,10 @@ SIGNATURES = {
     "tgcn_masked_nll_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "tgcn_dense_bwd": (C.c_int, [C.POINTER(DenseBwdArgs), c_void, C.c_size_t, c_void]),
     "tgcn_dense_bwd_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
-    "tgcn_project": (C.c_int, [c_void, C.c_int64, C.c_int32, C.c_int64, C.c_int32, c_void, C.c_int32,
+    "tgcn_project": (C.c_int, [c_void, C.c_int64, C.c_int32, C.c_int64, C.c_int32, c_void, C.c_int32, c_void,
                                c_void, C.c_int64, c_void, c_void]),
+    "tgcn_colsum": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int32, c_void, c_void, C.c_size_t, c_void]),
+    "tgcn_colsum_workspace_bytes": (C.c_int, [C.c_int32, C.POINTER(C.c_size_t)]),
     "tgcn_dropout_apply": (C.c_int, [c_void, C.c_int64, c_void, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float,
                                      c_void, C.c_int64, C.c_uint64, C.c_uint64, c_void, C.c_int64, c_void]),
     "tgcn_hier_forward": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int64, c_void, C.c_int64, C.c_int32,

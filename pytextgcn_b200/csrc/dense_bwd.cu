@@ -332,8 +332,8 @@ __global__ void __launch_bounds__(256) k_reduce_partials3(const float* __restric
 // memory so one 16-byte broadcast read feeds 4 FMAs per weight read); W staged in shared memory when it fits
 constexpr int PJ_ROWS = 4;
 __global__ void __launch_bounds__(256) k_project(const void* __restrict__ X, int64_t ldx, int x_dtype, int64_t n_rows, int K,
-                                                 const float* __restrict__ W, int M, float* __restrict__ P, int64_t ldp,
-                                                 int w_in_smem, float* __restrict__ mirror) {
+                                                 const float* __restrict__ W, int M, const float* __restrict__ bias,
+                                                 float* __restrict__ P, int64_t ldp, int w_in_smem, float* __restrict__ mirror) {
   extern __shared__ __align__(16) float smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* Ws = smem;
@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(256) k_project(const void* __restrict__ X, int
         const float4 x = *reinterpret_cast<const float4*>(rowbuf + k * PJ_ROWS);
         s0 = fmaf(x.x, w, s0); s1 = fmaf(x.y, w, s1); s2 = fmaf(x.z, w, s2); s3 = fmaf(x.w, w, s3);
       }
+      if (bias) { const float b = __ldg(bias + m); s0 += b; s1 += b; s2 += b; s3 += b; }
       if (row0 + 0 < n_rows) { P[(row0 + 0) * ldp + m] = s0; if (mirror) multimem_st_f32(mirror + (row0 + 0) * ldp + m, s0); }
       if (row0 + 1 < n_rows) { P[(row0 + 1) * ldp + m] = s1; if (mirror) multimem_st_f32(mirror + (row0 + 1) * ldp + m, s1); }
       if (row0 + 2 < n_rows) { P[(row0 + 2) * ldp + m] = s2; if (mirror) multimem_st_f32(mirror + (row0 + 2) * ldp + m, s2); }
@@ -368,6 +369,19 @@ __global__ void __launch_bounds__(256) k_project(const void* __restrict__ X, int
     __syncwarp();
   }
   if (mirror) __threadfence_system();
+}
+
+// column sums of X[n_rows, F]: per-CTA partial rows (a CTA walks a contiguous row range, thread = column), reduced in
+// CTA order by k_reduce_partials3 -- same order every run
+__global__ void __launch_bounds__(256) k_colsum_partial(const float* __restrict__ X, int64_t ldx, int64_t n_rows, int F,
+                                                        float* __restrict__ part) {
+  const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(n_rows, r0 + per);
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float s = 0.0f;
+    for (int64_t r = r0; r < r1; ++r) s += X[r * ldx + c];
+    part[(int64_t)blockIdx.x * F + c] = s;
+  }
 }
 
 struct DbLayout { size_t off_dw, off_dbh, off_dbo, total; int n_cta; };
@@ -464,8 +478,31 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
   return TGCN_OK;
 }
 
+extern "C" int tgcn_colsum_workspace_bytes(int32_t F, size_t* bytes_out) {
+  TGCN_CHECK_ARG(bytes_out && F > 0, "colsum_workspace_bytes: bad arguments");
+  *bytes_out = (size_t)sm_count() * 4 * F * sizeof(float);
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_colsum(const float* X, int64_t ldx, int64_t n_rows, int32_t F, float* out, void* workspace,
+                           size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TGCN_CHECK_ARG(X && out && n_rows > 0 && F > 0 && ldx >= F, "colsum: bad arguments");
+  const int grid = (int)std::min<int64_t>((int64_t)sm_count() * 4, cdiv(n_rows, 64));
+  if (!workspace || workspace_bytes < (size_t)grid * F * sizeof(float)) {
+    set_error("colsum workspace too small");
+    return TGCN_EWORKSPACE;
+  }
+  k_colsum_partial<<<grid, 256, 0, stream>>>(X, ldx, n_rows, F, (float*)workspace);
+  TGCN_LAUNCH_CHECK();
+  k_reduce_partials3<<<(unsigned)cdiv((int64_t)F * 32, 256), 256, 0, stream>>>((const float*)workspace, F, out, nullptr, 0, nullptr,
+                                                                              nullptr, 0, nullptr, grid);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
 extern "C" int tgcn_project(const void* X, int64_t ldx, int32_t x_dtype, int64_t n_rows, int32_t K,
-                            const float* W, int32_t M, float* P, int64_t ldp, void* P_mirror_mc, void* stream_) {
+                            const float* W, int32_t M, const float* bias, float* P, int64_t ldp, void* P_mirror_mc, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   TGCN_CHECK_ARG(X && W && P, "project: null pointer");
   TGCN_CHECK_ARG(n_rows > 0 && K > 0 && M > 0 && ldx >= K && ldp >= M, "project: bad shape");
@@ -474,7 +511,7 @@ extern "C" int tgcn_project(const void* X, int64_t ldx, int32_t x_dtype, int64_t
   size_t smem = ((w_in_smem ? ((K * M + 3) & ~3) : 0) + (size_t)wpb * K * PJ_ROWS) * sizeof(float);
   if (smem > 48 * 1024) TGCN_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(cdiv(cdiv(n_rows, PJ_ROWS), wpb), (int64_t)sm_count() * 8);
-  k_project<<<grid, threads, smem, stream>>>(X, ldx, x_dtype, n_rows, K, W, M, P, ldp, w_in_smem, (float*)P_mirror_mc);
+  k_project<<<grid, threads, smem, stream>>>(X, ldx, x_dtype, n_rows, K, W, M, bias, P, ldp, w_in_smem, (float*)P_mirror_mc);
   TGCN_LAUNCH_CHECK();
   return TGCN_OK;
 }

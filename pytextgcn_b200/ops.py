@@ -245,9 +245,9 @@ def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Option
 
 
 def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Optional[torch.Tensor] = None,
-            mirror: Optional[int] = None) -> torch.Tensor:
-    """P = X[:, :K] @ W (thin hidden->classes projection), P padded to a multiple of 4 columns."""
-    _need_cuda(X, W, out)
+            mirror: Optional[int] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """P = X[:, :K] @ W (+ bias) (thin projection), P padded to a multiple of 4 columns."""
+    _need_cuda(X, W, out, bias)
     lib = _native.load()
     K = int(W.shape[0]) if K is None else K
     M = int(W.shape[1])
@@ -257,8 +257,28 @@ def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Opti
     if out is None:
         out = torch.zeros((n, pad4(M)), dtype=torch.float32, device=X.device)
     with torch.cuda.device(X.device):
-        _native.check(lib.tgcn_project(X.data_ptr(), X.stride(0), _dt(X), n, K, W.data_ptr(), M,
+        _native.check(lib.tgcn_project(X.data_ptr(), X.stride(0), _dt(X), n, K, W.data_ptr(), M, _native.ptr(bias),
                                        out.data_ptr(), out.stride(0), mirror, _stream()))
+    return out
+
+
+def colsum(X: torch.Tensor, F: Optional[int] = None, out: Optional[torch.Tensor] = None,
+           workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[c] = sum over rows of X[:, c] (deterministic).  See tgcn_colsum."""
+    _need_cuda(X, out, workspace)
+    lib = _native.load()
+    F = int(X.shape[1]) if F is None else int(F)
+    if X.dtype != torch.float32 or X.stride(1) != 1:
+        raise RuntimeError("colsum: X must be a row-major fp32 matrix")
+    if out is None:
+        out = torch.empty(F, dtype=torch.float32, device=X.device)
+    need = C.c_size_t(0)
+    with torch.cuda.device(X.device):
+        _native.check(lib.tgcn_colsum_workspace_bytes(F, C.byref(need)))
+        if workspace is None or workspace.numel() < need.value:
+            workspace = torch.empty(need.value, dtype=torch.uint8, device=X.device)
+        _native.check(lib.tgcn_colsum(X.data_ptr(), X.stride(0), int(X.shape[0]), F, out.data_ptr(), workspace.data_ptr(),
+                                      workspace.numel(), _stream()))
     return out
 
 

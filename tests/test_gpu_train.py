@@ -336,3 +336,67 @@ def test_restricted_class_wide_propagations_change_nothing_that_is_read(cuda, gr
     for a, b in zip(res[True][2], res[False][2]):
         assert rel_err(a, b) < 1e-4
     assert rel_err(res[True][3], res[False][3]) < 1e-5 and (res[True][4] != res[False][4]).float().mean().item() < 0.01
+
+
+def test_colsum_and_biased_projection(cuda):
+    from pytextgcn_b200 import ops
+    torch.manual_seed(0)
+    X = torch.randn(5003, 36, device=cuda)
+    assert rel_err(ops.colsum(X[:, :32], F=32), X[:, :32].double().sum(0)) < 1e-6
+    W, b = torch.randn(32, 219, device=cuda), torch.randn(219, device=cuda)
+    P = ops.project(X, W, K=32, bias=b)
+    assert rel_err(P[:, :219], X[:, :32].double() @ W.double() + b.double()) < 1e-6 and bool((P[:, 219:] == 0).all())
+
+
+@pytest.mark.parametrize("restrict", [False, True])
+def test_propagate_first_layer2_matches_the_reference_order(cuda, restrict):
+    """More classes than hidden units: Z2 = (A_hat H1d) W2 + b2 (and its backward) against the oracle, which keeps the
+    reference's order A_hat (H1d W2) + b2 -- same linear maps, so logits / loss / gradients agree to fp32 rounding."""
+    from pytextgcn_b200 import GCN
+    from pytextgcn_b200.synthetic import make_graph, GraphShape
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    shape = GraphShape("t", 500, 700, 7000, 12, 70, 32)
+    g = make_graph(shape, seed=4, hierarchy_classes=9)
+    in_ch = int(g.x.shape[1])
+    torch.manual_seed(0)
+    ref = O.OracleGCN(in_ch, 70, n_hidden_gcn=32, dropout=0.0)
+    with torch.no_grad():
+        for l in ref.layers:
+            l.bias.uniform_(-0.2, 0.2)
+    mod = GCN(in_ch, 70, n_hidden_gcn=32, dropout=0.0)
+    with torch.no_grad():
+        for pd, ps in zip(mod.parameters(), ref.parameters()):
+            pd.copy_(ps)
+    mod = mod.to(cuda)
+    tr = TextGCNTrainer(mod, g.clone().to(cuda), lr=0.01, amsgrad=False, restrict_rows=restrict)
+    assert tr.propagate_first
+    opt = torch.optim.Adam(ref.parameters(), lr=0.01)
+    for step in range(4):
+        out_ref = O.reference_epoch(ref, g, opt)
+        out = tr.epoch()
+        if step == 0:
+            for name, gbuf, pr in zip(("W1", "b1", "W2", "b2"), tr.grads, ref.parameters()):
+                assert rel_err(gbuf, pr.grad) < TOL, name
+        assert abs(out["loss"] - out_ref[0]) < 1e-5 * max(1, abs(out_ref[0])) * (step + 1)
+        assert abs(out["val_loss"] - out_ref[1]) < 1e-4 * max(1, abs(out_ref[1])) * (step + 1)
+    ref.eval()
+    with torch.no_grad():
+        z_ref = ref(g)
+    z = tr.eval_step(full=True)["logits"]
+    assert rel_err(z, z_ref) < 1e-4          # after 4 Adam steps on both sides
+
+
+def test_propagate_first_dropout_mask_is_the_forward_mask(cuda):
+    from pytextgcn_b200.trainer import TextGCNTrainer
+    from pytextgcn_b200 import GCN
+    from pytextgcn_b200.synthetic import make_graph, GraphShape
+    shape = GraphShape("t", 300, 400, 4000, 12, 70, 32)
+    g = make_graph(shape, seed=5).to(cuda)
+    torch.manual_seed(1)
+    mod = GCN(int(g.x.shape[1]), 70, n_hidden_gcn=32, dropout=0.5).to(cuda)
+    tr = TextGCNTrainer(mod, g, lr=0.0, amsgrad=False, seed=3, restrict_rows=False)
+    assert tr.propagate_first
+    for _ in range(3):
+        tr.train_step()
+        dropped = tr.H1d == 0
+        assert torch.all(tr.dZ1[dropped] == 0) and abs((~dropped).float().mean().item() - 0.5) < 0.02
