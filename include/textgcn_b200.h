@@ -207,6 +207,20 @@ int tgcn_dense_bwd_workspace_bytes(int32_t H, int32_t C, size_t* bytes_out);
  * 219 classes, hidden 32): the propagation then moves hidden-wide instead of classes-wide rows. */
 int tgcn_project(const void* X, int64_t ldx, int32_t x_dtype, int64_t n_rows, int32_t K,
                  const float* W, int32_t M, const float* bias, float* P, int64_t ldp, void* P_mirror_mc, void* stream);
+/* The same projection with the training forward's dropout applied to X while it is loaded (the keep decision of the
+ * tgcn_spmm epilogue: keep-mask bytes, or Philox keyed by (seed, offset, (row + philox_row_offset) * K + col)) and the
+ * dropped block optionally written to Xd for the backward pass: P = dropout(X) W (+ bias), Xd = dropout(X).  One pass
+ * instead of tgcn_dropout_apply + tgcn_project when the pre-dropout activation is shared with an eval forward.
+ * fp32 X takes the row-per-lane kernel (csrc/dense_bwd.cu k_project_rows); bf16 X the 4-row kernel (no dropout). */
+typedef struct {
+  const void* X; int64_t ldx; int32_t x_dtype; int64_t n_rows; int32_t K;
+  const float* W; int32_t M; const float* bias;
+  float* P; int64_t ldp; void* P_mirror_mc;
+  int32_t drop_mode; float drop_p; const uint8_t* keep_mask; int64_t ldmask;
+  uint64_t philox_seed; uint64_t philox_offset; const int64_t* philox_offset_dev; int64_t philox_row_offset;
+  float* Xd; int64_t ldxd;
+} tgcn_project_args;
+int tgcn_project_ex(const tgcn_project_args* args, void* stream);
 /* out[c] = sum_r X[r, c] (deterministic two-stage sum): the bias gradient db1 = colsum(dZ1) in the propagate-first order */
 int tgcn_colsum(const float* X, int64_t ldx, int64_t n_rows, int32_t F, float* out, void* workspace, size_t workspace_bytes,
                 void* stream);

@@ -49,6 +49,18 @@ class TcPlanArgs(C.Structure):
     ]
 
 
+class ProjectArgs(C.Structure):
+    """Mirror of tgcn_project_args."""
+    _fields_ = [
+        ("X", c_void), ("ldx", C.c_int64), ("x_dtype", C.c_int32), ("n_rows", C.c_int64), ("K", C.c_int32),
+        ("W", c_void), ("M", C.c_int32), ("bias", c_void),
+        ("P", c_void), ("ldp", C.c_int64), ("P_mirror_mc", c_void),
+        ("drop_mode", C.c_int32), ("drop_p", C.c_float), ("keep_mask", c_void), ("ldmask", C.c_int64),
+        ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_offset_dev", c_void), ("philox_row_offset", C.c_int64),
+        ("Xd", c_void), ("ldxd", C.c_int64),
+    ]
+
+
 class DenseBwdArgs(C.Structure):
     """Mirror of tgcn_dense_bwd_args."""
     _fields_ = [
@@ -91,6 +103,7 @@ SIGNATURES = {
     "tgcn_dense_bwd_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "tgcn_project": (C.c_int, [c_void, C.c_int64, C.c_int32, C.c_int64, C.c_int32, c_void, C.c_int32, c_void,
                                c_void, C.c_int64, c_void, c_void]),
+    "tgcn_project_ex": (C.c_int, [C.POINTER(ProjectArgs), c_void]),
     "tgcn_colsum": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int32, c_void, c_void, C.c_size_t, c_void]),
     "tgcn_colsum_workspace_bytes": (C.c_int, [C.c_int32, C.POINTER(C.c_size_t)]),
     "tgcn_dropout_apply": (C.c_int, [c_void, C.c_int64, c_void, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float,

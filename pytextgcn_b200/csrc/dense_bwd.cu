@@ -384,6 +384,115 @@ __global__ void __launch_bounds__(256) k_colsum_partial(const float* __restrict_
   }
 }
 
+// Thin projection, lane = row:  P[r, c0 .. c0 + 4*N4) = dropout(X[r, :K]) W[:, c0 ..] (+ bias).
+// A warp owns 32 consecutive rows.  The X block of the warp goes through shared memory TRANSPOSED in chunks of 32
+// columns ([k][33]: every lane then reads its own row's value without bank conflicts), W sits in shared memory and is
+// read as 16-byte BROADCASTS (all lanes the same address): per k one 4-byte load + N4 broadcasts feed 4*N4 FMAs per lane
+// -- ~0.8 instructions per row and k at 20 classes, against 2 shared-memory loads per 4 FMAs in the row-blocked kernel
+// above (which stays for bf16 operands).  The dropout of the training forward (keep-mask bytes or Philox, the decision of
+// the SpMM epilogue) is applied while the block is loaded and the dropped block is written out (Xd) for the backward pass,
+// so a pre-dropout activation shared with the preceding eval forward needs no separate dropout pass.
+struct ProjParams {
+  const float* __restrict__ X; int64_t ldx; int64_t n_rows; int32_t K;
+  const float* __restrict__ W; int32_t M; const float* __restrict__ bias;
+  float* P; int64_t ldp; float* mirror;
+  int32_t drop_mode; float drop_p, drop_scale; const uint8_t* __restrict__ keep_mask; int64_t ldmask;
+  uint64_t philox_seed, philox_offset; const int64_t* __restrict__ philox_offset_dev; int64_t philox_row_offset; int32_t philox_F;
+  float* Xd; int64_t ldxd;
+};
+constexpr int PR_KC = 32;     // columns of X per shared-memory chunk
+template <int N4>
+__global__ void __launch_bounds__(256) k_project_rows(const ProjParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.y * (4 * N4);                 // first output column of this CTA's column tile
+  const int Kp = (p.K + PR_KC - 1) / PR_KC * PR_KC;
+  float* Ws = smem;                                      // [Kp][4*N4], zero past K / past M
+  float* Xs = smem + Kp * (4 * N4) + wid * (PR_KC * 33); // [32 k][33]
+  for (int i = threadIdx.x; i < Kp * (4 * N4); i += blockDim.x) {
+    const int k = i / (4 * N4), c = i - k * (4 * N4);
+    Ws[i] = (k < p.K && c0 + c < p.M) ? p.W[(int64_t)k * p.M + c0 + c] : 0.0f;
+  }
+  __syncthreads();
+  const uint64_t ph_off = p.philox_offset + (p.philox_offset_dev ? (uint64_t)__ldg(p.philox_offset_dev) : 0ull);
+  const int64_t n_blocks = (p.n_rows + 31) / 32;
+  for (int64_t blk = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid; blk < n_blocks; blk += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t row0 = blk * 32;
+    float acc[4 * N4];
+#pragma unroll
+    for (int i = 0; i < 4 * N4; ++i) acc[i] = 0.0f;
+    for (int k0 = 0; k0 < p.K; k0 += PR_KC) {
+      // ---- load 32 rows x 32 columns (8 float4 per lane), dropout, transpose into shared memory ----
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int t = i * 32 + lane, r = t >> 3, kq = t & 7;
+        const int64_t row = row0 + r;
+        const int k = k0 + 4 * kq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < p.n_rows && k < p.K) {
+          v = __ldg(reinterpret_cast<const float4*>(p.X + row * p.ldx + k));
+          if (p.drop_mode == TGCN_DROP_MASK) {
+            const uint8_t* m = p.keep_mask + row * p.ldmask + k;
+            v.x = m[0] ? v.x * p.drop_scale : 0.0f; v.y = m[1] ? v.y * p.drop_scale : 0.0f;
+            v.z = m[2] ? v.z * p.drop_scale : 0.0f; v.w = m[3] ? v.w * p.drop_scale : 0.0f;
+          } else if (p.drop_mode == TGCN_DROP_PHILOX) {
+            const uint64_t e4 = ((uint64_t)(row + p.philox_row_offset) * (uint64_t)p.philox_F + (uint64_t)k) >> 2;
+            const uint4 rr = philox_quad(e4, p.philox_seed, ph_off);
+            v.x = (u01(rr.x) >= p.drop_p) ? v.x * p.drop_scale : 0.0f; v.y = (u01(rr.y) >= p.drop_p) ? v.y * p.drop_scale : 0.0f;
+            v.z = (u01(rr.z) >= p.drop_p) ? v.z * p.drop_scale : 0.0f; v.w = (u01(rr.w) >= p.drop_p) ? v.w * p.drop_scale : 0.0f;
+          }
+          if (p.Xd && blockIdx.y == 0) *reinterpret_cast<float4*>(p.Xd + row * p.ldxd + k) = v;
+        }
+        float* d = Xs + (4 * kq) * 33 + r;
+        d[0] = v.x; d[33] = v.y; d[66] = v.z; d[99] = v.w;
+      }
+      __syncwarp();
+      const float* wk = Ws + k0 * (4 * N4);
+#pragma unroll 4
+      for (int k = 0; k < PR_KC; ++k) {
+        const float x = Xs[k * 33 + lane];
+#pragma unroll
+        for (int c4 = 0; c4 < N4; ++c4) {
+          const float4 w = *reinterpret_cast<const float4*>(wk + k * (4 * N4) + 4 * c4);
+          acc[4 * c4] = fmaf(x, w.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(x, w.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(x, w.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(x, w.w, acc[4 * c4 + 3]);
+        }
+      }
+      __syncwarp();
+    }
+    const int64_t row = row0 + lane;
+    if (row < p.n_rows) {
+#pragma unroll
+      for (int c4 = 0; c4 < N4; ++c4) {
+        const int c = c0 + 4 * c4;
+        if (c < p.ldp) {      // ldp is a multiple of 4 >= M: padding columns receive the zeros of the padded W
+          float4 o = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+          if (p.bias) {
+            if (c < p.M) o.x += __ldg(p.bias + c);
+            if (c + 1 < p.M) o.y += __ldg(p.bias + c + 1);
+            if (c + 2 < p.M) o.z += __ldg(p.bias + c + 2);
+            if (c + 3 < p.M) o.w += __ldg(p.bias + c + 3);
+          }
+          *reinterpret_cast<float4*>(p.P + row * p.ldp + c) = o;
+          if (p.mirror) multimem_st_v4(p.mirror + row * p.ldp + c, o.x, o.y, o.z, o.w);
+        }
+      }
+    }
+  }
+  if (p.mirror) __threadfence_system();
+}
+
+template <int N4>
+static int launch_project_rows(const ProjParams& p, int col_tiles, cudaStream_t stream) {
+  const int Kp = (p.K + PR_KC - 1) / PR_KC * PR_KC;
+  const size_t smem = ((size_t)Kp * 4 * N4 + 8 * (size_t)PR_KC * 33) * sizeof(float);
+  if (smem > 48 * 1024) TGCN_CUDA(cudaFuncSetAttribute(k_project_rows<N4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_blocks = cdiv(p.n_rows, 32);
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n_blocks, 8), (int64_t)sm_count() * 4));
+  k_project_rows<N4><<<dim3(gx, col_tiles), 256, smem, stream>>>(p);
+  return TGCN_OK;
+}
+
 struct DbLayout { size_t off_dw, off_dbh, off_dbo, total; int n_cta; };
 static DbLayout db_layout(int H, int C, int n_cta) {
   DbLayout L; size_t off = 0;
@@ -497,6 +606,49 @@ extern "C" int tgcn_colsum(const float* X, int64_t ldx, int64_t n_rows, int32_t 
   TGCN_LAUNCH_CHECK();
   k_reduce_partials3<<<(unsigned)cdiv((int64_t)F * 32, 256), 256, 0, stream>>>((const float*)workspace, F, out, nullptr, 0, nullptr,
                                                                               nullptr, 0, nullptr, grid);
+  TGCN_LAUNCH_CHECK();
+  return TGCN_OK;
+}
+
+extern "C" int tgcn_project_ex(const tgcn_project_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TGCN_CHECK_ARG(a && a->X && a->W && a->P, "project: null pointer");
+  TGCN_CHECK_ARG(a->n_rows > 0 && a->K > 0 && a->M > 0 && a->ldx >= a->K && a->ldp >= a->M, "project: bad shape");
+  TGCN_CHECK_ARG(a->drop_mode >= TGCN_DROP_NONE && a->drop_mode <= TGCN_DROP_PHILOX, "project: bad drop_mode");
+  const bool drop = a->drop_mode != TGCN_DROP_NONE && a->drop_p > 0.0f;
+  const int Kp4 = (a->K + 3) & ~3;
+  const bool rows_ok = a->x_dtype == TGCN_F32 && a->ldx % 4 == 0 && a->ldx >= Kp4 && a->ldp % 4 == 0 && (((uintptr_t)a->X | (uintptr_t)a->P) & 15) == 0 &&
+                       (a->P_mirror_mc == nullptr || ((uintptr_t)a->P_mirror_mc & 15) == 0);
+  if (!rows_ok || (size_t)((a->K + 31) / 32 * 32) * 32 * 4 > 150 * 1024) {
+    TGCN_CHECK_ARG(!drop && a->Xd == nullptr, "project: the fused dropout needs fp32 X with 16-byte aligned rows (ldx %% 4 == 0, ldx >= pad4(K))");
+    return tgcn_project(a->X, a->ldx, a->x_dtype, a->n_rows, a->K, a->W, a->M, a->bias, a->P, a->ldp, a->P_mirror_mc, stream_);
+  }
+  TGCN_CHECK_ARG(!drop || a->drop_p < 1.0f, "project: dropout p must be in [0,1)");
+  TGCN_CHECK_ARG(a->drop_mode != TGCN_DROP_MASK || !drop || a->keep_mask, "project: TGCN_DROP_MASK needs keep_mask");
+  TGCN_CHECK_ARG(a->Xd == nullptr || (a->ldxd % 4 == 0 && a->ldxd >= Kp4 && ((uintptr_t)a->Xd & 15) == 0), "project: bad Xd");
+  ProjParams p;
+  p.X = (const float*)a->X; p.ldx = a->ldx; p.n_rows = a->n_rows; p.K = a->K; p.W = a->W; p.M = a->M; p.bias = a->bias;
+  p.P = a->P; p.ldp = a->ldp; p.mirror = (float*)a->P_mirror_mc;
+  p.drop_mode = drop ? a->drop_mode : TGCN_DROP_NONE; p.drop_p = a->drop_p; p.drop_scale = drop ? 1.0f / (1.0f - a->drop_p) : 1.0f;
+  p.keep_mask = a->keep_mask; p.ldmask = a->ldmask; p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset;
+  p.philox_offset_dev = a->philox_offset_dev; p.philox_row_offset = a->philox_row_offset; p.philox_F = a->K;
+  p.Xd = drop ? a->Xd : nullptr; p.ldxd = a->ldxd;
+  const int Mp = (a->M + 3) & ~3;
+  const int n4_all = Mp / 4;
+  const int n4 = std::min(n4_all, 8);                    // <= 32 output columns per thread; more: column tiles (grid.y)
+  const int col_tiles = (n4_all + n4 - 1) / n4;
+  int rc;
+  switch (n4) {
+    case 1: rc = launch_project_rows<1>(p, col_tiles, stream); break;
+    case 2: rc = launch_project_rows<2>(p, col_tiles, stream); break;
+    case 3: rc = launch_project_rows<3>(p, col_tiles, stream); break;
+    case 4: rc = launch_project_rows<4>(p, col_tiles, stream); break;
+    case 5: rc = launch_project_rows<5>(p, col_tiles, stream); break;
+    case 6: rc = launch_project_rows<6>(p, col_tiles, stream); break;
+    case 7: rc = launch_project_rows<7>(p, col_tiles, stream); break;
+    default: rc = launch_project_rows<8>(p, col_tiles, stream); break;
+  }
+  if (rc) return rc;
   TGCN_LAUNCH_CHECK();
   return TGCN_OK;
 }

@@ -245,9 +245,13 @@ def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Option
 
 
 def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Optional[torch.Tensor] = None,
-            mirror: Optional[int] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """P = X[:, :K] @ W (+ bias) (thin projection), P padded to a multiple of 4 columns."""
-    _need_cuda(X, W, out, bias)
+            mirror: Optional[int] = None, bias: Optional[torch.Tensor] = None, drop_mode: int = DROP_NONE, drop_p: float = 0.0,
+            keep_mask: Optional[torch.Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,
+            philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0,
+            dropped_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """P = dropout(X[:, :K]) @ W (+ bias) (thin projection), P padded to a multiple of 4 columns.  With a dropout mode the
+    keep decision of the SpMM epilogue is applied to X on load and dropout(X) is written to `dropped_out` (tgcn_project_ex)."""
+    _need_cuda(X, W, out, bias, keep_mask, philox_offset_dev, dropped_out)
     lib = _native.load()
     K = int(W.shape[0]) if K is None else K
     M = int(W.shape[1])
@@ -256,9 +260,23 @@ def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Opti
         raise RuntimeError("project: W must be contiguous fp32")
     if out is None:
         out = torch.zeros((n, pad4(M)), dtype=torch.float32, device=X.device)
+    a = _native.ProjectArgs()
+    a.X, a.ldx, a.x_dtype, a.n_rows, a.K = X.data_ptr(), X.stride(0), _dt(X), n, K
+    a.W, a.M, a.bias = W.data_ptr(), M, _native.ptr(bias)
+    a.P, a.ldp, a.P_mirror_mc = out.data_ptr(), out.stride(0), mirror
+    a.drop_mode, a.drop_p = drop_mode, float(drop_p)
+    if keep_mask is not None:
+        if keep_mask.dtype not in (torch.uint8, torch.bool) or keep_mask.stride(1) != 1:
+            raise RuntimeError("project: keep_mask must be a row-major uint8/bool tensor")
+        a.keep_mask, a.ldmask = keep_mask.data_ptr(), keep_mask.stride(0)
+    a.philox_seed, a.philox_offset = philox_seed & (2**64 - 1), philox_offset & (2**64 - 1)
+    a.philox_offset_dev, a.philox_row_offset = _native.ptr(philox_offset_dev), int(row_id_offset)
+    if dropped_out is not None:
+        if dropped_out.dtype != torch.float32 or dropped_out.stride(1) != 1 or dropped_out.shape[0] < n:
+            raise RuntimeError("project: bad dropped_out tensor")
+        a.Xd, a.ldxd = dropped_out.data_ptr(), dropped_out.stride(0)
     with torch.cuda.device(X.device):
-        _native.check(lib.tgcn_project(X.data_ptr(), X.stride(0), _dt(X), n, K, W.data_ptr(), M, _native.ptr(bias),
-                                       out.data_ptr(), out.stride(0), mirror, _stream()))
+        _native.check(lib.tgcn_project_ex(C.byref(a), _stream()))
     return out
 
 

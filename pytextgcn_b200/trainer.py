@@ -266,7 +266,12 @@ class TextGCNTrainer:
                    philox_offset=0, philox_offset_dev=self.step_dev if drop else None)
         fuse = self.C <= ops.FUSED_PROJ_MAX_CLASSES and not reuse_h1
         if reuse_h1:
-            # H1 = act(A_hat (X W1) + b1) of the preceding eval pass, same W1/b1: only the dropout mask is applied
+            # H1 = act(A_hat (X W1) + b1) of the preceding eval pass, same W1/b1: only the dropout mask is applied --
+            # inside the projection kernel, which also writes the dropped activation for the backward pass
+            if drop and not self.propagate_first:
+                ops.project(self.H1, W2, K=self.H, out=self.P, dropped_out=self.H1d, **dkw)
+                ops.spmm(self.graph, self.P, F=self.Cp, plan=self.plan if full else self.plan_z2, out=self.Z2, bias=b2)
+                return
             if drop:
                 ops.dropout_apply(self.H1, F=self.H, out=self.H1d, **dkw)
             h_out = self.H1d

@@ -400,3 +400,29 @@ def test_propagate_first_dropout_mask_is_the_forward_mask(cuda):
         tr.train_step()
         dropped = tr.H1d == 0
         assert torch.all(tr.dZ1[dropped] == 0) and abs((~dropped).float().mean().item() - 0.5) < 0.02
+
+
+@pytest.mark.parametrize("K,M", [(200, 20), (100, 64), (32, 219), (219, 32), (64, 6), (256, 8)])
+def test_row_per_lane_projection_with_fused_dropout(cuda, K, M):
+    """tgcn_project_ex: P = dropout(X) W + b in one pass, dropout(X) written out: equal to tgcn_dropout_apply (bitwise)
+    followed by an fp64 product; also without dropout, with column tiles (M > 32) and K not a multiple of 4 / 32."""
+    from pytextgcn_b200 import ops
+    torch.manual_seed(K + M)
+    n = 3001
+    Kp = ops.pad4(K)
+    X = torch.zeros(n, Kp, device=cuda)
+    X[:, :K] = torch.randn(n, K, device=cuda)
+    W, b = torch.randn(K, M, device=cuda) * 0.2, torch.randn(M, device=cuda)
+    P = ops.project(X, W, K=K, bias=b)
+    assert rel_err(P[:, :M], X[:, :K].double() @ W.double() + b.double()) < 2e-6 and bool((P[:, M:] == 0).all())
+    if K % 4 == 0:
+        step = torch.full((1,), 3, dtype=torch.int64, device=cuda)
+        kw = dict(drop_mode=ops.DROP_PHILOX, drop_p=0.5, philox_seed=5, philox_offset_dev=step)
+        Xd_ref = ops.dropout_apply(X[:, :K], **kw) if Kp == K else None
+        Xd = torch.zeros(n, Kp, device=cuda)
+        P2 = ops.project(X, W, K=K, dropped_out=Xd, **kw)
+        assert torch.equal(Xd[:, :K], Xd_ref)
+        assert rel_err(P2[:, :M], Xd_ref.double() @ W.double()) < 2e-6
+        keep = (torch.rand(n, K, device=cuda) > 0.3).to(torch.uint8)
+        P3 = ops.project(X, W, K=K, drop_mode=ops.DROP_MASK, drop_p=0.3, keep_mask=keep)
+        assert rel_err(P3[:, :M], (X[:, :K].double() * keep.double() / 0.7) @ W.double()) < 2e-6
