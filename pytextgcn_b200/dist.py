@@ -162,7 +162,8 @@ class DistTextGCNTrainer:
                  rank: int, world: int, dev: torch.device, seed: int = 0, betas=(0.9, 0.999), eps: float = 1e-8,
                  graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None,
                  use_cuda_graph: bool = False, exchange: str = "peer", fused_stores: bool = True,
-                 fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True, restrict_rows: bool = True):
+                 fuse_adam: bool = True, keep_w1_grad: bool = True, share_h1: bool = True, restrict_rows: bool = True,
+                 tensor_cores: Optional[bool] = None, tc_min_density: float = 0.05):
         import torch.distributed as dist
         from . import ops
         from .graph import upload_graph
@@ -191,6 +192,15 @@ class DistTextGCNTrainer:
         del full
         self.plan = self.shard.plan()
         nl, npad, H, Cp = self.part.n_loc, self.part.n_pad, hidden, self.Cp
+        # hybrid hidden-wide propagation on the shard (csrc/spmm_tc.cu; same rule as TextGCNTrainer: L2-resident operand)
+        self.tc = None
+        auto = tensor_cores is None and self.shard.nnz >= 200_000 and npad * ((H + 15) // 16 * 16) * 8 <= (104 << 20)
+        if (tensor_cores or auto) and H % 4 == 0 and 64 <= H <= 256:
+            from .tc_plan import build_tc_plan
+            tc = build_tc_plan(self.shard, min_density=tc_min_density, width=H,
+                               n_sms=torch.cuda.get_device_properties(dev).multi_processor_count)
+            if tc is not None and (tensor_cores or tc.nnz_dense >= 0.15 * self.shard.nnz):
+                self.tc = tc
         f32 = dict(dtype=torch.float32, device=dev)
         # exchange buffers: symmetric (peer-mapped) allocations when the NVLink path is available.  The decision is
         # COLLECTIVE: every rank tries to allocate all of them, the outcomes are all-reduced (MIN), and either every
@@ -342,6 +352,12 @@ class DistTextGCNTrainer:
                 out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
         return out
 
+    def _wide_spmm(self, B: torch.Tensor, **kw):
+        """Hidden-wide propagation over this rank's rows: hybrid (tensor-core tiles + gathered remainder) when planned."""
+        if self.tc is not None:
+            return self.ops.spmm_hybrid(self.tc, B, F=self.H, plan=self.tc.remainder.plan(), **kw)
+        return self.ops.spmm(self.shard, B, F=self.H, plan=self.plan, **kw)
+
     # ---- collectives ----
     # One-sided stores need two guarantees the two-sided ncclAllGather gave for free:
     #  (1) visibility: a barrier after the producers, before any rank reads the exchanged buffer;
@@ -428,7 +444,7 @@ class DistTextGCNTrainer:
             self._gather_w1()
             self._mark("allgather_W1")
             h = self.H1d if training else self.H1
-            ops.spmm(self.shard, self.W1_full, F=self.H, plan=self.plan, out=h, bias=self.b1, **dkw)
+            self._wide_spmm(self.W1_full, out=h, bias=self.b1, **dkw)
             self._note_read("W1")
             self._mark("spmm_wide_fwd")
         pname = "Pt" if training else "Pe"                       # double-buffered, see _pending_reads
@@ -484,9 +500,9 @@ class DistTextGCNTrainer:
             # updated rows go straight to every rank's copy of W1 (multimem.st) -- compute, optimiser and
             # exchange in one kernel
             ops.adam_prepare(self.step_dev, self.adam_hyper, self.lr, self.betas[0], self.betas[1])
-            ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1 if self.keep_w1_grad else None,
-                     want_out=self.keep_w1_grad,
-                     adam=dict(param=self.W1_loc, exp_avg=self.st[0][0], exp_avg_sq=self.st[0][1], max_exp_avg_sq=self.st[0][2],
+            self._wide_spmm(self.dZ1_full, out=self.g_W1 if self.keep_w1_grad else None,
+                            want_out=self.keep_w1_grad,
+                            adam=dict(param=self.W1_loc, exp_avg=self.st[0][0], exp_avg_sq=self.st[0][1], max_exp_avg_sq=self.st[0][2],
                                hyper=self.adam_hyper, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, mirror=mir))
             self._note_read("dZ1")
             self._mark("spmm_wide_bwd")
@@ -494,7 +510,7 @@ class DistTextGCNTrainer:
             # [I | F]: dW1[own rows] = A_hat dZ1 on the shard; dW1[N:] = F^T (A_hat dZ1)[docs], summed over the ranks together
             # with the other small gradients; Adam on (own rows ; replicated tail) in one launch, identical tail on all ranks
             nl_ = self.part.n_loc
-            ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1[:nl_])
+            self._wide_spmm(self.dZ1_full, out=self.g_W1[:nl_])
             self._note_read("dZ1")
             self._mark("spmm_wide_bwd")
             ops.hier_backward(self.g_W1[:nl_], nl_, 0, self.F_loc, self.H, self.l_tail)
@@ -505,7 +521,7 @@ class DistTextGCNTrainer:
             ops.adam_step(self.W1_cat, self.g_W1, *self.st[0], **kw)
             mir = None
         else:
-            ops.spmm(self.shard, self.dZ1_full, F=self.H, plan=self.plan, out=self.g_W1)
+            self._wide_spmm(self.dZ1_full, out=self.g_W1)
             self._note_read("dZ1")
             self._mark("spmm_wide_bwd")
             ops.increment_step(self.step_dev)

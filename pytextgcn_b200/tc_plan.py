@@ -25,8 +25,8 @@ class TcPlan:
     n_nodes: int
     n_row_blocks: int
     n_col_blocks: int
-    rank: torch.Tensor          # int32 [N]: rank of each node (0 = largest degree)
-    perm: torch.Tensor          # int32 [n_col_blocks * 16]: node of each rank, -1 past the end
+    rank: torch.Tensor          # int32 [n_rows]: rank of each row (0 = longest)
+    perm: torch.Tensor          # int32 [>= n_col_blocks * 16]: column (node) of each column rank, -1 past the end
     tile_rb: torch.Tensor       # int32 [n_tiles] row block of each tile (sorted by (row block, column block))
     tile_kb: torch.Tensor       # int32 [n_tiles]
     A_tiles: torch.Tensor       # fp32 [n_tiles, 128, 16]: the values of A_hat, rows swizzled (split into TF32 hi/lo in the kernel)
@@ -84,28 +84,33 @@ def build_tc_plan(graph, min_density: float = 0.05, max_bytes: int = 2 << 30, n_
         (the hub columns); with Bt in HBM every tile would pull its 2 x 64 x width operand bytes from DRAM."""
     from .graph import GraphCSR
     dev = graph.rowptr.device
-    n = graph.n_nodes
-    if graph.n_cols != n:
-        raise RuntimeError("build_tc_plan needs a square matrix (full graph)")
+    n, n_cols = graph.n_nodes, graph.n_cols            # rectangular for a row shard of the 1D partition (rows = own nodes)
     rows = graph.row_ids()
     cols = graph.colidx.to(torch.int64)
     val = graph.val
     nnz = int(cols.numel())
-    # ---- degree ranking ----
-    score = (graph.rowptr[1:] - graph.rowptr[:-1]).to(torch.int64) + torch.bincount(cols, minlength=n)
-    order = torch.sort(score, descending=True, stable=True).indices
+    # ---- degree ranking: rows by their length, columns by the number of entries they hold ----
+    row_len = (graph.rowptr[1:] - graph.rowptr[:-1]).to(torch.int64)
+    col_cnt = torch.bincount(cols, minlength=n_cols)
+    if n == n_cols:                                     # square matrix: one ranking for both (rows and columns are the same nodes)
+        row_order = col_order = torch.sort(row_len + col_cnt, descending=True, stable=True).indices
+    else:
+        row_order = torch.sort(row_len, descending=True, stable=True).indices
+        col_order = torch.sort(col_cnt, descending=True, stable=True).indices
     rank = torch.empty(n, dtype=torch.int64, device=dev)
-    rank[order] = torch.arange(n, device=dev)
+    rank[row_order] = torch.arange(n, device=dev)
+    col_rank = torch.empty(n_cols, dtype=torch.int64, device=dev)
+    col_rank[col_order] = torch.arange(n_cols, device=dev)
     n_rb = (n + TILE_M - 1) // TILE_M
-    n_kb = n_rb * (TILE_M // TILE_K)
-    perm = torch.full((n_kb * TILE_K,), -1, dtype=torch.int32, device=dev)
-    perm[:n] = order.to(torch.int32)
+    n_kb = (n_cols + TILE_K - 1) // TILE_K
+    perm = torch.full(((n_kb * TILE_K + TILE_M - 1) // TILE_M * TILE_M,), -1, dtype=torch.int32, device=dev)
+    perm[:n_cols] = col_order.to(torch.int32)
     # ---- block census ----
-    rr, rc = rank[rows], rank[cols]
+    rr, rc = rank[rows], col_rank[cols]
     key = (rr >> 7) * n_kb + (rc >> 4)
     # duplicate (row, col) entries (possible in a general COO graph, never emitted by Text2GraphTransformer) cannot share
     # a dense cell: all but the first of each pair stay in the remainder
-    full_key = rows * n + cols
+    full_key = rows * n_cols + cols
     srt = torch.sort(full_key, stable=True)
     dup_sorted = torch.zeros(nnz, dtype=torch.bool, device=dev)
     if nnz > 1:
@@ -140,7 +145,7 @@ def build_tc_plan(graph, min_density: float = 0.05, max_bytes: int = 2 << 30, n_
     r_rows = rows[keep]
     rp = torch.zeros(n + 1, dtype=torch.int32, device=dev)
     rp[1:] = torch.cumsum(torch.bincount(r_rows, minlength=n), 0).to(torch.int32)
-    rem = GraphCSR(n, rp, graph.colidx[keep].contiguous(), val[keep].contiguous(), graph.dis)
+    rem = GraphCSR(n, rp, graph.colidx[keep].contiguous(), val[keep].contiguous(), graph.dis, n_cols=n_cols)
     rem._symmetric = False
     # ---- units: <= MAX_TILES_PER_UNIT consecutive tiles of one row block; slots consecutive per row block ----
     per_rb = torch.bincount(tile_rb.to(torch.int64), minlength=n_rb)

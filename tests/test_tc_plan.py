@@ -29,7 +29,7 @@ def test_plan_rebuilds_a_hat_exactly(name, density, n_sms):
     tc = build_tc_plan(gr, min_density=density, n_sms=n_sms)
     assert tc is not None and tc.nnz_dense + tc.remainder.nnz == gr.nnz
     perm = tc.perm.long()
-    assert torch.equal(tc.rank.long()[perm[:n]], torch.arange(n)) and bool((perm[n:] == -1).all())
+    assert torch.equal(tc.rank.long()[perm[:n]], torch.arange(n)) and bool((perm[n:] == -1).all())      # square: one ranking
     off = swizzled_offset(torch.arange(TILE_M).view(-1, 1), torch.arange(TILE_K).view(1, -1))
     assert sorted(off.view(-1).tolist()) == list(range(TILE_M * TILE_K))          # the swizzle is a permutation of the tile
     A = _dense(n, tc.remainder.rowptr, tc.remainder.colidx, tc.remainder.val)
@@ -75,3 +75,34 @@ def test_operand_cap_restricts_tiles_to_hub_column_blocks():
     capped = build_tc_plan(gr, min_density=0.01, n_sms=8, width=64, max_operand_bytes=10 * 2 * 64 * TILE_K * 4)   # 10 column blocks
     assert capped is not None and capped.n_col_blocks <= 10 and int(capped.tile_kb.max()) < 10
     assert 0 < capped.nnz_dense < full.nnz_dense and capped.nnz_dense + capped.remainder.nnz == gr.nnz
+
+
+def test_plan_of_a_row_shard_rebuilds_the_shard():
+    """Rectangular matrix (rows of one rank of the 1D partition, columns in the padded id space): separate row and
+    column rankings; tiles + remainder must rebuild the shard exactly."""
+    from pytextgcn_b200.dist import RowPartition, shard_csr
+    n, rowptr, col, val, gr = _csr("small", 3)
+    part = RowPartition(rowptr[1:] - rowptr[:-1], 3)
+    rp, ci, v = shard_csr(rowptr, col, val, part, 1)
+    shard = GraphCSR(part.n_loc, rp, ci, v, None, n_cols=part.n_pad)
+    tc = build_tc_plan(shard, min_density=0.02, n_sms=5, width=64)
+    assert tc is not None and tc.nnz_dense + tc.remainder.nnz == shard.nnz and tc.remainder.n_cols == part.n_pad
+    perm, rrank = tc.perm.long(), tc.rank.long()
+    row_of_rank = torch.empty(part.n_loc, dtype=torch.int64)
+    row_of_rank[rrank] = torch.arange(part.n_loc)
+    off = swizzled_offset(torch.arange(TILE_M).view(-1, 1), torch.arange(TILE_K).view(1, -1))
+    rows_r = torch.repeat_interleave(torch.arange(part.n_loc), (tc.remainder.rowptr[1:] - tc.remainder.rowptr[:-1]).long())
+    A = torch.zeros(part.n_loc, part.n_pad, dtype=torch.float64)
+    A.index_put_((rows_r, tc.remainder.colidx.long()), tc.remainder.val.double(), accumulate=True)
+    for t in range(tc.n_tiles):
+        tile = tc.A_tiles[t].reshape(-1)[off].double()
+        r0, k0 = int(tc.tile_rb[t]) * TILE_M, int(tc.tile_kb[t]) * TILE_K
+        nr = min(TILE_M, part.n_loc - r0)
+        cn = perm[k0:k0 + TILE_K]
+        vc = cn >= 0
+        assert float(tile[nr:].abs().sum()) == 0 and float(tile[:, ~vc].abs().sum()) == 0
+        A[row_of_rank[r0:r0 + nr].view(-1, 1), cn[vc].view(1, -1)] += tile[:nr][:, vc]
+    ref = torch.zeros(part.n_loc, part.n_pad, dtype=torch.float64)
+    rows_s = torch.repeat_interleave(torch.arange(part.n_loc), (rp[1:] - rp[:-1]).long())
+    ref.index_put_((rows_s, ci.long()), v.double(), accumulate=True)
+    assert torch.equal(A, ref)
