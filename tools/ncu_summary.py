@@ -36,6 +36,9 @@ WANT = {
     "sm__issue_active.avg.pct_of_peak_sustained_elapsed": "issue_active_pct",
     "smsp__issue_active.avg.pct_of_peak_sustained_elapsed": "issue_active_pct",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active": "fma_pipe_pct",
+    "sm__ops_path_tensor_src_tf32_dst_fp32.avg.per_cycle_elapsed": "tf32_flop_per_clk_per_sm",
+    "sm__ops_path_tensor_src_tf32_dst_fp32.avg.pct_of_peak_sustained_elapsed": "tf32_pct_of_ncu_peak",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor_memory_path_active_pct",
 }
 
 
@@ -70,7 +73,27 @@ def main():
                     tot += e[k] * scale.get(k.rsplit("_", 1)[1], 1.0)
             e["dram_bytes_per_launch"] = tot
         out.append(e)
-    json.dump({"source": rep, "launches": out}, sys.stdout, indent=1)
+    res = {"source": rep, "launches": out}
+    # `--hybrid k_tc_pack,k_tc_mma,k_spmm`: DRAM bytes of ONE hybrid propagation = the first launch of each named kernel
+    # after the first k_tc_pack (bench.py reads `dram_bytes_per_launch` as roofline.traffic)
+    if "--hybrid" in sys.argv:
+        names = sys.argv[sys.argv.index("--hybrid") + 1].split(",")
+        start = next((i for i, e in enumerate(out) if names[0] in e["kernel"]), None)
+        if start is not None:
+            tot, used, dur = 0.0, [], 0.0
+            j = start
+            for nm in names:
+                while j < len(out) and nm not in out[j]["kernel"]:
+                    j += 1
+                if j < len(out):
+                    tot += out[j].get("dram_bytes_per_launch", 0.0)
+                    dur += next((v for k, v in out[j].items() if k.startswith("duration")), 0.0)
+                    used.append(out[j]["kernel"][:60])
+                    j += 1
+            res["dram_bytes_per_launch"] = tot
+            res["hybrid_kernels"] = used
+            res["hybrid_duration_sum_us_under_ncu"] = dur
+    json.dump(res, sys.stdout, indent=1)
     print()
 
 
