@@ -43,6 +43,7 @@ constexpr int TC_M = 128;
 constexpr int TC_K = 16;             // 64-byte operand rows (SWIZZLE_64B): small stages, so that 4-5 of them are in flight
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_PREFETCH = 8;       // A tiles requested into L2 this many tiles ahead of their bulk copy
+constexpr int TC_ABUF = 3;           // {A hi, A lo} operand tiles in TMEM: the splitters run up to 2 tiles ahead of the tensor pipe
 constexpr int TC_THREADS = 320;
 constexpr uint32_t TC_A_PART = TC_M * TC_K * 4;      // 8 KB: the values of a tile, or one of its (hi, lo) operand tiles
 constexpr uint32_t TC_TMEM_COLS = 512;               // all of the SM's tensor memory: accumulator(s) + two {A hi, A lo} tiles
@@ -137,8 +138,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
   const int S = p.n_stages;
   const uint32_t stage_bytes = TC_A_PART + 2u * b_part;        // ring stage: A values, Bt hi, Bt lo
   const uint32_t bars = base + (uint32_t)S * stage_bytes;      // 8-byte mbarriers
-  const uint32_t full0 = bars, empty0 = bars + 8 * TC_MAX_STAGES, afull0 = empty0 + 8 * TC_MAX_STAGES, aempty0 = afull0 + 16,
-                 tfull0 = aempty0 + 16, tempty0 = tfull0 + 16;
+  const uint32_t full0 = bars, empty0 = bars + 8 * TC_MAX_STAGES, afull0 = empty0 + 8 * TC_MAX_STAGES, aempty0 = afull0 + 8 * TC_ABUF,
+                 tfull0 = aempty0 + 8 * TC_ABUF, tempty0 = tfull0 + 16;
   const uint32_t holder = tempty0 + 16;                        // TMEM base address written by tcgen05.alloc
   volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(tc_smem_raw + (holder - raw));
 
@@ -147,12 +148,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
       tc_mbar_init(full0 + 8 * s, 1);          // producer's arrive.expect_tx (+ the bytes of both bulk copies)
       tc_mbar_init(empty0 + 8 * s, 1 + 128);   // tcgen05.commit (Bt read) + the 128 splitter threads (A values read)
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < TC_ABUF; ++a) {
       tc_mbar_init(afull0 + 8 * a, 128);       // splitter threads: hi / lo tiles stored to TMEM
       tc_mbar_init(aempty0 + 8 * a, 1);        // tcgen05.commit: hi / lo tiles read
-      tc_mbar_init(tfull0 + 8 * a, 1);
-      tc_mbar_init(tempty0 + 8 * a, 128);
     }
+    for (int a = 0; a < 2; ++a) { tc_mbar_init(tfull0 + 8 * a, 1); tc_mbar_init(tempty0 + 8 * a, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {   // one warp allocates all 512 columns of this SM's tensor memory
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
-  const uint32_t tmem_a0 = tmem_base + (uint32_t)(p.n_acc * p.Fp);   // two {hi[16 cols], lo[16 cols]} A tiles behind the accumulators
+  const uint32_t tmem_a0 = tmem_base + (uint32_t)(p.n_acc * p.Fp);   // TC_ABUF {hi[16 cols], lo[16 cols]} A tiles behind the accumulators
 
   if (warp == 0) {
     // ---------------- producer: one thread issues two bulk copies per tile ----------------
@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.Fp);
         for (int t = un.x; t < un.y; ++t, ++it) {
-          const int s = it % S, a = it & 1;
-          const uint32_t ph = (uint32_t)(it / S) & 1u, sph = (uint32_t)(it >> 1) & 1u;
+          const int s = it % S, a = it % TC_ABUF;
+          const uint32_t ph = (uint32_t)(it / S) & 1u, sph = (uint32_t)(it / TC_ABUF) & 1u;
           tc_mbar_wait(full0 + 8 * s, ph);                     // the Bt tile has landed
           tc_mbar_wait(afull0 + 8 * a, sph);                   // the splitters have stored A hi / lo to TMEM
           tc_fence_after();
@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_mma(const TcParams p) {
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int4 un = __ldg(p.units + u);
       for (int t = un.x; t < un.y; ++t, ++it) {
-        const int s = it % S, a = it & 1;
-        const uint32_t ph = (uint32_t)(it / S) & 1u, sph = (uint32_t)(it >> 1) & 1u;
+        const int s = it % S, a = it % TC_ABUF;
+        const uint32_t ph = (uint32_t)(it / S) & 1u, sph = (uint32_t)(it / TC_ABUF) & 1u;
         tc_mbar_wait(full0 + 8 * s, ph);                       // the tile's values have landed
         const uint32_t src = base + s * stage_bytes + (uint32_t)row * (TC_K * 4);
         uint32_t hi[16], lo[16];
@@ -379,7 +379,7 @@ extern "C" int tgcn_spmm_tc(const tgcn_tc_plan* plan, const float* B, int64_t ld
   const size_t stage = (size_t)TC_A_PART + 2 * (size_t)Fp * TC_K * 4;
   const size_t fixed = 1024 /* alignment slack */ + 512 /* barriers */;
   const int n_stages = (int)std::min<size_t>(TC_MAX_STAGES, (227 * 1024 - fixed) / stage);
-  p.n_acc = (2 * Fp + 4 * TC_K <= (int)TC_TMEM_COLS) ? 2 : 1;
+  p.n_acc = (2 * Fp + TC_ABUF * 2 * TC_K <= (int)TC_TMEM_COLS) ? 2 : 1;
   TGCN_CHECK_ARG(n_stages >= 2, "spmm_tc: F = %d does not leave room for two pipeline stages", F);
   const size_t smem = n_stages * stage + fixed;
   p.n_stages = n_stages; p.n_tiles = plan->n_tiles;

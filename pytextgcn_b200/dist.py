@@ -434,11 +434,11 @@ class DistTextGCNTrainer:
         drop = training and self.p > 0
         dkw = dict(drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
                    philox_offset_dev=self.step_dev if drop else None, row_id_offset=self.rank * self.part.n_loc)
+        fused_drop = False
         if training and self.share_h1 and self._h1_valid:
-            # the eval forward that preceded this step saw the same W1/b1: its rows only need this step's dropout mask
-            if drop:
-                ops.dropout_apply(self.H1, F=self.H, out=self.H1d, **dkw)
-            h = self.H1d
+            # the eval forward that preceded this step saw the same W1/b1: its rows only need this step's dropout mask,
+            # applied inside the projection kernel below (which also writes the dropped rows for the backward pass)
+            h, fused_drop = (self.H1, True) if drop else (self.H1d, False)
             self._mark("dropout_apply")
         else:
             self._gather_w1()
@@ -451,7 +451,10 @@ class DistTextGCNTrainer:
         P_full, P_loc = (self.Pt_full, self.Pt_loc) if training else (self.Pe_full, self.Pe_loc)
         self._before_write(pname)
         mir = self._mirror(pname, P_loc, P_full)
-        ops.project(h, self.W2, K=self.H, out=P_loc, mirror=mir)     # layer 2's thin X W, stored to all ranks
+        if fused_drop:
+            ops.project(h, self.W2, K=self.H, out=P_loc, mirror=mir, dropped_out=self.H1d, **dkw)
+        else:
+            ops.project(h, self.W2, K=self.H, out=P_loc, mirror=mir)     # layer 2's thin X W, stored to all ranks
         self._exchange(P_full, P_loc, pname, mir is not None)
         self._mark("allgather_P")
         ops.spmm(self.shard, P_full, F=self.Cp, plan=self.plan_z2, out=self.Z2, bias=self.b2)
