@@ -175,6 +175,8 @@ int tgcn_masked_nll(const float* Z, int64_t ldz, int64_t n_rows, int32_t n_class
                     float* loss_out, double* partial_out,
                     float* dZ, int64_t lddz, int32_t* pred_out, int32_t* correct_out,
                     void* dZ_mirror_mc /* multicast mapping of dZ or NULL: see (6) */,
+                    const uint8_t* mask2, int32_t* correct2_out /* optional second accuracy count from the same pass:
+                       #rows of mask2 with argmax == y (the eval pass scores validation AND training rows, flat_amazon.py:113-114) */,
                     void* workspace, size_t workspace_bytes, void* stream);
 int tgcn_masked_nll_workspace_bytes(int64_t n_rows, size_t* bytes_out);
 

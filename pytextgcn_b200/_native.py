@@ -96,7 +96,7 @@ SIGNATURES = {
     "tgcn_spmm_tc": (C.c_int, [C.POINTER(TcPlanArgs), c_void, C.c_int64, C.c_int32, c_void, c_void, C.c_int64, c_void]),
     "tgcn_spmm_tc_workspace_elems": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_int64)]),
     "tgcn_masked_nll": (C.c_int, [c_void, C.c_int64, C.c_int64, C.c_int32, c_void, c_void, C.c_int64,
-                                  c_void, c_void, c_void, C.c_int64, c_void, c_void, c_void,
+                                  c_void, c_void, c_void, C.c_int64, c_void, c_void, c_void, c_void, c_void,
                                   c_void, C.c_size_t, c_void]),
     "tgcn_masked_nll_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "tgcn_dense_bwd": (C.c_int, [C.POINTER(DenseBwdArgs), c_void, C.c_size_t, c_void]),

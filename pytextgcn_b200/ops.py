@@ -164,7 +164,9 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
                partial: Optional[torch.Tensor] = None, dZ_mirror: Optional[int] = None):
     """Masked mean cross-entropy over rows of Z (+ gradient / argmax / #correct).  See tgcn_masked_nll.
     Returns dict(loss=[2] fp32 (mean nll, count), dZ, pred, correct, partial)."""
-    _need_cuda(Z, y, mask, dZ)
+    _need_cuda(Z, y, mask, dZ, mask2, correct2)
+    if correct2 is not None and (mask2 is None or mask2.dtype not in (torch.bool, torch.uint8) or not mask2.is_contiguous()):
+        raise RuntimeError("masked_nll: correct2 needs a contiguous bool/uint8 mask2")
     lib = _native.load()
     n = int(Z.shape[0])
     if Z.dtype != torch.float32 or Z.stride(1) != 1:
@@ -182,7 +184,7 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
         dZ = torch.zeros((n, pad4(n_classes)), dtype=torch.float32, device=dev)
     if pred is None and want_pred:
         pred = torch.empty(n, dtype=torch.int32, device=dev)
-    if correct is None and want_correct:
+    if correct is None and (want_correct or correct2 is not None):
         correct = torch.zeros(1, dtype=torch.int32, device=dev)
     need = 2 * ((n * 4 + 255) // 256 * 256) + 4096  # == tgcn_masked_nll_workspace_bytes(n)
     if workspace is None or workspace.numel() < need:
@@ -192,8 +194,9 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
                                           int(n_mask_total), loss_out.data_ptr(), _native.ptr(partial),
                                           _native.ptr(dZ) if want_grad else None, dZ.stride(0) if want_grad else 0,
                                           _native.ptr(pred), _native.ptr(correct), dZ_mirror,
+                                          _native.ptr(mask2) if correct2 is not None else None, _native.ptr(correct2),
                                           workspace.data_ptr(), workspace.numel(), _stream()))
-    return dict(loss=loss_out, dZ=dZ if want_grad else None, pred=pred, correct=correct, partial=partial)
+    return dict(loss=loss_out, dZ=dZ if want_grad else None, pred=pred, correct=correct, partial=partial, correct2=correct2)
 
 
 def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Optional[torch.Tensor], *,

@@ -336,11 +336,13 @@ class TextGCNTrainer:
         """eval forward, val loss, argmax, #correct on the val and train rows
         (flat_amazon.py:107-114 without the D2H copies)."""
         self._forward(False, full=full)
-        if self.n_val > 0:
+        if self.n_val > 0:      # one pass: val loss, argmax, #correct on the val rows and (mask2) on the train rows
             ops.masked_nll(self.Z2, self.C, self.y, self.val_mask, self.n_val, want_grad=False,
-                           loss_out=self.loss_val, workspace=self._nll_ws, pred=self.pred, correct=self.correct_val)
-        ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=False,
-                       loss_out=self.loss_tr_eval, workspace=self._nll_ws, pred=self.pred, correct=self.correct_train)
+                           loss_out=self.loss_val, workspace=self._nll_ws, pred=self.pred, correct=self.correct_val,
+                           mask2=self.train_mask, correct2=self.correct_train)
+        else:
+            ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=False,
+                           loss_out=self.loss_tr_eval, workspace=self._nll_ws, pred=self.pred, correct=self.correct_train)
 
     # ---- graph capture plumbing ----
     def _run(self, name: str, body) -> None:

@@ -426,3 +426,23 @@ def test_row_per_lane_projection_with_fused_dropout(cuda, K, M):
         keep = (torch.rand(n, K, device=cuda) > 0.3).to(torch.uint8)
         P3 = ops.project(X, W, K=K, drop_mode=ops.DROP_MASK, drop_p=0.3, keep_mask=keep)
         assert rel_err(P3[:, :M], (X[:, :K].double() * keep.double() / 0.7) @ W.double()) < 2e-6
+
+
+def test_masked_nll_second_accuracy_count(cuda):
+    """One pass gives the validation loss / accuracy AND the training-row accuracy (mask2)."""
+    from pytextgcn_b200 import ops
+    torch.manual_seed(2)
+    n, C = 5000, 20
+    z = torch.randn(n, C)
+    y = torch.randint(0, C, (n,))
+    u = torch.rand(n)
+    val, train = u < 0.2, (u >= 0.2) & (u < 0.7)
+    y_dev = y.clone(); y_dev[~(val | train)] = -1
+    zd = z.to(cuda)
+    c1, c2 = torch.zeros(1, dtype=torch.int32, device=cuda), torch.zeros(1, dtype=torch.int32, device=cuda)
+    r = ops.masked_nll(zd, C, y_dev.to(cuda), val.to(cuda), int(val.sum()), want_grad=False, want_pred=True, correct=c1,
+                       mask2=train.to(cuda), correct2=c2)
+    pred = z.argmax(1)
+    assert int(c1.item()) == int((pred[val] == y[val]).sum()) and int(c2.item()) == int((pred[train] == y[train]).sum())
+    assert abs(r["loss"][0].item() - torch.nn.functional.cross_entropy(z[val], y[val]).item()) < 1e-5
+    assert torch.equal(r["pred"].cpu().long(), pred)
