@@ -161,7 +161,8 @@ def masked_nll(Z: torch.Tensor, n_classes: int, y: torch.Tensor, mask: Optional[
                want_correct: bool = False, loss_out: Optional[torch.Tensor] = None,
                workspace: Optional[torch.Tensor] = None, pred: Optional[torch.Tensor] = None,
                correct: Optional[torch.Tensor] = None, want_partial: bool = False,
-               partial: Optional[torch.Tensor] = None, dZ_mirror: Optional[int] = None):
+               partial: Optional[torch.Tensor] = None, dZ_mirror: Optional[int] = None,
+               mask2: Optional[torch.Tensor] = None, correct2: Optional[torch.Tensor] = None):
     """Masked mean cross-entropy over rows of Z (+ gradient / argmax / #correct).  See tgcn_masked_nll.
     Returns dict(loss=[2] fp32 (mean nll, count), dZ, pred, correct, partial)."""
     _need_cuda(Z, y, mask, dZ, mask2, correct2)
