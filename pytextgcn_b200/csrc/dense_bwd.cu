@@ -421,16 +421,27 @@ __global__ void __launch_bounds__(256) k_project_rows(const ProjParams p) {
     float acc[4 * N4];
 #pragma unroll
     for (int i = 0; i < 4 * N4; ++i) acc[i] = 0.0f;
-    for (int k0 = 0; k0 < p.K; k0 += PR_KC) {
-      // ---- load 32 rows x 32 columns (8 float4 per lane), dropout, transpose into shared memory ----
+    // software pipeline: the 8 float4 of the NEXT chunk are in flight while the current chunk is multiplied
+    float4 nxt[8];
+    auto fetch = [&](int k0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int t = i * 32 + lane, r = t >> 3, kq = t & 7;
         const int64_t row = row0 + r;
         const int k = k0 + 4 * kq;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        nxt[i] = (row < p.n_rows && k < p.K) ? __ldg(reinterpret_cast<const float4*>(p.X + row * p.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < p.K; k0 += PR_KC) {
+      // ---- 32 rows x 32 columns (8 float4 per lane): dropout, write-out, transpose into shared memory ----
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int t = i * 32 + lane, r = t >> 3, kq = t & 7;
+        const int64_t row = row0 + r;
+        const int k = k0 + 4 * kq;
+        float4 v = nxt[i];
         if (row < p.n_rows && k < p.K) {
-          v = __ldg(reinterpret_cast<const float4*>(p.X + row * p.ldx + k));
           if (p.drop_mode == TGCN_DROP_MASK) {
             const uint8_t* m = p.keep_mask + row * p.ldmask + k;
             v.x = m[0] ? v.x * p.drop_scale : 0.0f; v.y = m[1] ? v.y * p.drop_scale : 0.0f;
@@ -447,6 +458,7 @@ __global__ void __launch_bounds__(256) k_project_rows(const ProjParams p) {
         d[0] = v.x; d[33] = v.y; d[66] = v.z; d[99] = v.w;
       }
       __syncwarp();
+      if (k0 + PR_KC < p.K) fetch(k0 + PR_KC);
       const float* wk = Ws + k0 * (4 * N4);
 #pragma unroll 4
       for (int k = 0; k < PR_KC; ++k) {
