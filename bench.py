@@ -625,6 +625,8 @@ def main():
     ap.add_argument("--no-cuda-graph", dest="no_cuda_graph", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-fused-stores", dest="no_fused_stores", action="store_true")
+    ap.add_argument("--partition", choices=("auto", "row", "words"), default="auto",
+                    help="N > 1: 1D row partition, or the word-block exchange (x = I graphs with many more documents than words)")
     ap.add_argument("--no-fuse-adam", dest="no_fuse_adam", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

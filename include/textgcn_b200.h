@@ -137,6 +137,10 @@ typedef struct {
    * entries OUTSIDE the dense tiles and, before the epilogue, row r adds part[s][tc_rank[r] % 128][:] for the slots
    * s in [tc_slot_ptr[tc_rank[r] / 128], tc_slot_ptr[tc_rank[r] / 128 + 1]), in slot order. */
   const float* tc_part; int64_t tc_ld; const int32_t* tc_rank; const int32_t* tc_slot_ptr;
+  /* optional partial rows computed elsewhere (bipartite exchange of the multi-GPU path: the contributions of the
+   * other ranks' documents to this rank's word rows): local row r < raw_rows adds raw_in[k * raw_stride + r * raw_ld + :]
+   * for k = 0 .. n_raw - 1, in that order, before the dense-tile partials and the epilogue. */
+  const float* raw_in; int64_t raw_ld; int64_t raw_stride; int32_t n_raw; int64_t raw_rows;
 } tgcn_spmm_args;
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
 

@@ -38,6 +38,7 @@ class SpmmArgs(C.Structure):
         ("adam_ld", C.c_int64), ("adam_hyper_dev", c_void), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float),
         ("adam_eps", C.c_float), ("adam_param_mirror_mc", c_void),
         ("tc_part", c_void), ("tc_ld", C.c_int64), ("tc_rank", c_void), ("tc_slot_ptr", c_void),
+        ("raw_in", c_void), ("raw_ld", C.c_int64), ("raw_stride", C.c_int64), ("n_raw", C.c_int32), ("raw_rows", C.c_int64),
     ]
 
 

@@ -157,6 +157,20 @@ __global__ void __launch_bounds__(256, (VPL * Vec<TB>::E <= 8) ? 4 : 2) k_spmm(c
     }
   }
   if constexpr (E == 4) {
+    if (p.raw_in != nullptr && (ch.x - p.c_row_offset) < p.raw_rows && lane < LPR) {
+      // contributions computed by the other ranks (bipartite exchange), fixed slot order
+      const float* src = p.raw_in + (ch.x - p.c_row_offset) * p.raw_ld;
+      for (int k = 0; k < p.n_raw; ++k, src += p.raw_stride) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c0 = (l + v * LPR) * E;
+          if (c0 < F) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(src + c0));
+            acc[v][0] += t.x; acc[v][1] += t.y; acc[v][2] += t.z; acc[v][3] += t.w;
+          }
+        }
+      }
+    }
     if (p.tc_part != nullptr) {
       // hybrid propagation: the dense blocks of this row were multiplied on the tensor cores (spmm_tc.cu); their
       // partial rows are added here in slot order (fixed order: deterministic), once per row (last chunk of a split row)

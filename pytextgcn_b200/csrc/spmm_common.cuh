@@ -26,6 +26,8 @@ struct SpmmParams {
   float ad_b1, ad_b2, ad_eps; float* ad_mirror;
   // dense-tile partial results of tgcn_spmm_tc, added to the row before the epilogue (hybrid propagation)
   const float* __restrict__ tc_part; int64_t tc_ld; const int32_t* __restrict__ tc_rank; const int32_t* __restrict__ tc_slot_ptr;
+  // partial rows of other ranks (bipartite exchange), added in slot order to local rows < raw_rows before the epilogue
+  const float* __restrict__ raw_in; int64_t raw_ld, raw_stride, raw_rows; int32_t n_raw;
 };
 
 // ---- loads of 16 bytes of the dense operand -> 4 (fp32) or 8 (bf16) floats ----
@@ -212,6 +214,11 @@ static inline int fill_spmm_params(const tgcn_spmm_args* a, SpmmParams* p) {
   p->ad_ld = a->adam_ld; p->ad_hyp = a->adam_hyper_dev; p->ad_b1 = a->adam_beta1; p->ad_b2 = a->adam_beta2; p->ad_eps = a->adam_eps;
   p->ad_mirror = (float*)a->adam_param_mirror_mc;
   p->tc_part = a->tc_part; p->tc_ld = a->tc_ld; p->tc_rank = a->tc_rank; p->tc_slot_ptr = a->tc_slot_ptr;
+  p->raw_in = a->n_raw > 0 ? a->raw_in : nullptr; p->raw_ld = a->raw_ld; p->raw_stride = a->raw_stride; p->raw_rows = a->raw_rows; p->n_raw = a->n_raw;
+  if (p->raw_in) {
+    TGCN_CHECK_ARG(p->raw_ld % 4 == 0 && p->raw_ld >= a->F && p->raw_stride % 4 == 0 && ((uintptr_t)p->raw_in & 15) == 0 && a->b_dtype == TGCN_F32,
+                   "spmm: raw_in needs fp32 operands and 16-byte aligned rows (raw_ld, raw_stride multiples of 4)");
+  }
   if (p->tc_part) {
     TGCN_CHECK_ARG(p->tc_rank && p->tc_slot_ptr && p->tc_ld % 4 == 0 && p->tc_ld >= a->F && ((uintptr_t)p->tc_part & 15) == 0,
                    "spmm: dense-tile partials need tc_rank, tc_slot_ptr and a 16-byte aligned buffer with tc_ld %% 4 == 0");

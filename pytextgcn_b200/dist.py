@@ -676,7 +676,24 @@ def renumbered_data(g, part: RowPartition):
                 test_mask=part.to_new(g.test_mask.cpu(), False), n_vocab=getattr(g, "n_vocab", 0))
 
 
-def parity_against_single_gpu(g, shape, rank: int, world: int, dev: torch.device, seed: int, epochs: int = 5, **trainer_kw):
+def choose_partition(g, requested: str = "auto") -> str:
+    """"row" (DistTextGCNTrainer: all N rows of an operand cross ranks) or "words" (dist_bipartite: the word block and
+    the partial word rows, 2 V rows).  auto: the word-block scheme when x = I and it moves at most 3/4 of the rows."""
+    if requested in ("row", "words"):
+        return requested
+    n, v = int(g.x.shape[0]), int(getattr(g, "n_vocab", 0) or 0)
+    return "words" if (int(g.x.shape[1]) == n and 0 < v and 2 * v <= 0.75 * n) else "row"
+
+
+def make_dist_trainer(g, shape, rank: int, world: int, dev: torch.device, partition: str = "auto", **kw):
+    if choose_partition(g, partition) == "words":
+        from .dist_bipartite import BipartiteTextGCNTrainer
+        return BipartiteTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad, rank, world, dev, **kw)
+    return DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad, rank, world, dev, **kw)
+
+
+def parity_against_single_gpu(g, shape, rank: int, world: int, dev: torch.device, seed: int, epochs: int = 5,
+                              partition: str = "row", **trainer_kw):
     """Runs `epochs` epochs of a FRESH N-rank trainer in its shipped configuration (CUDA graph from the third epoch on,
     multicast stores fused into the producers, dropout on) and, on rank 0, the same epochs of the single-GPU
     TextGCNTrainer on the renumbered graph with the same seed and initial weights.  Returns on rank 0
@@ -685,8 +702,7 @@ def parity_against_single_gpu(g, shape, rank: int, world: int, dev: torch.device
     from .models import GCN
     from .trainer import TextGCNTrainer
     n = int(g.x.shape[0])
-    tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad, rank, world, dev,
-                            seed=seed, **trainer_kw)
+    tr = make_dist_trainer(g, shape, rank, world, dev, partition, seed=seed, **trainer_kw)
     losses = []
     for _ in range(epochs):
         tr.epoch()
@@ -715,7 +731,7 @@ def parity_against_single_gpu(g, shape, rank: int, world: int, dev: torch.device
         def rel(a, b):
             return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
         out = {"epochs": epochs, "cuda_graph": graphed, "fused_stores": tr.fused_stores, "exchange": tr.exchange,
-               "dropout": shape.dropout,
+               "dropout": shape.dropout, "partition": type(tr.part).__name__,
                "max_rel_err_loss": max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(losses, ref_losses)),
                "max_rel_err_W2": rel(params["layers.1.weight"], gcn.layers[1].weight.data),
                "max_rel_err_W1": rel(params["layers.0.weight"], tr.part.to_old(gcn.layers[0].weight.data)),
@@ -739,10 +755,10 @@ def _timed_dist_workload(levels, args, rank, local_rank, world, dev, K, W, sampl
     import torch.distributed as dist
     from . import _native
     lib = _native.load()
-    trs = [DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad,
-                              rank, world, dev, seed=args.seed, use_cuda_graph=not getattr(args, "no_cuda_graph", False),
-                              exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False),
-                              fuse_adam=not getattr(args, "no_fuse_adam", False), keep_w1_grad=False) for g, shape in levels]
+    trs = [make_dist_trainer(g, shape, rank, world, dev, getattr(args, "partition", "auto"), seed=args.seed,
+                             use_cuda_graph=not getattr(args, "no_cuda_graph", False),
+                             exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False),
+                             fuse_adam=not getattr(args, "no_fuse_adam", False), keep_w1_grad=False) for g, shape in levels]
     tr = trs[-1]
 
     def epoch():
@@ -810,14 +826,14 @@ def _timed_dist_workload(levels, args, rank, local_rank, world, dev, K, W, sampl
     e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / (rounds * K)], device=dev, dtype=torch.float64)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler is not None else None
-    nnz_loc = torch.tensor([tr.shard.nnz], device=dev, dtype=torch.float64)
+    nnz_loc = torch.tensor([tr.shard.nnz + (tr.qshard.nnz if hasattr(tr, "qshard") else 0)], device=dev, dtype=torch.float64)
     nnz_all = [torch.zeros_like(nnz_loc) for _ in range(world)]
     dist.all_gather(nnz_all, nnz_loc)
     rec = dict(ms_per_step=ms_per_step, e2e_ms=float(e2e.item()), launches=launches, timed_steps=rounds * K, clocks=clocks,
                nl=nl, nnz_per_rank=[int(t.item()) for t in nnz_all], bytes_per_train_step=sum(t.bytes_per_train_step() for t in trs),
                last=last, cuda_graph=all(t._graph is not None for t in trs), graph_error=tr.graph_error, exchange=tr.exchange,
                exchange_error=tr.exchange_error, fused_stores=tr.fused_stores, share_h1=tr.share_h1,
-               restrict_rows=tr.restrict_rows,
+               restrict_rows=tr.restrict_rows, partition=[type(t.part).__name__ for t in trs],
                multicast=bool(tr.px is not None and any(tr.px.multicast.values())),
                launches_per_epoch=sum(t.launches_per_epoch for t in trs))
     for t in trs:
@@ -844,7 +860,7 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
              "last_epoch": main["last"], "cuda_graph": main["cuda_graph"], "cuda_graph_error": main["graph_error"],
              "exchange": main["exchange"], "exchange_error": main["exchange_error"], "fused_stores": main["fused_stores"],
              "multicast": main["multicast"], "share_h1": main["share_h1"], "restrict_rows": main["restrict_rows"],
-             "timed_steps": main["timed_steps"],
+             "timed_steps": main["timed_steps"], "partition": main["partition"],
              "kernels_per_epoch": main["launches_per_epoch"]}
     if not getattr(args, "no_extras", False):
         # (1) the shipped N-rank configuration (CUDA graph + multimem stores + dropout) against the single-GPU trainer
@@ -852,7 +868,8 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
             if hier0 is not None:
                 raise NotImplementedError("parity helper covers x = I")
             extra["parity"] = parity_against_single_gpu(
-                g, shape, rank, world, dev, args.seed, epochs=5, use_cuda_graph=not getattr(args, "no_cuda_graph", False),
+                g, shape, rank, world, dev, args.seed, epochs=5, partition=choose_partition(g, getattr(args, "partition", "auto")),
+                use_cuda_graph=not getattr(args, "no_cuda_graph", False),
                 exchange=getattr(args, "exchange", "peer"), fused_stores=not getattr(args, "no_fused_stores", False),
                 fuse_adam=not getattr(args, "no_fuse_adam", False), keep_w1_grad=False)
         except Exception as e:
@@ -868,7 +885,8 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
                                          "n_nodes": int(gs.x.shape[0]), "n_edges": int(gs.edge_index.shape[1]),
                                          "hidden": sc.hidden, "nnz_per_rank": r["nnz_per_rank"],
                                          "collective_bytes_received_per_rank_per_train_step": r["bytes_per_train_step"],
-                                         "e2e_epochs_per_s": 1e3 / r["e2e_ms"], "cuda_graph": r["cuda_graph"]}
+                                         "e2e_epochs_per_s": 1e3 / r["e2e_ms"], "cuda_graph": r["cuda_graph"],
+                                         "partition": r["partition"][0], "exchange": r["exchange"]}
                 g = gs
             except Exception as e:
                 extra["scale_config"] = {"error": repr(e)}
@@ -876,7 +894,9 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
         sh_last, hier_last = specs[-1][1], specs[-1][2]
         g_cfg = make_graph(sh_last, seed=args.seed, hierarchy_classes=hier_last)
         cfg = workload_config(args.workload, specs, g_cfg)
-        cfg["parallelism"] = (f"1D row partition x{world} (snake order by nnz); exchange between layers: " +
+        cfg["parallelism"] = (f"word-block partition x{world} (words and documents dealt in snake order; exchange = all-gather of the "
+                              "word block + all-to-all of the partial word rows, NCCL)" if main["partition"][0] == "BipartitePartition" else
+                              f"1D row partition x{world} (snake order by nnz); exchange between layers: " +
                               (("multimem stores fused into the producer kernels + device barrier" if main["fused_stores"] else
                                 "peer-store push kernel into symmetric buffers + device barrier") if main["exchange"] == "peer"
                                else "NCCL all_gather_into_tensor"))

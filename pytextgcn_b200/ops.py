@@ -56,7 +56,8 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
          drop_mode: int = DROP_NONE, drop_p: float = 0.0, keep_mask: Optional[torch.Tensor] = None,
          philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0,
          W_proj: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
-         want_out: bool = True, adam: Optional[dict] = None, tc=None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+         want_out: bool = True, adam: Optional[dict] = None, tc=None,
+         raw_slots: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """C = epi(A_hat[rows of plan] @ B[:, :F]) (+ P = C @ W_proj).  See tgcn_spmm.
     tc: a TcPlan whose dense-tile partial rows (already computed by tgcn_spmm_tc for this B, see spmm_hybrid) are
     added to every row before the epilogue; `graph` must then be the plan's remainder.
@@ -128,6 +129,12 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
         if P is None:
             P = torch.zeros((n_out, pad4(n_proj)), dtype=torch.float32, device=B.device)
         a.W_proj, a.n_proj, a.P, a.ldp = W_proj.data_ptr(), n_proj, P.data_ptr(), P.stride(0)
+    if raw_slots is not None:
+        # [n_slots, rows, >= F] fp32: partial rows added (slot order) to the first `rows` local rows before the epilogue
+        if raw_slots.dtype != torch.float32 or raw_slots.dim() != 3 or raw_slots.stride(2) != 1 or raw_slots.shape[2] < F:
+            raise RuntimeError("spmm: raw_slots must be an fp32 [n_slots, rows, >= F] tensor")
+        a.raw_in, a.raw_ld, a.raw_stride = raw_slots.data_ptr(), raw_slots.stride(1), raw_slots.stride(0)
+        a.n_raw, a.raw_rows = int(raw_slots.shape[0]), int(raw_slots.shape[1])
     if tc is not None:
         if graph is not tc.remainder:
             raise RuntimeError("spmm: with tc=..., graph must be the plan's remainder CSR")

@@ -40,6 +40,22 @@ def main():
         print("DIST_WORKER parity", par, flush=True)
         assert par["cuda_graph"], "the N-rank epoch was not captured in a CUDA graph"
         assert par["max_rel_err_loss"] < 1e-4 and par["max_rel_err_W2"] < 1e-3 and par["max_rel_err_W1"] < 1e-3, par
+    dist.barrier()
+    # the word-block exchange (dist_bipartite.py) in its shipped configuration on a documents >> words graph
+    shape3 = GraphShape("t3", 600, 2101, 12000, 20, 6, 64, dropout=0.5, amsgrad=True, lr=0.02)
+    g3 = make_graph(shape3, seed=7)
+    par = parity_against_single_gpu(g3, shape3, rank, world, dev, seed=4, epochs=6, partition="words", use_cuda_graph=True,
+                                    keep_w1_grad=False)
+    if rank == 0:
+        print("DIST_WORKER word-block parity", par, flush=True)
+        assert par["partition"] == "BipartitePartition" and par["cuda_graph"], par
+        assert par["max_rel_err_loss"] < 1e-4 and par["max_rel_err_W2"] < 1e-3 and par["max_rel_err_W1"] < 1e-3, par
+    # ... and with the hybrid (tensor-core tiles + gathered remainder) hidden-wide propagation on the shards
+    par = parity_against_single_gpu(g3, shape3, rank, world, dev, seed=4, epochs=6, partition="words", use_cuda_graph=True,
+                                    keep_w1_grad=False, tensor_cores=True, tc_min_density=0.01)
+    if rank == 0:
+        print("DIST_WORKER word-block + tensor-core tiles parity", par, flush=True)
+        assert par["max_rel_err_loss"] < 1e-4 and par["max_rel_err_W2"] < 1e-3 and par["max_rel_err_W1"] < 1e-3, par
         print("DIST_WORKER_OK", flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -141,3 +141,106 @@ def test_two_rank_gloo_collective_sequence_matches_oracle():
     assert res["loss"] < 1e-6
     for k in ("gW1", "db1", "dW2", "db2"):
         assert res[k] < 1e-5, (k, res[k])
+
+
+# --------------------------------------------------------------------------------------
+# word-block (bipartite) partition of dist_bipartite.py
+# --------------------------------------------------------------------------------------
+from pytextgcn_b200.dist_bipartite import BipartitePartition, shard_bipartite  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_bipartite_partition_is_a_bijection_with_words_first(world):
+    g = make_graph(SHAPE, seed=0)
+    n, rowptr, col, val = _global_csr(g)
+    part = BipartitePartition(rowptr[1:] - rowptr[:-1], g.n_vocab, world)
+    assert part.n_loc == part.v_loc + part.d_loc and part.n_pad == world * part.n_loc
+    assert torch.equal(part.old_id[part.new_id], torch.arange(n))
+    loc = part.new_id % part.n_loc
+    assert bool((loc[:g.n_vocab] < part.v_loc).all()) and bool((loc[g.n_vocab:] >= part.v_loc).all())
+    x = torch.randn(n, 3)
+    assert torch.equal(part.to_old(part.to_new(x)), x)
+    # words and documents are both balanced to within one row per rank
+    for lo, hi in ((0, g.n_vocab), (g.n_vocab, n)):
+        per = torch.bincount(part.new_id[lo:hi] // part.n_loc, minlength=world)
+        assert int(per.max() - per.min()) <= 1
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_bipartite_sharded_spmm_equals_global(world):
+    """main_r @ [all words ; own docs] + sum_s (q_s @ docs of s)[words of r] == rows of A_hat X owned by r."""
+    g = make_graph(SHAPE, seed=1)
+    n, rowptr, col, val = _global_csr(g)
+    part = BipartitePartition(rowptr[1:] - rowptr[:-1], g.n_vocab, world)
+    nl, vl, vp = part.n_loc, part.v_loc, part.v_pad
+    B = torch.randn(n, 8, dtype=torch.float64)
+    ref = _local_spmm(rowptr, col, val, B)
+    Bn = part.to_new(B).view(world, nl, 8)
+    words = Bn[:, :vl].reshape(vp, 8)                       # what the all-gather of the word block delivers
+    shards = [shard_bipartite(rowptr, col, val, part, r) for r in range(world)]
+    assert sum(int(m[1].numel() + q[1].numel()) for m, q in shards) == int(col.numel())      # every entry exactly once
+    partial = [_local_spmm(*q, Bn[r, vl:]) for r, (m, q) in enumerate(shards)]               # [vp, 8] per rank
+    outs = []
+    for r, (m, q) in enumerate(shards):
+        assert m[0].numel() == nl + 1 and int(m[1].max()) < vp + part.d_loc
+        o = _local_spmm(*m, torch.cat([words, Bn[r, vl:]]))
+        for s in range(world):                              # the all-to-all: slot s = rank s's partial rows of my words
+            o[:vl] += partial[s][r * vl:(r + 1) * vl]
+        outs.append(o)
+    assert rel_err(part.to_old(torch.cat(outs)), ref) < 1e-12
+
+
+def test_bipartite_rejects_document_document_edges():
+    g = make_graph(SHAPE, seed=1)
+    n, rowptr, col, val = _global_csr(g)
+    part = BipartitePartition(rowptr[1:] - rowptr[:-1], g.n_vocab - 5, 2)      # pretend 5 words are documents
+    with pytest.raises(NotImplementedError):
+        shard_bipartite(rowptr, col, val, part, 0)
+
+
+def _bip_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = make_graph(SHAPE, seed=2)
+        n, rowptr, col, val = _global_csr(g)
+        part = BipartitePartition(rowptr[1:] - rowptr[:-1], g.n_vocab, world)
+        nl, vl, vp, lo = part.n_loc, part.v_loc, part.v_pad, rank * part.n_loc
+        main, qq = shard_bipartite(rowptr, col, val, part, rank)
+        torch.manual_seed(0)
+        X = torch.randn(n, 6, dtype=torch.float64)
+        X_loc = part.to_new(X)[lo:lo + nl]
+        # the collective sequence of BipartiteTextGCNTrainer._propagate
+        OP = torch.zeros(vp + part.d_loc, 6, dtype=torch.float64)
+        dist.all_gather_into_tensor(OP[:vp], X_loc[:vl].contiguous())
+        OP[vp:] = X_loc[vl:]
+        Q = _local_spmm(*qq, OP[vp:]).contiguous()
+        SL = torch.zeros(world, vl, 6, dtype=torch.float64)
+        recv = list(SL.unbind(0))
+        for d in range(world):      # all_to_all_single on NCCL; gloo has no all-to-all, so one gather per destination
+            dist.gather(Q.view(world, vl, 6)[d].contiguous(), recv if rank == d else None, dst=d)
+        out = _local_spmm(*main, OP)
+        for s in range(world):
+            out[:vl] += recv[s]
+        full = torch.zeros(part.n_pad, 6, dtype=torch.float64)
+        dist.all_gather_into_tensor(full, out.contiguous())
+        if rank == 0:
+            q.put(rel_err(part.to_old(full), _local_spmm(rowptr, col, val, X)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_word_block_exchange_matches_global():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_bip_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res < 1e-12

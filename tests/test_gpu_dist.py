@@ -87,3 +87,49 @@ def test_renumbered_single_gpu_run_is_the_oracle_of_the_partitioned_run(cuda):
         assert par["max_rel_err_loss"] < 1e-5 and par["max_rel_err_W2"] < 1e-4 and par["max_rel_err_W1"] < 1e-4, par
     finally:
         torch.distributed.destroy_process_group()
+
+
+def test_word_block_trainer_single_rank(cuda):
+    """world = 1 exercises the whole word-block data path (split CSR pieces, partial word rows added in the SpMM
+    epilogue, restricted class-wide propagations, shared hidden rows, fused Adam): against the oracle's reference epoch
+    (dropout off), and -- dropout on, CUDA graph -- against the single-GPU trainer on the renumbered graph."""
+    from pytextgcn_b200.dist import parity_against_single_gpu
+    from pytextgcn_b200.dist_bipartite import BipartiteTextGCNTrainer
+    from pytextgcn_b200.synthetic import make_graph, GraphShape
+    shape = GraphShape("t", 700, 1555, 12000, 20, 6, 64)
+    g = make_graph(shape, seed=3)
+    n = int(g.x.shape[0])
+    torch.manual_seed(0)
+    ref = O.OracleGCN(n, shape.n_classes, n_hidden_gcn=shape.hidden, dropout=0.0)
+    with torch.no_grad():
+        for l in ref.layers:
+            l.bias.uniform_(-0.1, 0.1)
+    init = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    tr = BipartiteTextGCNTrainer(g, shape.n_classes, shape.hidden, 0.0, 0.01, True, 0, 1, cuda, seed=0, init_weights=init)
+    opt = torch.optim.Adam(ref.parameters(), lr=0.01, amsgrad=True)
+    for step in range(3):
+        out_ref = O.reference_epoch(ref, g, opt)
+        tr.train_step()
+        assert abs(tr.train_loss() - out_ref[0]) < 1e-5 * max(1, abs(out_ref[0]))
+        assert rel_err(tr.part.to_old(tr.g_W1), ref.layers[0].weight.grad) < 2e-5 * (step + 1)
+        assert rel_err(tr.g_W2, ref.layers[1].weight.grad) < 2e-5 * (step + 1)
+        assert rel_err(tr.g_b1, ref.layers[0].bias.grad) < 2e-5 * (step + 1)
+        tr.eval_step()
+        st = tr.epoch_stats()
+        assert abs(st["val_loss"] - out_ref[1]) < 1e-4 * max(1, abs(out_ref[1]))
+    for k, v in ref.state_dict().items():
+        assert rel_err(tr.gathered_parameters()[k], v) < 1e-3, k
+    del tr
+    if not torch.distributed.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29643")
+        torch.distributed.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        shape = GraphShape("t2", 500, 1433, 8000, 20, 6, 32, dropout=0.5, amsgrad=True, lr=0.02)
+        g = make_graph(shape, seed=6)
+        par = parity_against_single_gpu(g, shape, 0, 1, cuda, seed=2, epochs=6, partition="words", use_cuda_graph=True,
+                                        keep_w1_grad=False)
+        assert par["partition"] == "BipartitePartition" and par["cuda_graph"], par
+        assert par["max_rel_err_loss"] < 1e-4 and par["max_rel_err_W2"] < 1e-3 and par["max_rel_err_W1"] < 1e-3, par
+    finally:
+        torch.distributed.destroy_process_group()
