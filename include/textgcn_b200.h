@@ -141,6 +141,14 @@ typedef struct {
    * other ranks' documents to this rank's word rows): local row r < raw_rows adds raw_in[k * raw_stride + r * raw_ld + :]
    * for k = 0 .. n_raw - 1, in that order, before the dense-tile partials and the epilogue. */
   const float* raw_in; int64_t raw_ld; int64_t raw_stride; int32_t n_raw; int64_t raw_rows;
+  /* word-block exchange fused into the kernels (multi-GPU, see (6)):
+   * adam_mirror_rows > 0: only the first adam_mirror_rows local rows (the rank's words) are repeated to the multicast
+   *   mapping (0 = all rows);
+   * c_scatter_bases != NULL (device array of peer-mapped base pointers, fp32 C only): output row r is stored to
+   *   bases[r / c_scatter_rows] + (c_scatter_row0 + r % c_scatter_rows) * ldc instead of C + r * ldc -- the
+   *   all-to-all of the partial word rows happens in the epilogue's stores (plain peer stores over NVLink). */
+  int64_t adam_mirror_rows;
+  const uint64_t* c_scatter_bases; int64_t c_scatter_rows; int64_t c_scatter_row0;
 } tgcn_spmm_args;
 int tgcn_spmm(const tgcn_spmm_args* args, void* stream);
 
@@ -203,6 +211,7 @@ typedef struct {
   void* dZ1; int64_t lddz1; int32_t dz1_dtype;      /* out [n_rows, H] */
   void* dZ1_mirror_mc;                              /* multicast mapping of dZ1 (fp32) or NULL: see (6) */
   float* dW2; float* db_hidden; float* db_out;      /* out [H*C], [H], [C] */
+  int64_t dZ1_mirror_rows;                          /* > 0: only the first rows are repeated to the multicast mapping (0 = all) */
 } tgcn_dense_bwd_args;
 int tgcn_dense_bwd(const tgcn_dense_bwd_args* args, void* workspace, size_t workspace_bytes, void* stream);
 int tgcn_dense_bwd_workspace_bytes(int32_t H, int32_t C, size_t* bytes_out);
@@ -225,6 +234,7 @@ typedef struct {
   int32_t drop_mode; float drop_p; const uint8_t* keep_mask; int64_t ldmask;
   uint64_t philox_seed; uint64_t philox_offset; const int64_t* philox_offset_dev; int64_t philox_row_offset;
   float* Xd; int64_t ldxd;
+  int64_t mirror_rows;                              /* > 0: only the first rows are repeated to P_mirror_mc (0 = all) */
 } tgcn_project_args;
 int tgcn_project_ex(const tgcn_project_args* args, void* stream);
 /* out[c] = sum_r X[r, c] (deterministic two-stage sum): the bias gradient db1 = colsum(dZ1) in the propagate-first order */

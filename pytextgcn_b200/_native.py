@@ -39,6 +39,7 @@ class SpmmArgs(C.Structure):
         ("adam_eps", C.c_float), ("adam_param_mirror_mc", c_void),
         ("tc_part", c_void), ("tc_ld", C.c_int64), ("tc_rank", c_void), ("tc_slot_ptr", c_void),
         ("raw_in", c_void), ("raw_ld", C.c_int64), ("raw_stride", C.c_int64), ("n_raw", C.c_int32), ("raw_rows", C.c_int64),
+        ("adam_mirror_rows", C.c_int64), ("c_scatter_bases", c_void), ("c_scatter_rows", C.c_int64), ("c_scatter_row0", C.c_int64),
     ]
 
 
@@ -58,7 +59,7 @@ class ProjectArgs(C.Structure):
         ("P", c_void), ("ldp", C.c_int64), ("P_mirror_mc", c_void),
         ("drop_mode", C.c_int32), ("drop_p", C.c_float), ("keep_mask", c_void), ("ldmask", C.c_int64),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_offset_dev", c_void), ("philox_row_offset", C.c_int64),
-        ("Xd", c_void), ("ldxd", C.c_int64),
+        ("Xd", c_void), ("ldxd", C.c_int64), ("mirror_rows", C.c_int64),
     ]
 
 
@@ -76,7 +77,7 @@ class DenseBwdArgs(C.Structure):
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_offset_dev", c_void),
         ("dZ1", c_void), ("lddz1", C.c_int64), ("dz1_dtype", C.c_int32),
         ("dZ1_mirror_mc", c_void),
-        ("dW2", c_void), ("db_hidden", c_void), ("db_out", c_void),
+        ("dW2", c_void), ("db_hidden", c_void), ("db_out", c_void), ("dZ1_mirror_rows", C.c_int64),
     ]
 
 

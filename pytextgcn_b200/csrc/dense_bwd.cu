@@ -28,6 +28,7 @@ struct DenseBwdParams {
   uint64_t philox_seed, philox_offset; const int64_t* __restrict__ philox_offset_dev;
   void* dZ1; int64_t lddz1; int32_t dz1_dtype;
   float* dZ1_mirror;   // multicast mapping of dZ1 (fp32 only) or NULL
+  int64_t dZ1_mirror_rows;   // rows the mirror covers
   // workspace partials
   float* part_dW2;   // [n_cta_x][H*C]
   float* part_dbh;   // [n_cta_x][H]
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
         }
         if (p.dz1_dtype == TGCN_F32) {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dZ1) + row * p.lddz1 + 4 * hq) = make_float4(v[0], v[1], v[2], v[3]);
-          if (p.dZ1_mirror) multimem_st_v4(p.dZ1_mirror + row * p.lddz1 + 4 * hq, v[0], v[1], v[2], v[3]);
+          if (p.dZ1_mirror && row < p.dZ1_mirror_rows) multimem_st_v4(p.dZ1_mirror + row * p.lddz1 + 4 * hq, v[0], v[1], v[2], v[3]);
         } else {
           __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dZ1) + row * p.lddz1 + 4 * hq);
           o[0] = __floats2bfloat162_rn(v[0], v[1]);
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
           for (int i = 0; i < 4; ++i) dbh[k][i] += v[i];
           if (p.dz1_dtype == TGCN_F32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dZ1) + row * p.lddz1 + 4 * hq) = make_float4(v[0], v[1], v[2], v[3]);
-          if (p.dZ1_mirror) multimem_st_v4(p.dZ1_mirror + row * p.lddz1 + 4 * hq, v[0], v[1], v[2], v[3]);
+            if (p.dZ1_mirror && row < p.dZ1_mirror_rows) multimem_st_v4(p.dZ1_mirror + row * p.lddz1 + 4 * hq, v[0], v[1], v[2], v[3]);
           } else {
             __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dZ1) + row * p.lddz1 + 4 * hq);
             o[0] = __floats2bfloat162_rn(v[0], v[1]);
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(256) k_colsum_partial(const float* __restrict_
 struct ProjParams {
   const float* __restrict__ X; int64_t ldx; int64_t n_rows; int32_t K;
   const float* __restrict__ W; int32_t M; const float* __restrict__ bias;
-  float* P; int64_t ldp; float* mirror;
+  float* P; int64_t ldp; float* mirror; int64_t mirror_rows;
   int32_t drop_mode; float drop_p, drop_scale; const uint8_t* __restrict__ keep_mask; int64_t ldmask;
   uint64_t philox_seed, philox_offset; const int64_t* __restrict__ philox_offset_dev; int64_t philox_row_offset; int32_t philox_F;
   float* Xd; int64_t ldxd;
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(256) k_project_rows(const ProjParams p) {
             if (c + 3 < p.M) o.w += __ldg(p.bias + c + 3);
           }
           *reinterpret_cast<float4*>(p.P + row * p.ldp + c) = o;
-          if (p.mirror) multimem_st_v4(p.mirror + row * p.ldp + c, o.x, o.y, o.z, o.w);
+          if (p.mirror && row < p.mirror_rows) multimem_st_v4(p.mirror + row * p.ldp + c, o.x, o.y, o.z, o.w);
         }
       }
     }
@@ -558,6 +559,7 @@ extern "C" int tgcn_dense_bwd(const tgcn_dense_bwd_args* a, void* workspace, siz
   p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset; p.philox_offset_dev = a->philox_offset_dev;
   p.dZ1 = a->dZ1; p.lddz1 = a->lddz1; p.dz1_dtype = a->dz1_dtype;
   p.dZ1_mirror = (a->dz1_dtype == TGCN_F32) ? (float*)a->dZ1_mirror_mc : nullptr;
+  p.dZ1_mirror_rows = a->dZ1_mirror_rows > 0 ? a->dZ1_mirror_rows : INT64_MAX;
   p.part_dW2 = (float*)((char*)workspace + L.off_dw);
   p.part_dbh = (float*)((char*)workspace + L.off_dbh);
   p.part_dbo = (float*)((char*)workspace + L.off_dbo);
@@ -632,6 +634,7 @@ extern "C" int tgcn_project_ex(const tgcn_project_args* a, void* stream_) {
   const bool rows_ok = a->x_dtype == TGCN_F32 && a->ldx % 4 == 0 && a->ldx >= Kp4 && a->ldp % 4 == 0 && (((uintptr_t)a->X | (uintptr_t)a->P) & 15) == 0 &&
                        (a->P_mirror_mc == nullptr || ((uintptr_t)a->P_mirror_mc & 15) == 0);
   if (!rows_ok || (size_t)((a->K + 31) / 32 * 32) * 32 * 4 > 150 * 1024) {
+    TGCN_CHECK_ARG(a->mirror_rows <= 0 || a->mirror_rows >= a->n_rows, "project: mirror_rows needs fp32 X with 16-byte aligned rows");
     TGCN_CHECK_ARG(!drop && a->Xd == nullptr, "project: the fused dropout needs fp32 X with 16-byte aligned rows (ldx %% 4 == 0, ldx >= pad4(K))");
     return tgcn_project(a->X, a->ldx, a->x_dtype, a->n_rows, a->K, a->W, a->M, a->bias, a->P, a->ldp, a->P_mirror_mc, stream_);
   }
@@ -640,7 +643,7 @@ extern "C" int tgcn_project_ex(const tgcn_project_args* a, void* stream_) {
   TGCN_CHECK_ARG(a->Xd == nullptr || (a->ldxd % 4 == 0 && a->ldxd >= Kp4 && ((uintptr_t)a->Xd & 15) == 0), "project: bad Xd");
   ProjParams p;
   p.X = (const float*)a->X; p.ldx = a->ldx; p.n_rows = a->n_rows; p.K = a->K; p.W = a->W; p.M = a->M; p.bias = a->bias;
-  p.P = a->P; p.ldp = a->ldp; p.mirror = (float*)a->P_mirror_mc;
+  p.P = a->P; p.ldp = a->ldp; p.mirror = (float*)a->P_mirror_mc; p.mirror_rows = a->mirror_rows > 0 ? a->mirror_rows : INT64_MAX;
   p.drop_mode = drop ? a->drop_mode : TGCN_DROP_NONE; p.drop_p = a->drop_p; p.drop_scale = drop ? 1.0f / (1.0f - a->drop_p) : 1.0f;
   p.keep_mask = a->keep_mask; p.ldmask = a->ldmask; p.philox_seed = a->philox_seed; p.philox_offset = a->philox_offset;
   p.philox_offset_dev = a->philox_offset_dev; p.philox_row_offset = a->philox_row_offset; p.philox_F = a->K;

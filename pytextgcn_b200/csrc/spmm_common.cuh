@@ -28,6 +28,9 @@ struct SpmmParams {
   const float* __restrict__ tc_part; int64_t tc_ld; const int32_t* __restrict__ tc_rank; const int32_t* __restrict__ tc_slot_ptr;
   // partial rows of other ranks (bipartite exchange), added in slot order to local rows < raw_rows before the epilogue
   const float* __restrict__ raw_in; int64_t raw_ld, raw_stride, raw_rows; int32_t n_raw;
+  // word-block exchange: rows the Adam mirror covers; all-to-all of the output rows through peer-mapped bases
+  int64_t ad_mirror_rows;
+  const uint64_t* __restrict__ c_scatter; int32_t c_scatter_rows; int64_t c_scatter_row0;
 };
 
 // ---- loads of 16 bytes of the dense operand -> 4 (fp32) or 8 (bf16) floats ----
@@ -94,6 +97,10 @@ __device__ __forceinline__ void row_epilogue(const SpmmParams& p, int64_t row, i
       if (p.C) {
         if (p.c_dtype == TGCN_F32) {
           float* c = reinterpret_cast<float*>(p.C) + lrow * p.ldc + c0;
+          if (p.c_scatter) {     // this row belongs to another rank's slot buffer (peer store over NVLink)
+            const int d = (int)lrow / p.c_scatter_rows;
+            c = reinterpret_cast<float*>(__ldg(p.c_scatter + d)) + (p.c_scatter_row0 + ((int)lrow - d * p.c_scatter_rows)) * p.ldc + c0;
+          }
 #pragma unroll
           for (int q = 0; q < E / 4; ++q)
             *reinterpret_cast<float4*>(c + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
@@ -132,7 +139,7 @@ __device__ __forceinline__ void row_epilogue(const SpmmParams& p, int64_t row, i
           *reinterpret_cast<float4*>(p.ad_m + off + 4 * q) = M4;
           *reinterpret_cast<float4*>(p.ad_v + off + 4 * q) = V4;
           if (p.ad_x) *reinterpret_cast<float4*>(p.ad_x + off + 4 * q) = X4;
-          if (p.ad_mirror) multimem_st_v4(p.ad_mirror + off + 4 * q, P4.x, P4.y, P4.z, P4.w);
+          if (p.ad_mirror && lrow < p.ad_mirror_rows) multimem_st_v4(p.ad_mirror + off + 4 * q, P4.x, P4.y, P4.z, P4.w);
         }
       }
     } else {
@@ -214,6 +221,12 @@ static inline int fill_spmm_params(const tgcn_spmm_args* a, SpmmParams* p) {
   p->ad_ld = a->adam_ld; p->ad_hyp = a->adam_hyper_dev; p->ad_b1 = a->adam_beta1; p->ad_b2 = a->adam_beta2; p->ad_eps = a->adam_eps;
   p->ad_mirror = (float*)a->adam_param_mirror_mc;
   p->tc_part = a->tc_part; p->tc_ld = a->tc_ld; p->tc_rank = a->tc_rank; p->tc_slot_ptr = a->tc_slot_ptr;
+  p->ad_mirror_rows = a->adam_mirror_rows > 0 ? a->adam_mirror_rows : INT64_MAX;
+  p->c_scatter = a->c_scatter_bases; p->c_scatter_rows = (int32_t)a->c_scatter_rows; p->c_scatter_row0 = a->c_scatter_row0;
+  if (p->c_scatter) {
+    TGCN_CHECK_ARG(a->C && a->c_dtype == TGCN_F32 && a->c_scatter_rows > 0 && a->c_scatter_rows < INT32_MAX && a->c_scatter_row0 >= 0,
+                   "spmm: c_scatter_bases needs an fp32 C (for ldc), c_scatter_rows > 0 and c_scatter_row0 >= 0");
+  }
   p->raw_in = a->n_raw > 0 ? a->raw_in : nullptr; p->raw_ld = a->raw_ld; p->raw_stride = a->raw_stride; p->raw_rows = a->raw_rows; p->n_raw = a->n_raw;
   if (p->raw_in) {
     TGCN_CHECK_ARG(p->raw_ld % 4 == 0 && p->raw_ld >= a->F && p->raw_stride % 4 == 0 && ((uintptr_t)p->raw_in & 15) == 0 && a->b_dtype == TGCN_F32,

@@ -895,7 +895,9 @@ def run_distributed_bench(args, rank: int, local_rank: int, world: int, dev: tor
         g_cfg = make_graph(sh_last, seed=args.seed, hierarchy_classes=hier_last)
         cfg = workload_config(args.workload, specs, g_cfg)
         cfg["parallelism"] = (f"word-block partition x{world} (words and documents dealt in snake order; exchange = all-gather of the "
-                              "word block + all-to-all of the partial word rows, NCCL)" if main["partition"][0] == "BipartitePartition" else
+                              "word block + all-to-all of the partial word rows: " +
+                              ("multimem stores in the producers / peer stores in the Q SpMM epilogue + device barrier)"
+                               if main["exchange"].startswith("peer") else "NCCL)") if main["partition"][0] == "BipartitePartition" else
                               f"1D row partition x{world} (snake order by nnz); exchange between layers: " +
                               (("multimem stores fused into the producer kernels + device barrier" if main["fused_stores"] else
                                 "peer-store push kernel into symmetric buffers + device barrier") if main["exchange"] == "peer"

@@ -19,8 +19,11 @@ that is 1/3 of the row partition's traffic and the document rows need nothing re
 The class-wide propagations need even less: logits are read on document rows only (no partial word rows), and the
 loss gradient is zero on word rows (no all-gather, only the partial word rows of the training documents).
 
-The exchange uses the NCCL collectives of torch.distributed (all_gather_into_tensor, all_to_all_single), captured in
-the epoch's CUDA graph with the kernels; the all-gather of the word block runs concurrently with the Q SpMM.
+With symmetric memory (NVLink peer mappings + NVSwitch multicast) the exchange is fused into the kernels: producers repeat
+their word rows with multimem.st into every rank's operand buffer (all-gather), the Q SpMM's epilogue stores every partial
+word row straight into its owner's slot buffer (all-to-all), one device barrier per propagation.  Fallback: the NCCL
+collectives of torch.distributed (all_gather_into_tensor, all_to_all_single; the all-gather runs concurrently with the Q
+SpMM).  Either way the whole epoch is one CUDA graph.
 Parity: dist.parity_against_single_gpu(..., partition="words") -- the single-GPU trainer on the
 renumbered graph; only the order of the partial sums differs (fp32 rounding).
 """
@@ -108,7 +111,8 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
                  rank: int, world: int, dev: torch.device, seed: int = 0, betas=(0.9, 0.999), eps: float = 1e-8,
                  graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None,
                  use_cuda_graph: bool = False, keep_w1_grad: bool = True, share_h1: bool = True,
-                 tensor_cores: Optional[bool] = None, tc_min_density: float = 0.05, overlap: bool = True, **_unused):
+                 tensor_cores: Optional[bool] = None, tc_min_density: float = 0.05, overlap: bool = True,
+                 exchange: str = "peer", fused_stores: bool = True, **_unused):
         import torch.distributed as dist
         from . import ops
         from .graph import upload_graph
@@ -153,12 +157,51 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
             if tc is not None and (tensor_cores or tc.nnz_dense >= 0.15 * self.shard.nnz):
                 self.tc = tc
         f32 = dict(dtype=torch.float32, device=dev)
-        self.exchange, self.exchange_error, self.px, self.fused_stores = "nccl word-block", None, None, False
         self.overlap = bool(overlap) and world > 1
-        # operand buffers [all words ; own documents], partial word rows (mine for everyone / everyone's for mine)
-        self.OP = {F: torch.zeros((vp + dl, F), **f32) for F in {H, Cp}}
-        self.Q = {F: torch.zeros((vp, F), **f32) for F in {H, Cp}}
-        self.SL = {F: (torch.zeros((world, vl, F), **f32) if world > 1 else self.Q[F].view(1, vp, F)) for F in {H, Cp}}
+        n_small = H + H * n_classes + n_classes
+        self.n_small, self.n_small_pad = n_small, (n_small + 3) // 4 * 4
+        # Exchanged buffers.  OP*: operands [all words (v_pad rows, rank-major) ; own documents]: W1, dZ1, P of the train
+        # and of the eval forward (dZ2 reuses the train buffer's document tail: its word rows are zero and never read).
+        # SL*: partial word rows, slot s = rank s's contribution to MY words (two hidden-wide ones: the forward and the
+        # backward propagation alternate, so a peer never overwrites the slots a slower rank is still adding).
+        # With symmetric memory (NVLink peer mappings + NVSwitch multicast) the exchange is fused into the kernels: the
+        # producers of an operand repeat their WORD rows with multimem.st into every rank's OP buffer, the Q SpMM stores
+        # each partial word row straight into its owner's slot (peer stores), and one device barrier separates
+        # producers from consumers.  Otherwise: NCCL all_gather_into_tensor / all_to_all_single.
+        # The peer / NCCL decision is collective (see DistTextGCNTrainer).
+        self.exchange, self.exchange_error, self.px = "nccl word-block", None, None
+        xshapes = {"OPW": (vp + dl, H), "OPD": (vp + dl, H), "OPCt": (vp + dl, Cp), "OPCe": (vp + dl, Cp),
+                   "SLf": (world, vl, H), "SLb": (world, vl, H), "SLc": (world, vl, Cp), "small": (world, self.n_small_pad)}
+        xb: Dict[str, torch.Tensor] = {}
+        if world > 1 and exchange == "peer":
+            from .dist import PeerExchange
+            ok = 1
+            try:
+                self.px = PeerExchange(dist.group.WORLD, rank, world, dev)
+                for name, shp in xshapes.items():
+                    xb[name] = self.px.alloc(name, shp)
+            except Exception as e:
+                self.exchange_error, ok = repr(e), 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                self.exchange = "peer word-block"
+            else:
+                self.px, xb = None, {}
+                self.exchange_error = self.exchange_error or "symmetric allocation failed on another rank"
+        for name, shp in xshapes.items():
+            if name not in xb:
+                xb[name] = torch.zeros(shp, **f32)
+        self.X = xb
+        self.bases = {}
+        if self.px is not None:
+            self.bases = {k: torch.tensor([int(q) for q in self.px.handles[k].buffer_ptrs], dtype=torch.int64, device=dev)
+                          for k in ("SLf", "SLb", "SLc")}
+        self.fused_stores = bool(fused_stores and self.px is not None and
+                                 all(self.px.multicast.get(k, 0) for k in ("OPW", "OPD", "OPCt", "OPCe")))
+        self.Q = {} if self.px is not None else {F: torch.zeros((vp, F), **f32) for F in {H, Cp}}   # NCCL mode: a2a source
+        self._pending_reads = set()
+        self._w1_words_ready = False
         # parameters: same init on every rank (same draws as DistTextGCNTrainer), W1 rows in the new order
         gen = torch.Generator().manual_seed(seed)
         if init_weights is None:
@@ -173,9 +216,8 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
         self.W1_loc = part.to_new(W1[:n])[lo:lo + nl].to(dev).contiguous()
         self.W1_cat = None
         self.b1, self.W2, self.b2 = b1.to(dev), W2.to(dev).contiguous(), b2.to(dev)
-        n_small = H + H * n_classes + n_classes
-        self.n_small, self.n_small_pad = n_small, (n_small + 3) // 4 * 4
-        self.small_local = torch.zeros(self.n_small_pad, **f32)
+        self.small_slots = self.X["small"]                      # slot r = rank r's partial sums (peer mode)
+        self.small_local = self.small_slots[rank]
         self.small = torch.zeros(self.n_small_pad, **f32)
 
         def views(buf):
@@ -239,35 +281,70 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
             dist.barrier()
 
     # ---- one propagation over this rank's rows ----
-    def _propagate(self, X_loc: torch.Tensor, F: int, graph: GraphCSR, plan, qgraph: Optional[GraphCSR], qplan,
-                   gather_words: bool, tc=None, **kw):
-        """epi(rows of A_hat X owned by this rank).  X_loc = [own words ; own documents] rows of X."""
-        ops, part = self.ops, self.part
+    def _mirror_of(self, op: str):
+        """(multicast address of this rank's word rows inside operand buffer `op`, number of word rows) or (None, 0)."""
+        if not self.fused_stores:
+            return None, 0
+        OP = self.X[op]
+        return self.px.multicast[op] + self.rank * self.part.v_loc * OP.stride(0) * 4, self.part.v_loc
+
+    def _propagate(self, X_loc: torch.Tensor, F: int, op: str, sl: Optional[str], graph: GraphCSR, plan,
+                   qgraph: Optional[GraphCSR], qplan, gather_words: bool, words_mirrored: bool = False, tc=None, **kw):
+        """epi(rows of A_hat X owned by this rank).  X_loc = [own words ; own documents] rows of X; `op` names the
+        operand buffer, `sl` the slot buffer of the partial word rows (None: word rows not needed).
+        words_mirrored: the kernel that produced X_loc already stored its word rows into every rank's `op`."""
+        ops, part, r = self.ops, self.part, self.rank
         vl, vp = part.v_loc, part.v_pad
-        OP = self.OP[F]
+        OP = self.X[op]
+        peer = self.px is not None
         work = None
-        if gather_words:
-            if self.world > 1:
+        if gather_words and not words_mirrored:
+            if peer:
+                from . import _native
+                self._before_write(op)
+                mine = OP[r * vl:(r + 1) * vl]
+                mine.copy_(X_loc[:vl])
+                with torch.cuda.device(self.dev):
+                    _native.check(_native.load().tgcn_peer_push(
+                        mine.data_ptr(), self.px.peer_arrays[op], self.world, r, mine.numel() * 4,
+                        mine.data_ptr() - OP.data_ptr(), self.px.multicast[op] or None, torch.cuda.current_stream().cuda_stream))
+            elif self.world > 1:
                 work = self.dist.all_gather_into_tensor(OP[:vp], X_loc[:vl], async_op=self.overlap)
             else:
                 OP[:vl].copy_(X_loc[:vl])
         OP[vp:].copy_(X_loc[vl:])
         raw = None
         if qgraph is not None:
-            # this rank's contribution to EVERY word row, from its own documents; runs while the word block is gathered
-            ops.spmm(qgraph, OP[vp:], F=F, plan=qplan, out=self.Q[F])
-            if work is not None and self.overlap:
-                work.wait()
-                work = None
-            if self.world > 1:
-                self.dist.all_to_all_single(self.SL[F].view(vp, F), self.Q[F])
-            raw = self.SL[F]
+            # this rank's contribution to EVERY word row, from its own documents
+            if peer:
+                self._before_write(sl)
+                ops.spmm(qgraph, OP[vp:], F=F, plan=qplan, out=self.X[sl].view(vp, F),
+                         scatter=dict(bases=self.bases[sl], rows=vl, row0=r * vl))       # all-to-all in the epilogue's stores
+                raw = self.X[sl]
+            else:
+                ops.spmm(qgraph, OP[vp:], F=F, plan=qplan, out=self.Q[F])               # runs while the word block is gathered
+                if work is not None and self.overlap:
+                    work.wait()
+                    work = None
+                if self.world > 1:
+                    self.dist.all_to_all_single(self.X[sl].view(vp, F), self.Q[F])
+                    raw = self.X[sl]
+                else:
+                    raw = self.Q[F].view(1, vp, F)
         if work is not None and self.overlap:
             work.wait()
+        if peer and (gather_words or qgraph is not None):
+            self._barrier()                   # word rows and slots of every rank are in place
         self._mark("exchange_F%d" % F)
         if tc is not None:
-            return ops.spmm_hybrid(tc, OP, F=F, plan=tc.remainder.plan(), raw_slots=raw, **kw)
-        return ops.spmm(graph, OP, F=F, plan=plan, raw_slots=raw, **kw)
+            out = ops.spmm_hybrid(tc, OP, F=F, plan=tc.remainder.plan(), raw_slots=raw, **kw)
+        else:
+            out = ops.spmm(graph, OP, F=F, plan=plan, raw_slots=raw, **kw)
+        if gather_words:
+            self._note_read(op)
+        if qgraph is not None and sl is not None:
+            self._note_read(sl)
+        return out
 
     def _gather_w1(self) -> None:      # nothing is kept gathered between steps
         return
@@ -283,15 +360,20 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
             h, fused_drop = (self.H1, True) if drop else (self.H1d, False)
         else:
             h = self.H1d if training else self.H1
-            self._propagate(self.W1_loc, self.H, self.shard, self.plan, self.qshard, self.plan_q, True, tc=self.tc,
-                            out=h, bias=self.b1, **dkw)
+            self._propagate(self.W1_loc, self.H, "OPW", "SLf", self.shard, self.plan, self.qshard, self.plan_q, True,
+                            words_mirrored=self._w1_words_ready, tc=self.tc, out=h, bias=self.b1, **dkw)
             self._mark("spmm_wide_fwd")
+        opc = "OPCt" if training else "OPCe"
+        mir, mrows = self._mirror_of(opc)
+        if mir is not None:
+            self._before_write(opc)
         if fused_drop:
-            ops.project(h, self.W2, K=self.H, out=self.P_loc, dropped_out=self.H1d, **dkw)
+            ops.project(h, self.W2, K=self.H, out=self.P_loc, dropped_out=self.H1d, mirror=mir, mirror_rows=mrows, **dkw)
         else:
-            ops.project(h, self.W2, K=self.H, out=self.P_loc)
+            ops.project(h, self.W2, K=self.H, out=self.P_loc, mirror=mir, mirror_rows=mrows)
         self._mark("project")
-        self._propagate(self.P_loc, self.Cp, self.shard, self.plan_z2, None, None, True, out=self.Z2, bias=self.b2)
+        self._propagate(self.P_loc, self.Cp, opc, None, self.shard, self.plan_z2, None, None, True,
+                        words_mirrored=mir is not None, out=self.Z2, bias=self.b2)
         self._mark("spmm_narrow_fwd")
 
     def train_step(self) -> None:
@@ -300,26 +382,36 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
         ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2_loc,
                        loss_out=self.loss_buf, workspace=self._nll_ws, partial=self.loss_part)
         self._mark("masked_nll")
-        self._propagate(self.dZ2_loc, self.Cp, self.shard_g2, self.plan_g2, self.qshard_g2, self.plan_q_g2, False, out=self.G2)
+        self._propagate(self.dZ2_loc, self.Cp, "OPCt", "SLc", self.shard_g2, self.plan_g2, self.qshard_g2, self.plan_q_g2,
+                        False, out=self.G2)
         self._mark("spmm_narrow_bwd")
         drop = self.p > 0
+        mir, mrows = self._mirror_of("OPD")
+        if mir is not None:
+            self._before_write("OPD")
+        self._before_write("small")
         r = ops.dense_bwd(self.G2, self.H1d, self.W2, self.dZ2_loc, H=self.H, n_classes=self.C,
                           drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
                           philox_offset_dev=self.step_dev if drop else None, row_offset=self.rank * self.part.n_loc,
-                          dZ1=self.dZ1_loc, workspace=self._db_ws, dW2=self.l_W2, db_hidden=self.l_b1, db_out=self.l_b2)
+                          dZ1=self.dZ1_loc, workspace=self._db_ws, dW2=self.l_W2, db_hidden=self.l_b1, db_out=self.l_b2,
+                          dZ1_mirror=mir, dZ1_mirror_rows=mrows)
         self._db_ws = r["workspace"]
         self._mark("dense_bwd")
-        self.small.copy_(self.small_local)
-        if self.world > 1:
-            self.dist.all_reduce(self.small)
+        self._all_reduce_small()
         self._mark("allreduce_small_grads")
         kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad, step_dev=self.step_dev)
-        # dW1 rows of this rank never leave registers: Adam on W1[own rows] runs in the SpMM epilogue
+        # dW1 rows of this rank never leave registers: Adam on W1[own rows] runs in the SpMM epilogue, and the updated
+        # word rows go straight into every rank's W1 operand buffer (multimem.st) for the next forward
         ops.adam_prepare(self.step_dev, self.adam_hyper, self.lr, self.betas[0], self.betas[1])
-        self._propagate(self.dZ1_loc, self.H, self.shard, self.plan, self.qshard, self.plan_q, True, tc=self.tc,
-                        out=self.g_W1, want_out=self.keep_w1_grad,
+        wmir, wrows = self._mirror_of("OPW")
+        if wmir is not None:
+            self._before_write("OPW")
+        self._propagate(self.dZ1_loc, self.H, "OPD", "SLb", self.shard, self.plan, self.qshard, self.plan_q, True,
+                        words_mirrored=mir is not None, tc=self.tc, out=self.g_W1, want_out=self.keep_w1_grad,
                         adam=dict(param=self.W1_loc, exp_avg=self.st[0][0], exp_avg_sq=self.st[0][1], max_exp_avg_sq=self.st[0][2],
-                                  hyper=self.adam_hyper, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, mirror=None))
+                                  hyper=self.adam_hyper, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                                  mirror=wmir, mirror_rows=wrows))
+        self._w1_words_ready = wmir is not None
         self._mark("spmm_wide_bwd")
         ops.adam_step_small([self.b1, self.W2, self.b2], [self.g_b1, self.g_W2, self.g_b2], [s_[0] for s_ in self.st[1:]],
                             [s_[1] for s_ in self.st[1:]], [s_[2] for s_ in self.st[1:]], **kw)

@@ -57,7 +57,7 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
          philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0,
          W_proj: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
          want_out: bool = True, adam: Optional[dict] = None, tc=None,
-         raw_slots: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+         raw_slots: Optional[torch.Tensor] = None, scatter: Optional[dict] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """C = epi(A_hat[rows of plan] @ B[:, :F]) (+ P = C @ W_proj).  See tgcn_spmm.
     tc: a TcPlan whose dense-tile partial rows (already computed by tgcn_spmm_tc for this B, see spmm_hybrid) are
     added to every row before the epilogue; `graph` must then be the plan's remainder.
@@ -97,6 +97,7 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
         a.adam_ld, a.adam_hyper_dev = prm.stride(0), adam["hyper"].data_ptr()
         a.adam_beta1, a.adam_beta2, a.adam_eps = adam.get("beta1", 0.9), adam.get("beta2", 0.999), adam.get("eps", 1e-8)
         a.adam_param_mirror_mc = adam.get("mirror")
+        a.adam_mirror_rows = int(adam.get("mirror_rows") or 0)
     if plan.n_split_rows:
         a.slot_owner, a.split_counters = _native.ptr(plan.slot_owner), _native.ptr(plan.counters)
     a.B, a.ldb, a.b_dtype = B.data_ptr(), B.stride(0), _dt(B)
@@ -129,6 +130,10 @@ def spmm(graph: GraphCSR, B: torch.Tensor, *, F: Optional[int] = None, out: Opti
         if P is None:
             P = torch.zeros((n_out, pad4(n_proj)), dtype=torch.float32, device=B.device)
         a.W_proj, a.n_proj, a.P, a.ldp = W_proj.data_ptr(), n_proj, P.data_ptr(), P.stride(0)
+    if scatter is not None:
+        # dict(bases=int64 device tensor of peer-mapped base pointers, rows=rows per destination, row0=row offset there):
+        # output row r goes to bases[r // rows] + (row0 + r % rows) * ldc (see tgcn_spmm_args.c_scatter_bases)
+        a.c_scatter_bases, a.c_scatter_rows, a.c_scatter_row0 = scatter["bases"].data_ptr(), int(scatter["rows"]), int(scatter["row0"])
     if raw_slots is not None:
         # [n_slots, rows, >= F] fp32: partial rows added (slot order) to the first `rows` local rows before the epilogue
         if raw_slots.dtype != torch.float32 or raw_slots.dim() != 3 or raw_slots.stride(2) != 1 or raw_slots.shape[2] < F:
@@ -213,7 +218,7 @@ def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Option
               philox_offset_dev: Optional[torch.Tensor] = None, row_offset: int = 0, dZ1: Optional[torch.Tensor] = None, dz1_dtype: torch.dtype = torch.float32,
               want_dz1: bool = True, workspace: Optional[torch.Tensor] = None,
               dW2: Optional[torch.Tensor] = None, db_hidden: Optional[torch.Tensor] = None,
-              db_out: Optional[torch.Tensor] = None, dZ1_mirror: Optional[int] = None):
+              db_out: Optional[torch.Tensor] = None, dZ1_mirror: Optional[int] = None, dZ1_mirror_rows: int = 0):
     """dW2 = H1d^T G2, db_out = colsum(dZ2), dZ1 = (G2 W2^T) * dropout' * act', db_hidden = colsum(dZ1)."""
     _need_cuda(G2, H1d, W2, dZ2, keep_mask, dZ1)
     lib = _native.load()
@@ -239,6 +244,7 @@ def dense_bwd(G2: torch.Tensor, H1d: torch.Tensor, W2: torch.Tensor, dZ2: Option
             dZ1 = torch.zeros((n, width), dtype=dz1_dtype, device=dev)
         a.dZ1, a.lddz1, a.dz1_dtype = dZ1.data_ptr(), dZ1.stride(0), _dt(dZ1)
         a.dZ1_mirror_mc = dZ1_mirror
+        a.dZ1_mirror_rows = int(dZ1_mirror_rows)
     if dW2 is None:
         dW2 = torch.empty((H, n_classes), dtype=torch.float32, device=dev)
     if db_hidden is None and want_dz1:
@@ -259,7 +265,7 @@ def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Opti
             mirror: Optional[int] = None, bias: Optional[torch.Tensor] = None, drop_mode: int = DROP_NONE, drop_p: float = 0.0,
             keep_mask: Optional[torch.Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,
             philox_offset_dev: Optional[torch.Tensor] = None, row_id_offset: int = 0,
-            dropped_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            dropped_out: Optional[torch.Tensor] = None, mirror_rows: int = 0) -> torch.Tensor:
     """P = dropout(X[:, :K]) @ W (+ bias) (thin projection), P padded to a multiple of 4 columns.  With a dropout mode the
     keep decision of the SpMM epilogue is applied to X on load and dropout(X) is written to `dropped_out` (tgcn_project_ex)."""
     _need_cuda(X, W, out, bias, keep_mask, philox_offset_dev, dropped_out)
@@ -274,7 +280,7 @@ def project(X: torch.Tensor, W: torch.Tensor, K: Optional[int] = None, out: Opti
     a = _native.ProjectArgs()
     a.X, a.ldx, a.x_dtype, a.n_rows, a.K = X.data_ptr(), X.stride(0), _dt(X), n, K
     a.W, a.M, a.bias = W.data_ptr(), M, _native.ptr(bias)
-    a.P, a.ldp, a.P_mirror_mc = out.data_ptr(), out.stride(0), mirror
+    a.P, a.ldp, a.P_mirror_mc, a.mirror_rows = out.data_ptr(), out.stride(0), mirror, int(mirror_rows)
     a.drop_mode, a.drop_p = drop_mode, float(drop_p)
     if keep_mask is not None:
         if keep_mask.dtype not in (torch.uint8, torch.bool) or keep_mask.stride(1) != 1:

@@ -50,6 +50,12 @@ def main():
         print("DIST_WORKER word-block parity", par, flush=True)
         assert par["partition"] == "BipartitePartition" and par["cuda_graph"], par
         assert par["max_rel_err_loss"] < 1e-4 and par["max_rel_err_W2"] < 1e-3 and par["max_rel_err_W1"] < 1e-3, par
+    par = parity_against_single_gpu(g3, shape3, rank, world, dev, seed=4, epochs=6, partition="words", use_cuda_graph=True,
+                                    keep_w1_grad=False, exchange="nccl")
+    if rank == 0:
+        print("DIST_WORKER word-block (NCCL collectives) parity", par, flush=True)
+        assert par["exchange"].startswith("nccl") and par["cuda_graph"], par
+        assert par["max_rel_err_loss"] < 1e-4 and par["max_rel_err_W2"] < 1e-3 and par["max_rel_err_W1"] < 1e-3, par
     # ... and with the hybrid (tensor-core tiles + gathered remainder) hidden-wide propagation on the shards
     par = parity_against_single_gpu(g3, shape3, rank, world, dev, seed=4, epochs=6, partition="words", use_cuda_graph=True,
                                     keep_w1_grad=False, tensor_cores=True, tc_min_density=0.01)
