@@ -552,7 +552,7 @@ def run_own_arm(args):
                 "traffic": prof.get("dram_bytes_per_launch"),
                 "traffic_source": prof.get("source", None),
                 "kernel": ("hidden-wide propagation A_hat (X W1) + b1, F=%d, as the trainer runs it: " % F) +
-                          ("hybrid = k_tc_pack + k_tc_mma (dense 128x32 blocks of A_hat on tcgen05, 3xTF32, %.0f %% of the non-zeros) + "
+                          ("hybrid = k_tc_pack + k_tc_mma (dense 128x16 blocks of A_hat on tcgen05, 3xTF32, %.0f %% of the non-zeros) + "
                            "k_spmm<float,32,2,*> (gathered remainder + epilogue)" % (100.0 * tr.tc.nnz_dense / graph.nnz) if tr.tc is not None
                            else "k_spmm<float,32,2,*> (gather kernel)") +
                           "; %d such propagations per epoch (eval forward -- shared with the next train forward -- and the backward "

@@ -44,7 +44,7 @@ WANT = {
 
 def main():
     rep = sys.argv[1]
-    pat = sys.argv[2] if len(sys.argv) > 2 else ""
+    pat = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else ""
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units, body = rows[0], rows[1], rows[2:]
