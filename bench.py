@@ -550,7 +550,8 @@ def run_own_arm(args):
     wide_per_epoch = 2 if tr.share_h1 else 3
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": prof.get("dram_bytes_per_launch"),
-                "traffic_source": prof.get("source", None),
+                "traffic_source": ("profiles/r02_ncu_summary_spmm.json: dram__bytes_read.sum + dram__bytes_write.sum of k_tc_pack + k_tc_mma + "
+                                   "k_spmm (one propagation), ncu --set full of " + str(prof.get("source"))) if prof else None,
                 "kernel": ("hidden-wide propagation A_hat (X W1) + b1, F=%d, as the trainer runs it: " % F) +
                           ("hybrid = k_tc_pack + k_tc_mma (dense 128x16 blocks of A_hat on tcgen05, 3xTF32, %.0f %% of the non-zeros) + "
                            "k_spmm<float,32,2,*> (gathered remainder + epilogue)" % (100.0 * tr.tc.nnz_dense / graph.nnz) if tr.tc is not None

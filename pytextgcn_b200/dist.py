@@ -210,8 +210,16 @@ class DistTextGCNTrainer:
         n_small = H + H * n_classes + n_classes + self.c_prev * H            # packed grads of b1, W2, b2 (+ the [I|F] tail of W1)
         self.n_small = n_small
         self.n_small_pad = (n_small + 3) // 4 * 4
-        xshapes = {"W1": (npad, H), "small": (world, self.n_small_pad), "Pt": (npad, Cp), "Pe": (npad, Cp),
-                   "dZ2": (npad, Cp), "dZ1": (npad, H)}
+        # Propagate-first order of layer 2 when there are more classes than hidden units (perlevel_dbpedia.py: 70 / 219
+        # classes, hidden 32; see TextGCNTrainer.propagate_first): Z2 = (A_hat H1d) W2 + b2, dH1d = A_hat (dZ2 W2^T),
+        # dW2 = (A_hat H1d)^T dZ2 -- every exchanged operand is then hidden-wide (N x 32 instead of N x 220).
+        self.propagate_first = self.Cp > H
+        if self.propagate_first:
+            xshapes = {"W1": (npad, H), "small": (world, self.n_small_pad), "Ht": (npad, H), "He": (npad, H),
+                       "T": (npad, H), "dZ1": (npad, H)}
+        else:
+            xshapes = {"W1": (npad, H), "small": (world, self.n_small_pad), "Pt": (npad, Cp), "Pe": (npad, Cp),
+                       "dZ2": (npad, Cp), "dZ1": (npad, H)}
         xbufs: Dict[str, torch.Tensor] = {}
         if world > 1 and exchange == "peer":
             ok = 1
@@ -275,20 +283,33 @@ class DistTextGCNTrainer:
         self.adam_hyper = torch.zeros(2, dtype=torch.float32, device=dev)
         self.fuse_adam, self.keep_w1_grad = bool(fuse_adam) and not self.hier, bool(keep_w1_grad) or self.hier
         # activations
-        self.H1d = torch.empty((nl, H), **f32)
         # pre-dropout hidden rows of the last eval forward, reused by the next train step (same W1/b1,
         # flat_amazon.py:100-110): one hidden-wide SpMM less per epoch and per rank, bit-identical (trainer.py)
         self.share_h1 = bool(share_h1)
-        self.H1 = torch.empty((nl, H), **f32) if (self.share_h1 and dropout > 0) else self.H1d
         self._h1_valid = False
-        self.Pt_full = xbuf("Pt", (npad, Cp))        # projected rows, train forward
-        self.Pt_loc = self.Pt_full[lo:lo + nl]
-        self.Pe_full = xbuf("Pe", (npad, Cp))        # projected rows, eval forward (double buffer)
-        self.Pe_loc = self.Pe_full[lo:lo + nl]
         self.Z2 = torch.zeros((nl, Cp), **f32)
-        self.dZ2_full = xbuf("dZ2", (npad, Cp))
-        self.dZ2_loc = self.dZ2_full[lo:lo + nl]
-        self.G2 = torch.zeros((nl, Cp), **f32)
+        if self.propagate_first:
+            # the hidden rows themselves are exchanged: they live in this rank's slice of the exchange buffers
+            self.Ht_full, self.He_full = xbuf("Ht", (npad, H)), xbuf("He", (npad, H))
+            self.H1d = self.Ht_full[lo:lo + nl]
+            self.H1 = self.He_full[lo:lo + nl] if (self.share_h1 and dropout > 0) else self.H1d
+            self.T_full = xbuf("T", (npad, H))           # dZ2 W2^T
+            self.T_loc = self.T_full[lo:lo + nl]
+            self.U = torch.zeros((nl, H), **f32)         # A_hat H1d on the own rows
+            self.W2t = torch.zeros((n_classes, H), **f32)
+            self._cs_ws = torch.empty(4096 * H * 4, dtype=torch.uint8, device=dev)
+            self.dZ2_loc = torch.zeros((nl, Cp), **f32)
+            self._h_exchanged = None
+        else:
+            self.H1d = torch.empty((nl, H), **f32)
+            self.H1 = torch.empty((nl, H), **f32) if (self.share_h1 and dropout > 0) else self.H1d
+            self.Pt_full = xbuf("Pt", (npad, Cp))        # projected rows, train forward
+            self.Pt_loc = self.Pt_full[lo:lo + nl]
+            self.Pe_full = xbuf("Pe", (npad, Cp))        # projected rows, eval forward (double buffer)
+            self.Pe_loc = self.Pe_full[lo:lo + nl]
+            self.dZ2_full = xbuf("dZ2", (npad, Cp))
+            self.dZ2_loc = self.dZ2_full[lo:lo + nl]
+            self.G2 = torch.zeros((nl, Cp), **f32)
         self.dZ1_full = xbuf("dZ1", (npad, H))
         self.dZ1_loc = self.dZ1_full[lo:lo + nl]
         self.loss_part = torch.zeros(2, dtype=torch.float64, device=dev)        # train step: sum nll, count (local rows)
@@ -323,7 +344,7 @@ class DistTextGCNTrainer:
         self._w1_mirrored = False
         self._pending_reads = set()
         self.fused_stores = bool(fused_stores and self.px is not None and
-                                 all(self.px.multicast.get(k, 0) for k in ("W1", "Pt", "Pe", "dZ2", "dZ1")))
+                                 all(self.px.multicast.get(k, 0) for k in xshapes if k != "small"))
         self._w1_mirror_ok = not self.hier
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
@@ -428,7 +449,72 @@ class DistTextGCNTrainer:
                 self._exchange(self.W1_full, self.W1_loc, "W1", self._w1_mirrored)
             self.w1_stale = False
 
+    def _forward_propagate_first(self, training: bool) -> None:
+        """Layer 2 as (A_hat H1d) W2 + b2: the hidden rows are exchanged (N x H), the class-wide product stays local."""
+        ops = self.ops
+        self._mark("begin")
+        drop = training and self.p > 0
+        dkw = dict(drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
+                   philox_offset_dev=self.step_dev if drop else None, row_id_offset=self.rank * self.part.n_loc)
+        h = self.H1d if training else self.H1
+        hname, hfull = ("Ht", self.Ht_full) if h is self.H1d else ("He", self.He_full)
+        need_exchange = True
+        if training and self.share_h1 and self._h1_valid:
+            if drop:
+                self._before_write(hname)
+                ops.dropout_apply(self.H1, F=self.H, out=self.H1d, **dkw)
+            else:
+                need_exchange = False          # H1 is H1d and every rank's slice is already in place from the eval forward
+            self._mark("dropout_apply")
+        else:
+            self._gather_w1()
+            self._mark("allgather_W1")
+            self._before_write(hname)
+            self._wide_spmm(self.W1_full, out=h, bias=self.b1, **dkw)
+            self._note_read("W1")
+            self._mark("spmm_wide_fwd")
+        if need_exchange:
+            self._exchange(hfull, h, hname, False)
+        self._mark("allgather_P")
+        ops.spmm(self.shard, hfull, F=self.H, plan=self.plan_z2, out=self.U)
+        self._note_read(hname)
+        ops.project(self.U, self.W2, K=self.H, out=self.Z2, bias=self.b2)
+        self._mark("spmm_narrow_fwd")
+
+    def _train_step_propagate_first(self) -> None:
+        ops = self.ops
+        self._forward_propagate_first(True)
+        ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2_loc,
+                       loss_out=self.loss_buf, workspace=self._nll_ws, partial=self.loss_part)
+        self._mark("masked_nll")
+        drop = self.p > 0
+        dkw = dict(drop_mode=ops.DROP_PHILOX if drop else ops.DROP_NONE, drop_p=self.p, philox_seed=self.seed,
+                   philox_offset_dev=self.step_dev if drop else None, row_id_offset=self.rank * self.part.n_loc)
+        self.W2t.copy_(self.W2.t())
+        self._before_write("T")
+        ops.project(self.dZ2_loc, self.W2t, K=self.C, out=self.T_loc)                 # T = dZ2 W2^T (zero off the train rows)
+        self._exchange(self.T_full, self.T_loc, "T", False)
+        self._mark("allgather_dZ2")
+        self._before_write("dZ1")
+        ops.spmm(self.shard_g2, self.T_full, F=self.H, plan=self.plan_g2, out=self.dZ1_loc, **dkw)   # dZ1 = dropout'(A_hat T)
+        self._note_read("T")
+        self._mark("spmm_narrow_bwd")
+        self._before_write("small")
+        r = ops.dense_bwd(self.dZ2_loc, self.U, self.W2, self.dZ2_loc, H=self.H, n_classes=self.C, want_dz1=False,
+                          workspace=self._db_ws, dW2=self.l_W2, db_out=self.l_b2)      # dW2 = U^T dZ2, db2 = colsum(dZ2)
+        self._db_ws = r["workspace"]
+        ops.colsum(self.dZ1_loc, F=self.H, out=self.l_b1, workspace=self._cs_ws)
+        self._mark("dense_bwd")
+        if not self.hier:
+            self._all_reduce_small()
+            self._mark("allreduce_small_grads")
+        self._exchange(self.dZ1_full, self.dZ1_loc, "dZ1", False)
+        self._mark("allgather_dZ1")
+        self._wide_backward_and_adam()
+
     def _forward(self, training: bool) -> None:
+        if self.propagate_first:
+            return self._forward_propagate_first(training)
         ops = self.ops
         self._mark("begin")
         drop = training and self.p > 0
@@ -462,6 +548,8 @@ class DistTextGCNTrainer:
         self._mark("spmm_narrow_fwd")
 
     def train_step(self) -> None:
+        if self.propagate_first:
+            return self._train_step_propagate_first()
         ops = self.ops
         self._forward(True)
         self._before_write("dZ2")
@@ -494,6 +582,11 @@ class DistTextGCNTrainer:
         elif self.hier:
             self._barrier()                   # publishes the mirrored dZ1 stores (the small all-reduce comes later here)
         self._mark("allgather_dZ1")
+        self._wide_backward_and_adam()
+
+    def _wide_backward_and_adam(self) -> None:
+        """dW1[own rows] = A_hat dZ1 on the shard + Adam on W1 (fused into the epilogue when x = I), Adam on b1 / W2 / b2."""
+        ops = self.ops
         kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, amsgrad=self.amsgrad,
                   step_dev=self.step_dev)
         self._before_write("W1")
@@ -626,7 +719,7 @@ class DistTextGCNTrainer:
         """Bytes each rank RECEIVES per train step (+ the W1 gather that precedes the forward)."""
         P, nl = self.world, self.part.n_loc
         big = (P - 1) * nl * self.H * 4
-        small = (P - 1) * nl * self.Cp * 4
+        small = big if self.propagate_first else (P - 1) * nl * self.Cp * 4
         return 2 * big + 2 * small + 2 * self.n_small_pad * 4
 
 

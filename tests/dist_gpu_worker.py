@@ -24,8 +24,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     worst_all = 0.0
-    for hier in (None, 7):
-        worst_all = max(worst_all, run_against_oracle(rank, world, dev, hier))
+    for hier, classes, hidden in ((None, 6, 64), (7, 6, 64), (None, 21, 16), (7, 21, 16)):     # classes > hidden: propagate-first layer 2
+        worst_all = max(worst_all, run_against_oracle(rank, world, dev, hier, classes, hidden))
     if rank == 0:
         assert worst_all < 2e-5, worst_all
     dist.barrier()
@@ -39,6 +39,15 @@ def main():
     if rank == 0:
         print("DIST_WORKER parity", par, flush=True)
         assert par["cuda_graph"], "the N-rank epoch was not captured in a CUDA graph"
+        assert par["max_rel_err_loss"] < 1e-4 and par["max_rel_err_W2"] < 1e-3 and par["max_rel_err_W1"] < 1e-3, par
+    dist.barrier()
+    # the same check for the propagate-first order (classes > hidden, perlevel_dbpedia.py shapes)
+    shape4 = GraphShape("t4", 900, 701, 15000, 20, 37, 16, dropout=0.5, amsgrad=False, lr=0.02)
+    g4 = make_graph(shape4, seed=8)
+    par = parity_against_single_gpu(g4, shape4, rank, world, dev, seed=5, epochs=6, use_cuda_graph=True, keep_w1_grad=False)
+    if rank == 0:
+        print("DIST_WORKER propagate-first parity", par, flush=True)
+        assert par["cuda_graph"], par
         assert par["max_rel_err_loss"] < 1e-4 and par["max_rel_err_W2"] < 1e-3 and par["max_rel_err_W1"] < 1e-3, par
     dist.barrier()
     # the word-block exchange (dist_bipartite.py) in its shipped configuration on a documents >> words graph
@@ -67,9 +76,9 @@ def main():
     dist.destroy_process_group()
 
 
-def run_against_oracle(rank, world, dev, hier):
+def run_against_oracle(rank, world, dev, hier, classes=6, hidden=64):
     """4 eager epochs (dropout off) of the N-rank trainer against oracle.reference_epoch; x = I or [I | F]."""
-    shape = GraphShape("t", 900, 701, 15000, 20, 6, 64)
+    shape = GraphShape("t", 900, 701, 15000, 20, classes, hidden)
     g = make_graph(shape, seed=3, hierarchy_classes=hier)
     n = int(g.x.shape[0])
     torch.manual_seed(0)
@@ -102,7 +111,7 @@ def run_against_oracle(rank, world, dev, hier):
     if rank == 0:
         for k, v in ref.state_dict().items():
             worst = max(worst, rel_err(params[k], v) / 100)
-        print(f"DIST_WORKER world={world} hier={hier} worst_rel_err={worst:.3e}", flush=True)
+        print(f"DIST_WORKER world={world} hier={hier} classes={classes} hidden={hidden} worst_rel_err={worst:.3e}", flush=True)
     del tr
     dist.barrier()
     return worst

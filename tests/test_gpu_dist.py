@@ -15,17 +15,19 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("hier", [None, 5])
-def test_world_size_one_matches_oracle(cuda, hier):
+@pytest.mark.parametrize("hier,classes,hidden", [(None, 6, 64), (5, 6, 64), (None, 21, 16), (5, 21, 16)])
+def test_world_size_one_matches_oracle(cuda, hier, classes, hidden):
+    """classes > hidden exercises the propagate-first order of layer 2 (hidden rows exchanged instead of class-wide ones)."""
     from pytextgcn_b200.dist import DistTextGCNTrainer
     from pytextgcn_b200.synthetic import make_graph, GraphShape
-    shape = GraphShape("t", 700, 555, 12000, 20, 6, 64)
+    shape = GraphShape("t", 700, 555, 12000, 20, classes, hidden)
     g = make_graph(shape, seed=3, hierarchy_classes=hier)
     n = int(g.x.shape[0])
     torch.manual_seed(0)
     ref = O.OracleGCN(int(g.x.shape[1]), shape.n_classes, n_hidden_gcn=shape.hidden, dropout=0.0)
     init = {k: v.detach().clone() for k, v in ref.state_dict().items()}
     tr = DistTextGCNTrainer(g, shape.n_classes, shape.hidden, 0.0, 0.01, True, 0, 1, cuda, seed=0, init_weights=init)
+    assert tr.propagate_first == (classes > hidden)
     opt = torch.optim.Adam(ref.parameters(), lr=0.01, amsgrad=True)
     for step in range(3):
         out_ref = O.reference_epoch(ref, g, opt)
@@ -35,6 +37,8 @@ def test_world_size_one_matches_oracle(cuda, hier):
         if hier:
             assert rel_err(tr.g_W1[tr.part.n_loc:], ref.layers[0].weight.grad[n:]) < 2e-5 * (step + 1)
         assert rel_err(tr.g_W2, ref.layers[1].weight.grad) < 2e-5 * (step + 1)
+        assert rel_err(tr.g_b1, ref.layers[0].bias.grad) < 2e-5 * (step + 1)
+        assert rel_err(tr.g_b2, ref.layers[1].bias.grad) < 2e-5 * (step + 1)
         tr.eval_step()
         st = tr.epoch_stats()
         assert abs(st["val_loss"] - out_ref[1]) < 1e-4 * max(1, abs(out_ref[1]))
