@@ -47,6 +47,7 @@ __device__ __forceinline__ float load_h(const void* H1d, int h_dtype, int64_t id
 template <int KQ>   // KQ = ceil(H/128) upper bound
 __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParams p) {
   extern __shared__ __align__(16) float smem[];
+  bool mirrored = false;                          // this thread stored to the multicast mapping (fence at the end)
   const int H = p.H, C = p.C;                    // H % 4 == 0 (host pads)
   const int Cp = (C + 3) & ~3;
   float* W2t = smem;                             // [C][H]   transposed weights (h contiguous) when staged
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
         }
         if (p.dz1_dtype == TGCN_F32) {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dZ1) + row * p.lddz1 + 4 * hq) = make_float4(v[0], v[1], v[2], v[3]);
-          if (p.dZ1_mirror && row < p.dZ1_mirror_rows) multimem_st_v4(p.dZ1_mirror + row * p.lddz1 + 4 * hq, v[0], v[1], v[2], v[3]);
+          if (p.dZ1_mirror && row < p.dZ1_mirror_rows) { multimem_st_v4(p.dZ1_mirror + row * p.lddz1 + 4 * hq, v[0], v[1], v[2], v[3]); mirrored = true; }
         } else {
           __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dZ1) + row * p.lddz1 + 4 * hq);
           o[0] = __floats2bfloat162_rn(v[0], v[1]);
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
           for (int i = 0; i < 4; ++i) dbh[k][i] += v[i];
           if (p.dz1_dtype == TGCN_F32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dZ1) + row * p.lddz1 + 4 * hq) = make_float4(v[0], v[1], v[2], v[3]);
-            if (p.dZ1_mirror && row < p.dZ1_mirror_rows) multimem_st_v4(p.dZ1_mirror + row * p.lddz1 + 4 * hq, v[0], v[1], v[2], v[3]);
+            if (p.dZ1_mirror && row < p.dZ1_mirror_rows) { multimem_st_v4(p.dZ1_mirror + row * p.lddz1 + 4 * hq, v[0], v[1], v[2], v[3]); mirrored = true; }
           } else {
             __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dZ1) + row * p.lddz1 + 4 * hq);
             o[0] = __floats2bfloat162_rn(v[0], v[1]);
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(DB_THREADS, 2) k_dense_bwd(const DenseBwdParam
     __syncthreads();
   }
 
-  if (p.dZ1_mirror) __threadfence_system();
+  if (mirrored) __threadfence_system();      // only the threads that stored to the multicast mapping
   // ---- per-CTA partials ----
   float* my_dw = p.part_dW2 + (int64_t)blockIdx.x * H * C;
 #pragma unroll
@@ -405,6 +406,7 @@ constexpr int PR_KC = 32;     // columns of X per shared-memory chunk
 template <int N4>
 __global__ void __launch_bounds__(256) k_project_rows(const ProjParams p) {
   extern __shared__ __align__(16) float smem[];
+  bool mirrored = false;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.y * (4 * N4);                 // first output column of this CTA's column tile
   const int Kp = (p.K + PR_KC - 1) / PR_KC * PR_KC;
@@ -487,12 +489,12 @@ __global__ void __launch_bounds__(256) k_project_rows(const ProjParams p) {
             if (c + 3 < p.M) o.w += __ldg(p.bias + c + 3);
           }
           *reinterpret_cast<float4*>(p.P + row * p.ldp + c) = o;
-          if (p.mirror && row < p.mirror_rows) multimem_st_v4(p.mirror + row * p.ldp + c, o.x, o.y, o.z, o.w);
+          if (p.mirror && row < p.mirror_rows) { multimem_st_v4(p.mirror + row * p.ldp + c, o.x, o.y, o.z, o.w); mirrored = true; }
         }
       }
     }
   }
-  if (p.mirror) __threadfence_system();
+  if (mirrored) __threadfence_system();
 }
 
 template <int N4>

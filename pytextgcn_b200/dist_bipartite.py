@@ -8,7 +8,7 @@ A Text2GraphTransformer graph is bipartite apart from its word-word block (text2
 The row partition of dist.py exchanges all N rows of every operand.  Here every rank owns a block of the WORDS and a
 block of the DOCUMENTS (both dealt in snake order of decreasing row length), and only word rows ever cross ranks:
 
-    own rows of A_hat X  =  main_r @ [ X_words (all-gathered) ; X_own_docs ]          (word rows: WW part only)
+    own rows of A_hat X  =  main_r @ [ X_words (all-gathered) ; X_own_rows ]          (word rows: WW part only)
     word rows, WD part   =  sum over ranks s of  Q_s @ X_docs_of_s                     (Q_s = the columns of WD rank s owns)
 
 so per propagation a rank all-gathers the [V, F] word block and exchanges (all-to-all) the [V, F] partial word rows
@@ -77,8 +77,11 @@ def _csr(n_rows: int, rows: torch.Tensor, cols: torch.Tensor, val: torch.Tensor)
 def shard_bipartite(rowptr: torch.Tensor, colidx: torch.Tensor, val: torch.Tensor, part: BipartitePartition, rank: int):
     """The two CSR pieces of rank `rank` (device-agnostic torch index ops; covered by the CPU tests):
 
-    main: n_loc rows (own words, own documents) x (v_pad + d_loc) columns = [all words in new-id order of their
-          owners ; own documents]; holds every entry of the own rows EXCEPT word-row x document-column ones.
+    main: n_loc rows (own words, own documents) x (v_pad + n_loc) columns = [all words in new-id order of their
+          owners ; the rank's own rows (words, documents)]; holds every entry of the own rows EXCEPT word-row x
+          document-column ones.  Word columns point into the first v_pad positions, document columns into the tail
+          (v_pad + local id), so an operand buffer is [gathered word block ; X_loc] and the kernels that produce X_loc
+          write it in place.
     q:    v_pad rows (all words, ordered by owner rank) x d_loc columns (own documents): the entries A_hat[w, d] of the
           documents this rank owns; q @ X_own_docs is this rank's contribution to every word row.
     Returns ((rowptr, colidx, val) of main, (rowptr, colidx, val) of q)."""
@@ -96,7 +99,7 @@ def shard_bipartite(rowptr: torch.Tensor, colidx: torch.Tensor, val: torch.Tenso
                                   "(text2graph.py:148-170); use the row partition (DistTextGCNTrainer)")
     del rn, cn
     m = (r_rank == rank) & ~(r_word & ~c_word)
-    m_cols = torch.where(c_word[m], c_rank[m] * vl + c_loc[m], vp + c_loc[m] - vl)
+    m_cols = torch.where(c_word[m], c_rank[m] * vl + c_loc[m], vp + c_loc[m])
     main = _csr(nl, r_loc[m], m_cols, val[m])
     q = r_word & ~c_word & (c_rank == rank)
     qq = _csr(vp, r_rank[q] * vl + r_loc[q], c_loc[q] - vl, val[q])
@@ -143,13 +146,13 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
         self.nnz_global = full.nnz
         del full
         nl, vl, dl, vp, H, Cp = part.n_loc, part.v_loc, part.d_loc, part.v_pad, hidden, self.Cp
-        self.shard = GraphCSR(nl, mrp, mci, mv, None, None, n_cols=vp + dl)
+        self.shard = GraphCSR(nl, mrp, mci, mv, None, None, n_cols=vp + nl)
         self.shard._symmetric = True          # only ever used as rows of the symmetric global matrix
         self.qshard = GraphCSR(vp, qrp, qci, qv, None, None, n_cols=dl)
         self.qshard._symmetric = True
         self.plan, self.plan_q = self.shard.plan(), self.qshard.plan()
         self.tc = None
-        auto = tensor_cores is None and self.shard.nnz >= 200_000 and (vp + dl) * ((H + 15) // 16 * 16) * 8 <= (104 << 20)
+        auto = tensor_cores is None and self.shard.nnz >= 200_000 and (vp + nl) * ((H + 15) // 16 * 16) * 8 <= (104 << 20)
         if (tensor_cores or auto) and 64 <= H <= 256:
             from .tc_plan import build_tc_plan
             tc = build_tc_plan(self.shard, min_density=tc_min_density, width=H,
@@ -160,8 +163,9 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
         self.overlap = bool(overlap) and world > 1
         n_small = H + H * n_classes + n_classes
         self.n_small, self.n_small_pad = n_small, (n_small + 3) // 4 * 4
-        # Exchanged buffers.  OP*: operands [all words (v_pad rows, rank-major) ; own documents]: W1, dZ1, P of the train
-        # and of the eval forward (dZ2 reuses the train buffer's document tail: its word rows are zero and never read).
+        # Exchanged buffers.  OP*: operands [all words (v_pad rows, rank-major) ; this rank's own rows X_loc (n_loc)]: W1,
+        # dZ1, P of the train and of the eval forward.  The tail IS the local operand (W1_loc, dZ1_loc, P_loc are views
+        # of it): its producer writes it in place and the main SpMM reads the document columns from there, no copies.
         # SL*: partial word rows, slot s = rank s's contribution to MY words (two hidden-wide ones: the forward and the
         # backward propagation alternate, so a peer never overwrites the slots a slower rank is still adding).
         # With symmetric memory (NVLink peer mappings + NVSwitch multicast) the exchange is fused into the kernels: the
@@ -170,7 +174,7 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
         # producers from consumers.  Otherwise: NCCL all_gather_into_tensor / all_to_all_single.
         # The peer / NCCL decision is collective (see DistTextGCNTrainer).
         self.exchange, self.exchange_error, self.px = "nccl word-block", None, None
-        xshapes = {"OPW": (vp + dl, H), "OPD": (vp + dl, H), "OPCt": (vp + dl, Cp), "OPCe": (vp + dl, Cp),
+        xshapes = {"OPW": (vp + nl, H), "OPD": (vp + nl, H), "OPCt": (vp + nl, Cp), "OPCe": (vp + nl, Cp),
                    "SLf": (world, vl, H), "SLb": (world, vl, H), "SLc": (world, vl, Cp), "small": (world, self.n_small_pad)}
         xb: Dict[str, torch.Tensor] = {}
         if world > 1 and exchange == "peer":
@@ -213,7 +217,8 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
             W1, b1, W2, b2 = (init_weights[k].detach().cpu().float() for k in
                               ("layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias"))
         lo = rank * nl
-        self.W1_loc = part.to_new(W1[:n])[lo:lo + nl].to(dev).contiguous()
+        self.W1_loc = self.X["OPW"][vp:]                        # authoritative copy of this rank's W1 rows
+        self.W1_loc.copy_(part.to_new(W1[:n])[lo:lo + nl].to(dev))
         self.W1_cat = None
         self.b1, self.W2, self.b2 = b1.to(dev), W2.to(dev).contiguous(), b2.to(dev)
         self.small_slots = self.X["small"]                      # slot r = rank r's partial sums (peer mode)
@@ -236,11 +241,12 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
         self.share_h1 = bool(share_h1)
         self.H1 = torch.empty((nl, H), **f32) if (self.share_h1 and dropout > 0) else self.H1d
         self._h1_valid = False
-        self.P_loc = torch.zeros((nl, Cp), **f32)
+        self.Pt_loc, self.Pe_loc = self.X["OPCt"][vp:], self.X["OPCe"][vp:]
         self.Z2 = torch.zeros((nl, Cp), **f32)
-        self.dZ2_loc = torch.zeros((nl, Cp), **f32)
+        self.OPZ = torch.zeros((vp + nl, Cp), **f32)             # operand of the class-wide backward (word part never read)
+        self.dZ2_loc = self.OPZ[vp:]
         self.G2 = torch.zeros((nl, Cp), **f32)
-        self.dZ1_loc = torch.zeros((nl, H), **f32)
+        self.dZ1_loc = self.X["OPD"][vp:]
         self.loss_part = torch.zeros(2, dtype=torch.float64, device=dev)
         self.loss_part_val = torch.zeros(2, dtype=torch.float64, device=dev)
         self.loss_buf = torch.zeros(2, **f32)
@@ -263,8 +269,8 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
         self.restrict_rows = True
         rows_loc = part.to_new(masks, False)[lo:lo + nl].to(dev)
         self.plan_z2 = self.shard.plan_for_rows(rows_loc, self.plan)
-        col_train = torch.zeros(vp + dl, dtype=torch.bool, device=dev)
-        col_train[vp:] = self.train_mask[vl:]
+        col_train = torch.zeros(vp + nl, dtype=torch.bool, device=dev)
+        col_train[vp:] = self.train_mask
         self.shard_g2 = self.shard.select_columns(col_train)
         is_word_row = torch.arange(nl, device=dev) < vl
         nonempty = (self.shard_g2.rowptr[1:] - self.shard_g2.rowptr[:-1]) > 0
@@ -288,14 +294,15 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
         OP = self.X[op]
         return self.px.multicast[op] + self.rank * self.part.v_loc * OP.stride(0) * 4, self.part.v_loc
 
-    def _propagate(self, X_loc: torch.Tensor, F: int, op: str, sl: Optional[str], graph: GraphCSR, plan,
+    def _propagate(self, OP: torch.Tensor, F: int, op: Optional[str], sl: Optional[str], graph: GraphCSR, plan,
                    qgraph: Optional[GraphCSR], qplan, gather_words: bool, words_mirrored: bool = False, tc=None, **kw):
-        """epi(rows of A_hat X owned by this rank).  X_loc = [own words ; own documents] rows of X; `op` names the
-        operand buffer, `sl` the slot buffer of the partial word rows (None: word rows not needed).
-        words_mirrored: the kernel that produced X_loc already stored its word rows into every rank's `op`."""
+        """epi(rows of A_hat X owned by this rank).  OP = operand buffer [word block ; X_loc] whose tail already holds
+        this rank's rows of X; `op` names it when it is an exchanged buffer, `sl` the slot buffer of the partial word
+        rows (None: word rows not needed).
+        words_mirrored: the kernel that produced X_loc already stored its word rows into every rank's word block."""
         ops, part, r = self.ops, self.part, self.rank
         vl, vp = part.v_loc, part.v_pad
-        OP = self.X[op]
+        X_loc = OP[vp:]
         peer = self.px is not None
         work = None
         if gather_words and not words_mirrored:
@@ -312,17 +319,16 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
                 work = self.dist.all_gather_into_tensor(OP[:vp], X_loc[:vl], async_op=self.overlap)
             else:
                 OP[:vl].copy_(X_loc[:vl])
-        OP[vp:].copy_(X_loc[vl:])
         raw = None
         if qgraph is not None:
             # this rank's contribution to EVERY word row, from its own documents
             if peer:
                 self._before_write(sl)
-                ops.spmm(qgraph, OP[vp:], F=F, plan=qplan, out=self.X[sl].view(vp, F),
+                ops.spmm(qgraph, X_loc[vl:], F=F, plan=qplan, out=self.X[sl].view(vp, F),
                          scatter=dict(bases=self.bases[sl], rows=vl, row0=r * vl))       # all-to-all in the epilogue's stores
                 raw = self.X[sl]
             else:
-                ops.spmm(qgraph, OP[vp:], F=F, plan=qplan, out=self.Q[F])               # runs while the word block is gathered
+                ops.spmm(qgraph, X_loc[vl:], F=F, plan=qplan, out=self.Q[F])             # runs while the word block is gathered
                 if work is not None and self.overlap:
                     work.wait()
                     work = None
@@ -340,7 +346,7 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
             out = ops.spmm_hybrid(tc, OP, F=F, plan=tc.remainder.plan(), raw_slots=raw, **kw)
         else:
             out = ops.spmm(graph, OP, F=F, plan=plan, raw_slots=raw, **kw)
-        if gather_words:
+        if gather_words and op is not None:
             self._note_read(op)
         if qgraph is not None and sl is not None:
             self._note_read(sl)
@@ -360,19 +366,19 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
             h, fused_drop = (self.H1, True) if drop else (self.H1d, False)
         else:
             h = self.H1d if training else self.H1
-            self._propagate(self.W1_loc, self.H, "OPW", "SLf", self.shard, self.plan, self.qshard, self.plan_q, True,
+            self._propagate(self.X["OPW"], self.H, "OPW", "SLf", self.shard, self.plan, self.qshard, self.plan_q, True,
                             words_mirrored=self._w1_words_ready, tc=self.tc, out=h, bias=self.b1, **dkw)
             self._mark("spmm_wide_fwd")
-        opc = "OPCt" if training else "OPCe"
+        opc, P_loc = ("OPCt", self.Pt_loc) if training else ("OPCe", self.Pe_loc)
         mir, mrows = self._mirror_of(opc)
         if mir is not None:
             self._before_write(opc)
         if fused_drop:
-            ops.project(h, self.W2, K=self.H, out=self.P_loc, dropped_out=self.H1d, mirror=mir, mirror_rows=mrows, **dkw)
+            ops.project(h, self.W2, K=self.H, out=P_loc, dropped_out=self.H1d, mirror=mir, mirror_rows=mrows, **dkw)
         else:
-            ops.project(h, self.W2, K=self.H, out=self.P_loc, mirror=mir, mirror_rows=mrows)
+            ops.project(h, self.W2, K=self.H, out=P_loc, mirror=mir, mirror_rows=mrows)
         self._mark("project")
-        self._propagate(self.P_loc, self.Cp, opc, None, self.shard, self.plan_z2, None, None, True,
+        self._propagate(self.X[opc], self.Cp, opc, None, self.shard, self.plan_z2, None, None, True,
                         words_mirrored=mir is not None, out=self.Z2, bias=self.b2)
         self._mark("spmm_narrow_fwd")
 
@@ -382,7 +388,7 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
         ops.masked_nll(self.Z2, self.C, self.y, self.train_mask, self.n_train, want_grad=True, dZ=self.dZ2_loc,
                        loss_out=self.loss_buf, workspace=self._nll_ws, partial=self.loss_part)
         self._mark("masked_nll")
-        self._propagate(self.dZ2_loc, self.Cp, "OPCt", "SLc", self.shard_g2, self.plan_g2, self.qshard_g2, self.plan_q_g2,
+        self._propagate(self.OPZ, self.Cp, None, "SLc", self.shard_g2, self.plan_g2, self.qshard_g2, self.plan_q_g2,
                         False, out=self.G2)
         self._mark("spmm_narrow_bwd")
         drop = self.p > 0
@@ -406,7 +412,7 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
         wmir, wrows = self._mirror_of("OPW")
         if wmir is not None:
             self._before_write("OPW")
-        self._propagate(self.dZ1_loc, self.H, "OPD", "SLb", self.shard, self.plan, self.qshard, self.plan_q, True,
+        self._propagate(self.X["OPD"], self.H, "OPD", "SLb", self.shard, self.plan, self.qshard, self.plan_q, True,
                         words_mirrored=mir is not None, tc=self.tc, out=self.g_W1, want_out=self.keep_w1_grad,
                         adam=dict(param=self.W1_loc, exp_avg=self.st[0][0], exp_avg_sq=self.st[0][1], max_exp_avg_sq=self.st[0][2],
                                   hyper=self.adam_hyper, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,

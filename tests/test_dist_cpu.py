@@ -168,7 +168,7 @@ def test_bipartite_partition_is_a_bijection_with_words_first(world):
 
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_bipartite_sharded_spmm_equals_global(world):
-    """main_r @ [all words ; own docs] + sum_s (q_s @ docs of s)[words of r] == rows of A_hat X owned by r."""
+    """main_r @ [all words ; own rows] + sum_s (q_s @ docs of s)[words of r] == rows of A_hat X owned by r."""
     g = make_graph(SHAPE, seed=1)
     n, rowptr, col, val = _global_csr(g)
     part = BipartitePartition(rowptr[1:] - rowptr[:-1], g.n_vocab, world)
@@ -182,8 +182,8 @@ def test_bipartite_sharded_spmm_equals_global(world):
     partial = [_local_spmm(*q, Bn[r, vl:]) for r, (m, q) in enumerate(shards)]               # [vp, 8] per rank
     outs = []
     for r, (m, q) in enumerate(shards):
-        assert m[0].numel() == nl + 1 and int(m[1].max()) < vp + part.d_loc
-        o = _local_spmm(*m, torch.cat([words, Bn[r, vl:]]))
+        assert m[0].numel() == nl + 1 and int(m[1].max()) < vp + nl
+        o = _local_spmm(*m, torch.cat([words, Bn[r]]))
         for s in range(world):                              # the all-to-all: slot s = rank s's partial rows of my words
             o[:vl] += partial[s][r * vl:(r + 1) * vl]
         outs.append(o)
@@ -212,10 +212,10 @@ def _bip_worker(rank, world, port, q):
         X = torch.randn(n, 6, dtype=torch.float64)
         X_loc = part.to_new(X)[lo:lo + nl]
         # the collective sequence of BipartiteTextGCNTrainer._propagate
-        OP = torch.zeros(vp + part.d_loc, 6, dtype=torch.float64)
-        dist.all_gather_into_tensor(OP[:vp], X_loc[:vl].contiguous())
-        OP[vp:] = X_loc[vl:]
-        Q = _local_spmm(*qq, OP[vp:]).contiguous()
+        OP = torch.zeros(vp + nl, 6, dtype=torch.float64)       # [gathered word block ; this rank's own rows]
+        OP[vp:] = X_loc
+        dist.all_gather_into_tensor(OP[:vp], OP[vp:vp + vl].contiguous())
+        Q = _local_spmm(*qq, OP[vp + vl:]).contiguous()
         SL = torch.zeros(world, vl, 6, dtype=torch.float64)
         recv = list(SL.unbind(0))
         for d in range(world):      # all_to_all_single on NCCL; gloo has no all-to-all, so one gather per destination
