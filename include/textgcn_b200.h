@@ -295,6 +295,10 @@ int tgcn_adam_step_small(int32_t n_tensors, float* const* params, const float* c
  * every store with multimem.st -- compute and exchange in ONE kernel, only the barrier remains.  tgcn_sum_slots adds `n_slots`
  * vectors in slot order (the all-reduce of the small gradients: every rank pushes its vector into
  * slot `rank` of every peer, then sums the slots locally -- bit-identical on all ranks).
+ * Word-block partition (documents >> words; pytextgcn_b200/dist_bipartite.py): the same mirrors restricted to the
+ * producer's first `*_mirror_rows` rows (its words) are the all-gather of the word block, and tgcn_spmm with
+ * c_scatter_bases stores every output row into the slot buffer of the rank that owns it (the all-to-all of the partial
+ * word rows, plain peer stores); the consuming tgcn_spmm adds the slots through raw_in.
  */
 int tgcn_peer_push(const void* src, void* const* peer_bases_host, int32_t world, int32_t rank, int64_t bytes,
                    int64_t dst_offset_bytes, void* multicast_base, void* stream);
