@@ -244,3 +244,20 @@ def test_two_rank_gloo_word_block_exchange_matches_global():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res < 1e-12
+
+
+def test_partition_choice_rule():
+    """auto = word-block when x = I and the word block + partial word rows (2 V rows) are at most 3/4 of the N rows the
+    row partition moves; [I | F] inputs and word-heavy graphs keep the row partition."""
+    from types import SimpleNamespace
+    from pytextgcn_b200.dist import choose_partition
+
+    def g(n_vocab, n_docs, extra_cols=0):
+        n = n_vocab + n_docs
+        return SimpleNamespace(x=torch.empty((n, n + extra_cols), device="meta"), n_vocab=n_vocab)
+    assert choose_partition(g(42757, 18846)) == "row"            # 20NG: words outnumber documents
+    assert choose_partition(g(200_000, 1_000_000)) == "words"    # scale configuration
+    assert choose_partition(g(20_000, 50_000)) == "words"        # Amazon-shape
+    assert choose_partition(g(10_000, 337_739, extra_cols=9)) == "row"   # per-level input [I | onehot(parent)]
+    assert choose_partition(g(10_000, 337_739)) == "words"
+    assert choose_partition(g(200_000, 1_000_000), "row") == "row" and choose_partition(g(42757, 18846), "words") == "words"
