@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 /* Counts the co-occurrences of all windows, computes the PMI edge list and keeps it behind an opaque handle.
- * Returns NULL on bad input (null X, non-positive sizes, a token id >= n_vocab or < -1).
+ * Returns NULL on bad input (null X, non-positive sizes, a token id >= n_vocab or < -1) or when memory runs out.
  * n_threads <= 0: all hardware threads.  *n_edges_out = number of DIRECTED edges (2 per unordered pair);
  * *n_windows_out (optional) = number of sliding windows (the denominator of the probabilities, graphbuilder.pyx:150). */
 void* tgcn_ww_build(const int32_t* X, int64_t n_docs, int64_t seq_len, int64_t n_vocab, int64_t window_size,

@@ -152,7 +152,7 @@ extern "C" {
 
 // Builds the edge list; returns an opaque handle (NULL on bad input), *n_edges_out = number of DIRECTED edges.
 void* tgcn_ww_build(const int32_t* X, int64_t n_docs, int64_t seq_len, int64_t n_vocab, int64_t window_size,
-                    int32_t n_threads, int64_t* n_edges_out, uint64_t* n_windows_out) {
+                    int32_t n_threads, int64_t* n_edges_out, uint64_t* n_windows_out) try {
   if (!X || n_docs < 0 || seq_len <= 0 || n_vocab <= 0 || window_size <= 0 || !n_edges_out) return nullptr;
   const uint64_t V = (uint64_t)n_vocab;
   int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
@@ -163,15 +163,18 @@ void* tgcn_ww_build(const int32_t* X, int64_t n_docs, int64_t seq_len, int64_t n
   std::vector<uint64_t> nwin((size_t)T, 0);
   std::vector<int> bad((size_t)T, 0);
   std::vector<std::vector<uint64_t>> samples((size_t)T);
+  std::atomic<bool> failed(false);
   std::vector<std::thread> th;
   const int64_t per = (n_docs + T - 1) / T;
   for (int t = 0; t < T; ++t) {
     const int64_t d0 = std::min<int64_t>(n_docs, t * per), d1 = std::min<int64_t>(n_docs, d0 + per);
     th.emplace_back([&, t, d0, d1]() {
-      count_docs(X, d0, d1, seq_len, window_size, V, tabs[t], nwin[t], bad[t]);
-      size_t seen = 0;                                        // sample of this table's keys for the range splitters below
-      for (const PairTable::Slot& sl : tabs[t].slots)
-        if (sl.key != PairTable::EMPTY && (seen++ % 61) == 0) samples[t].push_back(sl.key);
+      try {
+        count_docs(X, d0, d1, seq_len, window_size, V, tabs[t], nwin[t], bad[t]);
+        size_t seen = 0;                                      // sample of this table's keys for the range splitters below
+        for (const PairTable::Slot& sl : tabs[t].slots)
+          if (sl.key != PairTable::EMPTY && (seen++ % 61) == 0) samples[t].push_back(sl.key);
+      } catch (...) { failed = true; }                        // out of memory: reported as NULL, never thrown across the C ABI
     });
   }
   for (auto& t : th) t.join();
@@ -182,6 +185,7 @@ void* tgcn_ww_build(const int32_t* X, int64_t n_docs, int64_t seq_len, int64_t n
     t_start = now;
   };
   lap("count pairs");
+  if (failed) return nullptr;
   for (int t = 0; t < T; ++t) if (bad[t]) return nullptr;    // token id outside [0, n_vocab)
   uint64_t n_windows = 0;
   for (uint64_t v : nwin) n_windows += v;
@@ -206,7 +210,9 @@ void* tgcn_ww_build(const int32_t* X, int64_t n_docs, int64_t seq_len, int64_t n
     std::atomic<int> next(0);
     std::vector<std::thread> ws;
     const int W = std::min(T, n_tasks);
-    for (int k = 0; k < W; ++k) ws.emplace_back([&]() { for (int q; (q = next.fetch_add(1)) < n_tasks;) fn(q); });
+    for (int k = 0; k < W; ++k) ws.emplace_back([&]() {
+      try { for (int q; (q = next.fetch_add(1)) < n_tasks;) fn(q); } catch (...) { failed = true; }
+    });
     for (auto& x : ws) x.join();
   };
   run_parallel(T, [&](int t) {
@@ -271,11 +277,14 @@ void* tgcn_ww_build(const int32_t* X, int64_t n_docs, int64_t seq_len, int64_t n
     res->w[r] = std::move(wv);
   });
   lap("pmi");
+  if (failed) { delete res; return nullptr; }
   size_t n_e = 0;
   for (int r = 0; r < NR; ++r) n_e += res->w[r].size();
   *n_edges_out = (int64_t)n_e;
   if (n_windows_out) *n_windows_out = n_windows;
   return res;
+} catch (...) {                                               // allocation failure on the calling thread
+  return nullptr;
 }
 
 int tgcn_ww_fetch(void* handle, int32_t* coo_out, float* w_out) {
