@@ -126,6 +126,79 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _pf_worker(rank, world, port, q):
+    """The collective sequence of DistTextGCNTrainer's propagate-first order (classes > hidden): the exchanged operands
+    are the hidden rows and dZ2 W2^T (N x H), the class-wide products stay local."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        shape = GraphShape("t", 300, 257, 5000, 14, 23, 8)          # 23 classes > 8 hidden units
+        g = make_graph(shape, seed=2)
+        n, rowptr, col, val = _global_csr(g)
+        H, C = shape.hidden, shape.n_classes
+        part = RowPartition(rowptr[1:] - rowptr[:-1], world)
+        rp, ci, v = shard_csr(rowptr, col, val, part, rank)
+        nl, lo = part.n_loc, rank * part.n_loc
+        W1 = torch.randn(n, H, dtype=torch.float64) * 0.2
+        b1 = torch.randn(H, dtype=torch.float64) * 0.1
+        W2 = torch.randn(H, C, dtype=torch.float64) * 0.2
+        b2 = torch.randn(C, dtype=torch.float64) * 0.1
+        y = part.to_new(g.y)[lo:lo + nl]
+        tm = part.to_new(g.train_mask, False)[lo:lo + nl]
+        n_train = int(g.train_mask.sum())
+
+        def gather(loc):
+            full = torch.zeros(part.n_pad, loc.shape[1], dtype=torch.float64)
+            dist.all_gather_into_tensor(full, loc.contiguous())
+            return full
+        H1 = _local_spmm(rp, ci, v, gather(part.to_new(W1)[lo:lo + nl])) + b1          # own rows of A_hat W1 + b1
+        U = _local_spmm(rp, ci, v, gather(H1))                                           # A_hat H1 (hidden-wide exchange)
+        Z2 = U @ W2 + b2
+        logp = torch.log_softmax(Z2, dim=1)
+        dZ2 = torch.zeros_like(Z2)
+        rows = torch.nonzero(tm).view(-1)
+        dZ2[rows] = torch.exp(logp[rows])
+        dZ2[rows, y[rows]] -= 1.0
+        dZ2 /= n_train
+        loss_part = -logp[rows, y[rows]].sum().view(1)
+        dZ1 = _local_spmm(rp, ci, v, gather(dZ2 @ W2.T))                                 # A_hat (dZ2 W2^T)
+        small = torch.cat([dZ1.sum(0), (U.T @ dZ2).reshape(-1), dZ2.sum(0)])             # db1, dW2 = U^T dZ2, db2
+        dist.all_reduce(small)
+        dist.all_reduce(loss_part)
+        gW1_full = gather(_local_spmm(rp, ci, v, gather(dZ1)))
+        if rank == 0:
+            Wr = [W1.clone().requires_grad_(), W2.clone().requires_grad_()]
+            br = [b1.clone().requires_grad_(), b2.clone().requires_grad_()]
+            z = O.gcn_forward(g.x.double(), g.edge_index, g.edge_attr.double(), Wr, br)
+            loss = O.masked_cross_entropy(z, g.y, g.train_mask)
+            loss.backward()
+            q.put(dict(loss=abs(loss_part.item() / n_train - loss.item()),
+                       gW1=rel_err(part.to_old(gW1_full), Wr[0].grad),
+                       db1=rel_err(small[:H], br[0].grad), dW2=rel_err(small[H:H + H * C].view(H, C), Wr[1].grad),
+                       db2=rel_err(small[H + H * C:], br[1].grad)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_propagate_first_sequence_matches_oracle():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_pf_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res["loss"] < 1e-6
+    for k in ("gW1", "db1", "dW2", "db2"):
+        assert res[k] < 1e-5, (k, res[k])
+
+
 def test_two_rank_gloo_collective_sequence_matches_oracle():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
