@@ -46,19 +46,26 @@ def _stop_words() -> Optional[List[str]]:
         return sorted(ENGLISH_STOP_WORDS)
 
 
+def _encode_chunk(docs, vocabulary, max_len):
+    """Token ids of every document of the chunk: tokenise, lower-case each token, keep in-vocabulary tokens, truncate."""
+    sl = slice(None) if max_len is None else slice(max_len)
+    get = vocabulary.get
+    return [[i for i in map(get, [m.lower() for m in _TOKEN.findall(doc)]) if i is not None][sl] for doc in docs]
+
+
 def _encode_input(X, n_jobs, vocabulary, verbose, n_docs, max_len):
     """text2graph.py:20-46: tokenise, lower-case, keep in-vocabulary tokens, truncate to max_len,
-    pad with -1 to the longest document."""
-    sl = slice(None) if max_len is None else slice(max_len)
-
-    def enc(doc):
-        return [vocabulary[t] for t in (m.lower() for m in _TOKEN.findall(doc)) if t in vocabulary][sl]
-
-    if n_jobs and n_jobs > 1 and len(X) > 2000:
+    pad with -1 to the longest document.  The reference hands every document to joblib as its own task, which pickles
+    the vocabulary with each batch; here one process encodes ~10 k documents per second, so worker processes are used
+    only for large corpora, one contiguous chunk per worker (the vocabulary crosses the process boundary n_jobs times)."""
+    if n_jobs and n_jobs > 1 and len(X) > 50000:
         import joblib as jl
-        docs = jl.Parallel(n_jobs=n_jobs)(jl.delayed(enc)(d) for d in X)
+        k = min(int(n_jobs), 64)
+        bounds = [len(X) * i // k for i in range(k + 1)]
+        parts = jl.Parallel(n_jobs=k)(jl.delayed(_encode_chunk)(X[bounds[i]:bounds[i + 1]], vocabulary, max_len) for i in range(k))
+        docs = [d for part in parts for d in part]
     else:
-        docs = [enc(d) for d in X]
+        docs = _encode_chunk(X, vocabulary, max_len)
     max_sent_len = max(map(len, docs)) if docs else 0
     max_sent_len = max(max_sent_len, 1)
     out = np.full((n_docs, max_sent_len), -1, dtype=np.int32)
