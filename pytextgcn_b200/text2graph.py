@@ -46,6 +46,9 @@ def _stop_words() -> Optional[List[str]]:
         return sorted(ENGLISH_STOP_WORDS)
 
 
+_PARALLEL_MIN_DOCS = 50000      # below this a single process is faster than starting workers
+
+
 def _encode_chunk(docs, vocabulary, max_len):
     """Token ids of every document of the chunk: tokenise, lower-case each token, keep in-vocabulary tokens, truncate."""
     sl = slice(None) if max_len is None else slice(max_len)
@@ -58,7 +61,7 @@ def _encode_input(X, n_jobs, vocabulary, verbose, n_docs, max_len):
     pad with -1 to the longest document.  The reference hands every document to joblib as its own task, which pickles
     the vocabulary with each batch; here one process encodes ~10 k documents per second, so worker processes are used
     only for large corpora, one contiguous chunk per worker (the vocabulary crosses the process boundary n_jobs times)."""
-    if n_jobs and n_jobs > 1 and len(X) > 50000:
+    if n_jobs and n_jobs > 1 and len(X) > _PARALLEL_MIN_DOCS:
         import joblib as jl
         k = min(int(n_jobs), 64)
         bounds = [len(X) * i // k for i in range(k + 1)]

@@ -101,3 +101,17 @@ def test_reference_import_surface():
     assert textgcn.Text2GraphTransformer is Text2GraphTransformer and c2 is compute_word_word_edges
     m = GCN(10, 3, n_hidden_gcn=100, dropout=0.7)
     assert [k for k, _ in m.named_parameters()] == ["layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias"]
+
+
+def test_token_encoding_in_worker_processes_matches_single_process(monkeypatch):
+    """Large corpora are encoded by n_jobs worker processes, one contiguous chunk each: same token matrix."""
+    import numpy as np
+    from pytextgcn_b200 import text2graph as T
+    rng = np.random.default_rng(3)
+    vocab = {f"w{i}": i for i in range(50)}
+    docs = [" ".join(f"W{j}" if j % 7 == 0 else f"w{j}" for j in rng.integers(0, 60, size=rng.integers(0, 30))) for _ in range(101)]
+    one, l1 = T._encode_input(docs, 1, vocab, 0, len(docs), 12)
+    monkeypatch.setattr(T, "_PARALLEL_MIN_DOCS", 10)
+    many, l2 = T._encode_input(docs, 3, vocab, 0, len(docs), 12)
+    assert l1 == l2 and np.array_equal(one, many)
+    assert one.max() < 50 and (one >= -1).all()
