@@ -781,6 +781,8 @@ def choose_partition(g, requested: str = "auto") -> str:
 def make_dist_trainer(g, shape, rank: int, world: int, dev: torch.device, partition: str = "auto", **kw):
     if choose_partition(g, partition) == "words":
         from .dist_bipartite import BipartiteTextGCNTrainer
+        if not kw.get("fuse_adam", True):          # a row-partition switch (bench --no-fuse-adam); the word-block trainer has no unfused form
+            kw = {k: v for k, v in kw.items() if k != "fuse_adam"}
         return BipartiteTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad, rank, world, dev, **kw)
     return DistTextGCNTrainer(g, shape.n_classes, shape.hidden, shape.dropout, shape.lr, shape.amsgrad, rank, world, dev, **kw)
 

@@ -115,13 +115,15 @@ class BipartiteTextGCNTrainer(DistTextGCNTrainer):
                  graph: Optional[GraphCSR] = None, init_weights: Optional[Dict[str, torch.Tensor]] = None,
                  use_cuda_graph: bool = False, keep_w1_grad: bool = True, share_h1: bool = True,
                  tensor_cores: Optional[bool] = None, tc_min_density: float = 0.05, overlap: bool = True,
-                 exchange: str = "peer", fused_stores: bool = True, **_unused):
+                 exchange: str = "peer", fused_stores: bool = True, fuse_adam: bool = True):
         import torch.distributed as dist
         from . import ops
         from .graph import upload_graph
         from .models import decode_features
         self.dist, self.ops = dist, ops
         self.rank, self.world, self.dev = rank, world, dev
+        if not fuse_adam:
+            raise NotImplementedError("the word-block trainer always runs Adam on W1 in the SpMM epilogue")
         n = int(g.x.shape[0])
         feat = decode_features(g.x, getattr(g, "n_vocab", None))
         if feat is None or feat.Fdoc is not None:
